@@ -1,0 +1,332 @@
+"""Mesh containers, IO and synthetic generators for the spectral-correspondence path.
+
+The reference consumes ``vtkPolyData`` objects and touches only four accessors on the hot
+path (``GetNumberOfPoints/GetPoint/GetNumberOfCells/GetCell``; reference
+``pyfocusr/graph.py:58-62,155-164``) plus ``GetPointData()`` for optional scalars
+(``graph.py:88-104``).  VTK is not installable in this image, so :class:`PolyData` is a
+duck-typed stand-in exposing the same accessors (so the *unmodified* reference can consume it
+in the oracle harness) together with flat ``points``/``tris`` arrays that the CUDA path
+uploads directly.
+
+Generators implement the synthetic inputs of BASELINE.json ``configs[2..4]`` (SURVEY.md
+§8d): class-I geodesic icospheres (``10*nu**2 + 2`` vertices) and perturbed ellipsoids.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+__all__ = [
+    "PolyData",
+    "read_vtk_mesh",
+    "mesh_arrays",
+    "icosphere",
+    "perturbed_ellipsoid",
+    "ellipsoid_pair",
+]
+
+
+class _Edge:
+    __slots__ = ("_a", "_b")
+
+    def __init__(self, a, b):
+        self._a = a
+        self._b = b
+
+    def GetPointId(self, i):
+        return self._a if i == 0 else self._b
+
+
+class _Cell:
+    __slots__ = ("_ids",)
+
+    def __init__(self, ids):
+        self._ids = ids
+
+    def GetNumberOfEdges(self):
+        return len(self._ids)
+
+    def GetNumberOfPoints(self):
+        return len(self._ids)
+
+    def GetPointId(self, i):
+        return int(self._ids[i])
+
+    def GetEdge(self, j):
+        # VTK polygon edge order: (0,1), (1,2), ..., (nv-1,0)
+        n = len(self._ids)
+        return _Edge(int(self._ids[j]), int(self._ids[(j + 1) % n]))
+
+
+class _Array:
+    def __init__(self, name, values):
+        self._name = name
+        self.values = np.ascontiguousarray(values)
+
+    def GetName(self):
+        return self._name
+
+    # numpy_support.vtk_to_numpy stub in the oracle harness is np.asarray
+    def __array__(self, dtype=None, copy=None):
+        return self.values if dtype is None else self.values.astype(dtype)
+
+
+class _PointData:
+    def __init__(self, arrays):
+        self._arrays = arrays
+
+    def GetNumberOfArrays(self):
+        return len(self._arrays)
+
+    def GetArray(self, idx):
+        return self._arrays[idx]
+
+    def GetScalars(self):
+        return self._arrays[0] if self._arrays else None
+
+
+class PolyData:
+    """Triangle surface mesh: ``points (N,3) float64`` and ``tris (F,3) int32``.
+
+    Exposes the vtkPolyData accessors used by the reference (``graph.py:58-62,155-164``).
+    """
+
+    def __init__(self, points, tris, point_scalars=None):
+        self.points = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        self.tris = np.ascontiguousarray(tris, dtype=np.int32).reshape(-1, 3)
+        self.point_scalars = dict(point_scalars or {})
+
+    # --- vtkPolyData duck-typing -------------------------------------------------
+    def GetNumberOfPoints(self):
+        return self.points.shape[0]
+
+    def GetPoint(self, i):
+        p = self.points[i]
+        return (float(p[0]), float(p[1]), float(p[2]))
+
+    def GetNumberOfCells(self):
+        return self.tris.shape[0]
+
+    def GetCell(self, i):
+        return _Cell(self.tris[i])
+
+    def GetPointData(self):
+        return _PointData([_Array(k, v) for k, v in self.point_scalars.items()])
+
+    def copy(self):
+        return PolyData(self.points.copy(), self.tris.copy(), dict(self.point_scalars))
+
+
+def read_vtk_mesh(path_to_file):
+    """Legacy-ASCII ``DATASET POLYDATA`` reader (replaces ``vtk_functions.py:5-9``).
+
+    Handles the sections present in the shipped data files (``POINTS``, ``POLYGONS``,
+    ``POINT_DATA``/``SCALARS``); all polygons must be triangles.
+    """
+    with open(path_to_file, "r") as f:
+        tokens = f.read().split("\n")
+    header = tokens[:4]
+    if len(header) < 4 or "ASCII" not in header[2].upper():
+        raise ValueError("only legacy ASCII VTK files are supported: %s" % path_to_file)
+    words = " ".join(tokens[4:]).split()
+    pos = 0
+    points = tris = None
+    scalars = {}
+    n_points = 0
+    while pos < len(words):
+        w = words[pos].upper()
+        if w == "DATASET":
+            if words[pos + 1].upper() != "POLYDATA":
+                raise ValueError("DATASET must be POLYDATA")
+            pos += 2
+        elif w == "POINTS":
+            n_points = int(words[pos + 1])
+            pos += 3
+            points = np.array(words[pos : pos + 3 * n_points], dtype=np.float64).reshape(-1, 3)
+            pos += 3 * n_points
+        elif w == "POLYGONS":
+            n_cells, size = int(words[pos + 1]), int(words[pos + 2])
+            pos += 3
+            raw = np.array(words[pos : pos + size], dtype=np.int64)
+            pos += size
+            if size != 4 * n_cells or not np.all(raw[0::4] == 3):
+                raise ValueError("only triangle meshes are supported")
+            tris = raw.reshape(-1, 4)[:, 1:].astype(np.int32)
+        elif w == "POINT_DATA":
+            pos += 2
+        elif w == "SCALARS":
+            name = words[pos + 1]
+            pos += 3
+            # optional numComp
+            if words[pos].upper() != "LOOKUP_TABLE":
+                pos += 1
+            pos += 2  # LOOKUP_TABLE <name>
+            scalars[name] = np.array(words[pos : pos + n_points], dtype=np.float64)
+            pos += n_points
+        else:
+            pos += 1
+    if points is None or tris is None:
+        raise ValueError("file has no POINTS/POLYGONS section: %s" % path_to_file)
+    return PolyData(points, tris, scalars)
+
+
+def mesh_arrays(vtk_mesh):
+    """Return ``(points f64 (N,3), tris i32 (F,3))`` for a PolyData-like object.
+
+    Fast paths: our own :class:`PolyData`; real ``vtkPolyData`` through numpy_support when
+    VTK is importable.  Otherwise the generic accessor walk the reference itself performs
+    (``graph.py:58-62,155-164``).
+    """
+    if isinstance(vtk_mesh, PolyData):
+        return vtk_mesh.points, vtk_mesh.tris
+    try:  # real VTK, zero python loops
+        from vtk.util.numpy_support import vtk_to_numpy  # type: ignore
+
+        pts = np.ascontiguousarray(vtk_to_numpy(vtk_mesh.GetPoints().GetData()), dtype=np.float64)
+        polys = vtk_mesh.GetPolys()
+        conn = vtk_to_numpy(polys.GetConnectivityArray())
+        offs = vtk_to_numpy(polys.GetOffsetsArray())
+        if not np.all(np.diff(offs) == 3):
+            raise ValueError("only triangle meshes are supported")
+        return pts, np.ascontiguousarray(conn.reshape(-1, 3), dtype=np.int32)
+    except (ImportError, AttributeError):
+        pass
+    n = vtk_mesh.GetNumberOfPoints()
+    pts = np.zeros((n, 3))
+    for i in range(n):
+        pts[i, :] = vtk_mesh.GetPoint(i)
+    nc = vtk_mesh.GetNumberOfCells()
+    tris = np.zeros((nc, 3), dtype=np.int32)
+    for c in range(nc):
+        cell = vtk_mesh.GetCell(c)
+        if cell.GetNumberOfEdges() != 3:
+            raise ValueError("only triangle meshes are supported")
+        for e in range(3):
+            tris[c, e] = cell.GetEdge(e).GetPointId(0)
+    return pts, tris
+
+
+# ---------------------------------------------------------------------------------------
+# synthetic meshes
+# ---------------------------------------------------------------------------------------
+def _icosahedron():
+    t = (1.0 + 5.0**0.5) / 2.0
+    v = np.array(
+        [
+            [-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0],
+            [0, -1, t], [0, 1, t], [0, -1, -t], [0, 1, -t],
+            [t, 0, -1], [t, 0, 1], [-t, 0, -1], [-t, 0, 1],
+        ],
+        dtype=np.float64,
+    )
+    v /= np.linalg.norm(v, axis=1)[:, None]
+    f = np.array(
+        [
+            [0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11],
+            [1, 5, 9], [5, 11, 4], [11, 10, 2], [10, 7, 6], [7, 1, 8],
+            [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8], [3, 8, 9],
+            [4, 9, 5], [2, 4, 11], [6, 2, 10], [8, 6, 7], [9, 8, 1],
+        ],
+        dtype=np.int64,
+    )
+    return v, f
+
+
+def icosphere(nu, radius=1.0):
+    """Class-I geodesic icosphere of frequency ``nu``: ``10*nu**2+2`` vertices, ``20*nu**2`` faces.
+
+    Vertices are emitted face by face in lattice order (first occurrence wins for points
+    shared between icosahedron faces), which keeps graph neighbours close in index — the
+    locality the CSR SpMM kernel's L1/shared-memory staging relies on.  Triangles are
+    consistently oriented (outward), so the reference's directed edge fill
+    (``graph.py:158-178``) produces a symmetric adjacency.
+    """
+    nu = int(nu)
+    if nu < 1:
+        raise ValueError("nu must be >= 1")
+    v0, f0 = _icosahedron()
+    # integer barycentric lattice on one face: (i, j) with i + j <= nu
+    ii, jj = np.meshgrid(np.arange(nu + 1), np.arange(nu + 1), indexing="ij")
+    keep = (ii + jj) <= nu
+    li = ii[keep]
+    lj = jj[keep]
+    lk = nu - li - lj
+    n_loc = li.size
+    loc_id = -np.ones((nu + 1, nu + 1), dtype=np.int64)
+    loc_id[li, lj] = np.arange(n_loc)
+    # local triangles (two orientations of lattice cells)
+    a_i, a_j = np.meshgrid(np.arange(nu), np.arange(nu), indexing="ij")
+    up = (a_i + a_j) <= nu - 1
+    ui, uj = a_i[up], a_j[up]
+    tri_up = np.stack([loc_id[ui, uj], loc_id[ui + 1, uj], loc_id[ui, uj + 1]], axis=1)
+    dn = (a_i + a_j) <= nu - 2
+    di, dj = a_i[dn], a_j[dn]
+    tri_dn = np.stack([loc_id[di + 1, dj], loc_id[di + 1, dj + 1], loc_id[di, dj + 1]], axis=1)
+    tri_loc = np.concatenate([tri_up, tri_dn], axis=0)
+
+    # exact integer keys for lattice points so shared edge/corner points merge exactly:
+    # key = sorted tuple of (icosahedron vertex id, weight) with non-zero weight.
+    all_pts = []
+    all_keys = []
+    for f in f0:
+        A, B, C = v0[f[0]], v0[f[1]], v0[f[2]]
+        # point = (lk*A + li*B + lj*C)/nu  (lattice index (li,lj) -> weights (lk, li, lj))
+        p = (lk[:, None] * A[None] + li[:, None] * B[None] + lj[:, None] * C[None]) / float(nu)
+        all_pts.append(p)
+        w = np.stack([lk, li, lj], axis=1)  # weights for vertices f[0], f[1], f[2]
+        ids = np.broadcast_to(f[None, :], w.shape)
+        # encode up to three (id, weight) pairs, zero-weight pairs dropped, sorted by id
+        code = np.where(w > 0, ids * (nu + 1) + w, -1)
+        code = np.sort(code, axis=1)  # -1 entries first
+        base = 12 * (nu + 1) + 1
+        key = (code[:, 0] + 1) * base * base + (code[:, 1] + 1) * base + (code[:, 2] + 1)
+        all_keys.append(key)
+    pts = np.concatenate(all_pts, axis=0)
+    keys = np.concatenate(all_keys, axis=0)
+    _, first_idx, inverse = np.unique(keys, return_index=True, return_inverse=True)
+    # rank unique points by first occurrence to keep face-major lattice order
+    order = np.argsort(first_idx, kind="stable")
+    rank = np.empty_like(order)
+    rank[order] = np.arange(order.size)
+    vid = rank[inverse]  # global vertex id for every (face, local) point
+    verts = pts[first_idx[order]]
+    verts /= np.linalg.norm(verts, axis=1)[:, None]
+    tris = np.concatenate([vid[tri_loc + k * n_loc] for k in range(20)], axis=0)
+    # orientation: make all faces outward (centroid . normal > 0)
+    p0, p1, p2 = verts[tris[:, 0]], verts[tris[:, 1]], verts[tris[:, 2]]
+    nrm = np.cross(p1 - p0, p2 - p0)
+    flip = np.einsum("ij,ij->i", nrm, p0 + p1 + p2) < 0
+    tris[flip] = tris[flip][:, [0, 2, 1]]
+    assert verts.shape[0] == 10 * nu * nu + 2 and tris.shape[0] == 20 * nu * nu
+    return PolyData(verts * float(radius), tris.astype(np.int32))
+
+
+def perturbed_ellipsoid(nu=39, seed=0, semi_axes=(43.0, 32.0, 33.0), bump_amp=0.05, jitter=0.02,
+                        base=None):
+    """Perturbed ellipsoid of SURVEY.md §8d config 3.
+
+    Icosphere of frequency ``nu`` (39 -> 15 212 vertices) scaled to ``semi_axes``; radial
+    perturbation = sum of 6 random smooth bumps (total amplitude <= ``bump_amp``); vertex
+    jitter ``N(0, (jitter * mean_edge)^2)``.  ``base`` may carry a precomputed unit icosphere.
+    """
+    sph = base if base is not None else icosphere(nu)
+    rng = np.random.RandomState(int(seed))
+    u = sph.points / np.linalg.norm(sph.points, axis=1)[:, None]
+    centers = rng.normal(size=(6, 3))
+    centers /= np.linalg.norm(centers, axis=1)[:, None]
+    amps = rng.uniform(-1.0, 1.0, size=6) * (bump_amp / 6.0)
+    widths = rng.uniform(0.5, 1.2, size=6)
+    radial = np.ones(u.shape[0])
+    for c, a, w in zip(centers, amps, widths):
+        ang2 = np.sum((u - c[None]) ** 2, axis=1)  # chord^2 on unit sphere
+        radial += a * np.exp(-ang2 / (2.0 * w * w))
+    pts = u * radial[:, None] * np.asarray(semi_axes, dtype=np.float64)[None]
+    t = sph.tris
+    mean_edge = np.mean(np.linalg.norm(pts[t[:, 0]] - pts[t[:, 1]], axis=1))
+    pts = pts + rng.normal(scale=jitter * mean_edge, size=pts.shape)
+    return PolyData(pts, t.copy())
+
+
+def ellipsoid_pair(i, nu=39, base=None):
+    """Pair ``i`` of config 3: target seed ``2i``, source seed ``2i+1``."""
+    base = base if base is not None else icosphere(nu)
+    return (perturbed_ellipsoid(nu, 2 * i, base=base), perturbed_ellipsoid(nu, 2 * i + 1, base=base))
