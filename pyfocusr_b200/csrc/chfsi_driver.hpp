@@ -1,0 +1,352 @@
+// Host driver of the block eigen-solver that replaces scipy `eigs(L, k, sigma=1e-10, which="LM",
+// ncv=4k)` + the retry logic of `recursive_eig` (reference graph.py:357-389) on the B200.
+//
+// Method: Chebyshev-filtered subspace iteration (ChFSI) on L = D~^-1 (D - A) itself, no
+// factorisation.  One outer iteration =
+//     Z = (D - A) X                       (CSR SpMM, GPU)
+//     G = X^T g X,  H = X^T h Z           (tall-skinny Gram, GPU, FP64 tensor cores)
+//     Rayleigh-Ritz on (G, H) -> W, theta (b x b: GPU warp-Jacobi if A is symmetric,
+//                                          host complex-Schur if not, see nonsym_host.hpp)
+//     X <- X W, residuals                 (GPU)
+//     X <- p_m(L) X                       (m fused SpMM+axpby Chebyshev steps, GPU: the hot loop)
+// with (g, h) = (D~, 1) for a symmetric adjacency (L is self-adjoint in the D~ inner product, so
+// H is symmetric) and (1, D~^-1) otherwise (Euclidean projection, H general).
+// The filter damps [a, beta], a = largest Ritz value of the block, beta = 2 (Gershgorin bound of
+// the random-walk Laplacian).  Zero-degree rows (unreferenced vertices) are exact null vectors
+// e_i; they are pinned to zero in X (an invariant of every step) and accounted for analytically
+// in the retry count, reproducing `k_final` of SURVEY.md section 7.3-2.
+//
+// This header is pure C++ (no CUDA types): the N-sized work is behind the `Backend` concept.
+// The product backend is CudaBackend (eigs.cu); tests/hostsim has a plain-loop backend used
+// only to exercise this driver logic on machines without a GPU.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <vector>
+
+#include "dense_small.h"
+#include "nonsym_host.hpp"
+
+namespace fb {
+
+enum SolveStatus {
+  SOLVE_OK = 0,
+  SOLVE_NOT_CONVERGED = 1,
+  SOLVE_BLOCK_TOO_SMALL = 2,
+  SOLVE_BREAKDOWN = 3,
+  SOLVE_OUTPUT_TOO_SMALL = 4
+};
+
+struct SolveParams {
+  int k0;            // `k` of recursive_eig (graph.py:245: n_spectral_features + 1)
+  int n_needed;      // `n_k_needed`
+  int k_buffer;      // `k_buffer`
+  double min_eig;    // MIN_EIG_VAL = 1e-10 (graph.py:369)
+  double tol;        // residual ||L v - theta v||_2 / ||v||_2 of every returned pair
+  int max_outer;     // outer (Rayleigh-Ritz) iterations
+  double amp_target; // filter amplification of the slowest wanted pair per outer iteration
+  int max_degree;    // cap of the Chebyshev degree per outer iteration
+  double beta;       // upper bound of the spectrum
+  int ldv;           // capacity (columns) of the output arrays
+};
+
+struct MeshResult {
+  int status;
+  int n_out;       // eigenpairs written (theta > min_eig among the k_final smallest)
+  int k_final;     // the k the reference's recursion would have ended at
+  int outer_iters;
+  int total_degree;
+  int block;
+  double max_residual;
+};
+
+inline void cheb_table(double a, double a_low, double beta, int m, double* alpha, double* gamma,
+                       double* center) {
+  const double e = 0.5 * (beta - a), c = 0.5 * (beta + a);
+  double sigma = e / (a_low - c);
+  const double sigma1 = sigma;
+  alpha[0] = sigma1 / e;
+  gamma[0] = 0.0;
+  for (int s = 1; s < m; ++s) {
+    const double sigma2 = 1.0 / (2.0 / sigma1 - sigma);
+    alpha[s] = 2.0 * sigma2 / e;
+    gamma[s] = sigma * sigma2;
+    sigma = sigma2;
+  }
+  *center = c;
+}
+
+inline int cheb_degree(double a, double theta_k, double beta, double amp, int max_degree) {
+  const double e = 0.5 * (beta - a);
+  const double eps = std::max((a - theta_k) / e, 1e-14);
+  const double rate = std::acosh(1.0 + eps);
+  double m = std::ceil(std::log(2.0 * amp) / rate);
+  if (!(m < (double)max_degree)) m = max_degree;
+  return std::max(4, (int)m);
+}
+
+// Non-symmetric Rayleigh-Ritz on the host.  g = X^T X, h = X^T L X (b x b row-major, both
+// overwritten).  Produces w (b x b; columns = real basis of Ritz vectors: the `n_low` real Ritz
+// values below `cut` first, ascending, then the rest with complex pairs as (Re, Im)) and theta
+// (real parts, same order).  Returns #clamped Cholesky pivots, or -1 if the QR iteration failed.
+inline int rr_nonsym_host(double* g, double* h, int b, double cut, double* w, double* theta,
+                          int* n_low_out) {
+  SeqPar par;
+  std::vector<double> diag0(b);
+  const int bad = cholesky_upper(g, diag0.data(), b, par);
+  // h <- R^-T h R^-1 without symmetrising
+  for (int i = 0; i < b; ++i) {
+    const double dinv = 1.0 / g[i * b + i];
+    for (int j = 0; j < b; ++j) {
+      double v = h[i * b + j];
+      for (int k = 0; k < i; ++k) v -= g[k * b + i] * h[k * b + j];
+      h[i * b + j] = v * dinv;
+    }
+  }
+  for (int j = 0; j < b; ++j) {
+    const double dinv = 1.0 / g[j * b + j];
+    for (int i = 0; i < b; ++i) {
+      double v = h[i * b + j];
+      for (int k = 0; k < j; ++k) v -= h[i * b + k] * g[k * b + j];
+      h[i * b + j] = v * dinv;
+    }
+  }
+  std::vector<cplx> ev(b), evec((size_t)b * b);
+  if (eig_general(h, b, ev.data(), evec.data()) != 0) return -1;
+
+  std::vector<int> low, rest;
+  std::vector<char> is_real(b);
+  for (int i = 0; i < b; ++i) {
+    const double mag = std::abs(ev[i]);
+    is_real[i] = std::fabs(ev[i].imag()) <= std::max(1e-8 * mag, 1e-13);
+    if (is_real[i] && ev[i].real() <= cut)
+      low.push_back(i);
+    else
+      rest.push_back(i);
+  }
+  std::sort(low.begin(), low.end(), [&](int x, int y) { return ev[x].real() < ev[y].real(); });
+  std::sort(rest.begin(), rest.end(), [&](int x, int y) {
+    if (ev[x].real() != ev[y].real()) return ev[x].real() < ev[y].real();
+    return ev[x].imag() > ev[y].imag();
+  });
+  std::vector<double> yr((size_t)b * b, 0.0);
+  int col = 0;
+  auto put = [&](int idx, bool imag_part) {
+    double nrm = 0.0;
+    for (int i = 0; i < b; ++i) {
+      const double v = imag_part ? evec[i * b + idx].imag() : evec[i * b + idx].real();
+      yr[i * b + col] = v;
+      nrm += v * v;
+    }
+    nrm = std::sqrt(nrm);
+    if (nrm > 0.0)
+      for (int i = 0; i < b; ++i) yr[i * b + col] /= nrm;
+    theta[col] = ev[idx].real();
+    ++col;
+  };
+  for (int idx : low) put(idx, false);
+  *n_low_out = col;
+  std::vector<char> used(b, 0);
+  for (int idx : low) used[idx] = 1;
+  for (int idx : rest) {
+    if (used[idx] || col >= b) continue;
+    used[idx] = 1;
+    if (is_real[idx]) {
+      put(idx, false);
+    } else {
+      // conjugate partner: closest unused eigenvalue to conj(ev[idx])
+      int partner = -1;
+      double best = 1e300;
+      for (int j : rest)
+        if (!used[j] && !is_real[j]) {
+          const double d = std::abs(ev[j] - std::conj(ev[idx]));
+          if (d < best) {
+            best = d;
+            partner = j;
+          }
+        }
+      put(idx, false);
+      if (col < b && partner >= 0 && best <= 1e-6 * std::abs(ev[idx])) {
+        used[partner] = 1;
+        put(idx, true);
+      }
+    }
+  }
+  // numerical leftovers (unpaired complex values): fill with remaining real parts
+  for (int idx = 0; idx < b && col < b; ++idx)
+    if (!used[idx]) {
+      used[idx] = 1;
+      put(idx, false);
+    }
+  // w = R^-1 yr
+  for (int j = 0; j < b; ++j)
+    for (int i = b - 1; i >= 0; --i) {
+      double v = yr[i * b + j];
+      for (int k = i + 1; k < b; ++k) v -= g[i * b + k] * w[k * b + j];
+      w[i * b + j] = v / g[i * b + i];
+    }
+  return bad;
+}
+
+// Retry contract of recursive_eig (graph.py:374-379) given the pinned operator's Ritz values
+// (ascending) and `zr` analytically known zero eigenvalues.  Returns the number `kp` of pinned
+// pairs that must be converged, and k_final through *k_final; kp > n_avail means "need a bigger
+// block".
+inline int retry_contract(const double* theta, int n_avail, int zr, const SolveParams& p,
+                          int* k_final) {
+  int k_cur = p.k0;
+  for (;;) {
+    const int kp = k_cur - std::min(zr, k_cur);
+    if (kp > n_avail) {
+      *k_final = k_cur;
+      return kp;
+    }
+    int good = 0;
+    for (int j = 0; j < kp; ++j) good += theta[j] > p.min_eig;
+    if (good >= p.n_needed) {
+      *k_final = k_cur;
+      return kp;
+    }
+    k_cur += p.k_buffer + p.n_needed;
+  }
+}
+
+template <class BE>
+int chfsi_solve(BE& be, const SolveParams& p, MeshResult* out) {
+  const int M = be.n_meshes();
+  const int B = be.block();
+  const bool sym = be.symmetric();
+  const int guard = sym ? 2 : 4;  // Ritz values kept between the wanted set and the filter edge
+  std::vector<double> theta((size_t)M * B), res((size_t)M * B);
+  std::vector<double> a_prev(M, -1.0), last_a(M, 0.5 * p.beta), last_alow(M, 0.0);
+  std::vector<int> done(M, 0), n_low(M, B), flags(M), sel((size_t)M * B), n_out(M), last_kp(M, 1);
+  std::vector<double> gh, wbuf, thbuf;
+  if (!sym) {
+    gh.resize((size_t)2 * M * B * B);
+    wbuf.resize((size_t)M * B * B);
+    thbuf.resize((size_t)M * B);
+  }
+  for (int m = 0; m < M; ++m) {
+    out[m].status = SOLVE_NOT_CONVERGED;
+    out[m].n_out = 0;
+    out[m].k_final = p.k0;
+    out[m].outer_iters = 0;
+    out[m].total_degree = 0;
+    out[m].block = B;
+    out[m].max_residual = -1.0;
+  }
+  std::vector<double> alpha, gamma, center(M);
+  be.init_block();
+  int n_done = 0;
+  int rc = SOLVE_OK;
+  for (int outer = 0; outer < p.max_outer && n_done < M; ++outer) {
+    be.apply_DmA();
+    be.gram();
+    if (sym) {
+      be.rr_sym();
+    } else {
+      be.get_GH(gh.data(), gh.data() + (size_t)M * B * B);
+      for (int m = 0; m < M; ++m) {
+        const double cut = a_prev[m] < 0.0 ? 0.5 * p.beta : 2.0 * a_prev[m];
+        const int r = rr_nonsym_host(gh.data() + (size_t)m * B * B,
+                                     gh.data() + (size_t)(M + m) * B * B, B, cut,
+                                     wbuf.data() + (size_t)m * B * B, thbuf.data() + (size_t)m * B,
+                                     &n_low[m]);
+        if (r < 0 && !done[m]) {
+          out[m].status = SOLVE_BREAKDOWN;
+          done[m] = 1;
+          ++n_done;
+          rc = SOLVE_BREAKDOWN;
+        }
+      }
+      be.set_W_theta(wbuf.data(), thbuf.data());
+    }
+    be.rotate_and_residual();
+    be.get_theta_res(theta.data(), res.data());
+
+    bool any_flag = false;
+    for (int m = 0; m < M; ++m) {
+      flags[m] = 0;
+      if (done[m]) continue;
+      const double* th = &theta[(size_t)m * B];
+      const double* rs = &res[(size_t)m * B];
+      out[m].outer_iters = outer + 1;
+      const int n_avail = (sym ? B : n_low[m]) - guard;
+      int k_final = p.k0;
+      const int kp = retry_contract(th, std::max(n_avail, 0), be.zero_rows(m), p, &k_final);
+      if (kp > n_avail || !(th[0] == th[0])) {
+        out[m].status = (th[0] == th[0]) ? SOLVE_BLOCK_TOO_SMALL : SOLVE_BREAKDOWN;
+        out[m].k_final = k_final;
+        done[m] = 1;
+        ++n_done;
+        rc = std::max(rc, out[m].status);
+        continue;
+      }
+      last_kp[m] = std::max(kp, 1);
+      double worst = 0.0;
+      for (int j = 0; j < kp; ++j) worst = std::max(worst, rs[j]);
+      out[m].max_residual = worst;
+      if (worst <= p.tol) {
+        int cnt = 0;
+        for (int j = 0; j < kp; ++j)
+          if (th[j] > p.min_eig) sel[(size_t)m * B + cnt++] = j;
+        for (int j = cnt; j < B; ++j) sel[(size_t)m * B + j] = -1;
+        out[m].k_final = k_final;
+        out[m].n_out = cnt;
+        if (cnt > p.ldv) {
+          out[m].status = SOLVE_OUTPUT_TOO_SMALL;
+          rc = std::max(rc, (int)SOLVE_OUTPUT_TOO_SMALL);
+        } else {
+          out[m].status = SOLVE_OK;
+          n_out[m] = cnt;
+          flags[m] = 1;
+          any_flag = true;
+        }
+        done[m] = 1;
+        ++n_done;
+      }
+    }
+    if (any_flag) be.finalize(flags.data(), sel.data(), n_out.data());
+    if (n_done >= M) break;
+
+    // --- next filter: per-mesh interval, one common degree
+    int deg = 0;
+    for (int m = 0; m < M; ++m) {
+      if (done[m]) continue;
+      const double* th = &theta[(size_t)m * B];
+      const int top = (sym ? B : n_low[m]) - 1;
+      double a = th[top];
+      if (!(a < p.beta)) a = 0.5 * p.beta;
+      if (!(a > 0.0)) a = 1e-3 * p.beta;
+      const int kp = last_kp[m];
+      const double thk = th[std::max(0, std::min(kp, top) - 1)];
+      if (outer >= 3 && (a - thk) <= 1e-3 * a) {
+        // the wanted set touches the filter edge (a multiplet cut by the block): more columns needed
+        out[m].status = SOLVE_BLOCK_TOO_SMALL;
+        done[m] = 1;
+        ++n_done;
+        rc = std::max(rc, (int)SOLVE_BLOCK_TOO_SMALL);
+        continue;
+      }
+      last_a[m] = a;
+      last_alow[m] = std::min(th[0], 0.0);
+      a_prev[m] = a;
+      deg = std::max(deg, cheb_degree(a, thk, p.beta, p.amp_target, p.max_degree));
+    }
+    if (n_done >= M) break;
+    alpha.resize((size_t)M * deg);
+    gamma.resize((size_t)M * deg);
+    for (int m = 0; m < M; ++m)
+      cheb_table(last_a[m], last_alow[m], p.beta, deg, &alpha[(size_t)m * deg],
+                 &gamma[(size_t)m * deg], &center[m]);
+    be.filter(deg, alpha.data(), gamma.data(), center.data());
+    for (int m = 0; m < M; ++m)
+      if (!done[m]) out[m].total_degree += deg;
+  }
+  for (int m = 0; m < M; ++m)
+    if (!done[m]) rc = std::max(rc, (int)SOLVE_NOT_CONVERGED);
+  return rc;
+}
+
+}  // namespace fb

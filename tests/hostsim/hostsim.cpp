@@ -1,0 +1,243 @@
+// TEST DOUBLE -- never shipped, never loaded by pyfocusr_b200.
+//
+// Plain-loop implementation of the `Backend` concept of pyfocusr_b200/csrc/chfsi_driver.hpp so the
+// solver's host logic (filter bounds, degree schedule, retry contract, symmetric warp-Jacobi code
+// path in its sequential instantiation, non-symmetric complex-Schur path) can be exercised by
+// `pytest -m "not gpu"` on a machine without a GPU.  The product backend is CudaBackend in
+// pyfocusr_b200/csrc/eigs.cu; nothing in the product links or calls this file.
+//
+// Build: tests/hostsim/build.sh  (g++ -O2 -ffp-contract=off -shared -fPIC)
+#include <cstring>
+#include <vector>
+
+#include "../../pyfocusr_b200/csrc/chfsi_driver.hpp"
+#include "../../pyfocusr_b200/csrc/rowops.h"
+
+namespace {
+
+struct HostBackend {
+  const int* rp;
+  const int* cols;
+  const double* w;
+  const double* deg;
+  const double* dinv;
+  const double* pts;
+  const int* off;
+  const int* zr;
+  int N, M, B;
+  bool sym;
+  double* out_vals;
+  double* out_vecs;
+  int ldv;
+  std::vector<double> X, Y, Xn, Z, G, H, W, theta, res;
+
+  int n_meshes() const { return M; }
+  int block() const { return B; }
+  bool symmetric() const { return sym; }
+  int zero_rows(int m) const { return zr[m]; }
+
+  void init_block() {
+    X.assign((size_t)N * B, 0.0);
+    Y = X;
+    Xn = X;
+    Z = X;
+    G.assign((size_t)M * B * B, 0.0);
+    H = G;
+    W = G;
+    theta.assign((size_t)M * B, 0.0);
+    res = theta;
+    for (int m = 0; m < M; ++m) {
+      double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+      for (int i = off[m]; i < off[m + 1]; ++i)
+        for (int a = 0; a < 3; ++a) {
+          lo[a] = std::min(lo[a], pts[3 * i + a]);
+          hi[a] = std::max(hi[a], pts[3 * i + a]);
+        }
+      double scale = 0.0;
+      for (int a = 0; a < 3; ++a) scale = std::max(scale, 0.5 * (hi[a] - lo[a]));
+      if (!(scale > 0.0)) scale = 1.0;
+      for (int i = off[m]; i < off[m + 1]; ++i) {
+        if (deg[i] == 0.0) continue;
+        const double x = (pts[3 * i] - 0.5 * (lo[0] + hi[0])) / scale;
+        const double y = (pts[3 * i + 1] - 0.5 * (lo[1] + hi[1])) / scale;
+        const double z = (pts[3 * i + 2] - 0.5 * (lo[2] + hi[2])) / scale;
+        for (int c = 0; c < B; ++c)
+          X[(size_t)i * B + c] = fb::start_block_value(c, x, y, z, (uint32_t)(i - off[m]), 1u);
+      }
+    }
+  }
+  void spmm(const std::vector<double>& in, int i, double* acc) const {
+    for (int c = 0; c < B; ++c) acc[c] = 0.0;
+    for (int p = rp[i]; p < rp[i + 1]; ++p) {
+      const double* row = &in[(size_t)cols[p] * B];
+      for (int c = 0; c < B; ++c) acc[c] += w[p] * row[c];
+    }
+  }
+  void apply_DmA() {
+    std::vector<double> acc(B);
+    for (int i = 0; i < N; ++i) {
+      spmm(X, i, acc.data());
+      for (int c = 0; c < B; ++c) Z[(size_t)i * B + c] = deg[i] * X[(size_t)i * B + c] - acc[c];
+    }
+  }
+  void gram() {
+    std::fill(G.begin(), G.end(), 0.0);
+    std::fill(H.begin(), H.end(), 0.0);
+    for (int m = 0; m < M; ++m)
+      for (int i = off[m]; i < off[m + 1]; ++i) {
+        const double gw = sym ? deg[i] + 1e-8 : 1.0;
+        const double hw = sym ? 1.0 : dinv[i];
+        const double* x = &X[(size_t)i * B];
+        const double* z = &Z[(size_t)i * B];
+        for (int p = 0; p < B; ++p)
+          for (int q = 0; q < B; ++q) {
+            G[((size_t)m * B + p) * B + q] += x[p] * gw * x[q];
+            H[((size_t)m * B + p) * B + q] += x[p] * hw * z[q];
+          }
+      }
+  }
+  int rr_sym() {
+    fb::SeqPar par;
+    std::vector<double> y((size_t)B * B);
+    std::vector<int> rank(B);
+    int worst = 0;
+    for (int m = 0; m < M; ++m) {
+      double* g = &G[(size_t)m * B * B];
+      double* h = &H[(size_t)m * B * B];
+      worst |= fb::rayleigh_ritz_sym(g, h, y.data(), &W[(size_t)m * B * B], &theta[(size_t)m * B],
+                                     rank.data(), B, par);
+    }
+    return worst;
+  }
+  void get_GH(double* g, double* h) {
+    std::memcpy(g, G.data(), G.size() * sizeof(double));
+    std::memcpy(h, H.data(), H.size() * sizeof(double));
+  }
+  void set_W_theta(const double* wv, const double* th) {
+    std::memcpy(W.data(), wv, W.size() * sizeof(double));
+    std::memcpy(theta.data(), th, theta.size() * sizeof(double));
+  }
+  void rotate_and_residual() {
+    std::vector<double> xr(B), zr_(B), num((size_t)M * B, 0.0), den((size_t)M * B, 0.0);
+    for (int m = 0; m < M; ++m) {
+      const double* wm = &W[(size_t)m * B * B];
+      for (int i = off[m]; i < off[m + 1]; ++i) {
+        double* x = &X[(size_t)i * B];
+        const double* z = &Z[(size_t)i * B];
+        for (int j = 0; j < B; ++j) {
+          double a = 0.0, b2 = 0.0;
+          for (int k = 0; k < B; ++k) {
+            a += x[k] * wm[k * B + j];
+            b2 += z[k] * wm[k * B + j];
+          }
+          xr[j] = a;
+          zr_[j] = b2;
+        }
+        for (int j = 0; j < B; ++j) {
+          x[j] = xr[j];
+          const double r = dinv[i] * zr_[j] - theta[(size_t)m * B + j] * xr[j];
+          num[(size_t)m * B + j] += r * r;
+          den[(size_t)m * B + j] += xr[j] * xr[j];
+        }
+      }
+      for (int j = 0; j < B; ++j)
+        res[(size_t)m * B + j] = std::sqrt(num[(size_t)m * B + j] / den[(size_t)m * B + j]);
+    }
+  }
+  void get_theta_res(double* th, double* rs) {
+    std::memcpy(th, theta.data(), theta.size() * sizeof(double));
+    std::memcpy(rs, res.data(), res.size() * sizeof(double));
+  }
+  void filter(int deg_m, const double* alpha, const double* gamma, const double* center) {
+    std::vector<double> acc(B);
+    Y = X;  // Y = current, X = previous
+    for (int s = 0; s < deg_m; ++s) {
+      for (int m = 0; m < M; ++m) {
+        const double al = alpha[(size_t)m * deg_m + s], ga = gamma[(size_t)m * deg_m + s], c = center[m];
+        for (int i = off[m]; i < off[m + 1]; ++i) {
+          spmm(Y, i, acc.data());
+          for (int k = 0; k < B; ++k) {
+            const double y = Y[(size_t)i * B + k];
+            const double ly = dinv[i] * (deg[i] * y - acc[k]);
+            Xn[(size_t)i * B + k] = al * (ly - c * y) - ga * X[(size_t)i * B + k];
+          }
+        }
+      }
+      X.swap(Y);   // X <- old Y
+      Y.swap(Xn);  // Y <- new
+    }
+    X = Y;
+  }
+  void finalize(const int* flags, const int* sel, const int* n_out) {
+    for (int m = 0; m < M; ++m) {
+      if (!flags[m]) continue;
+      for (int j = 0; j < n_out[m]; ++j) {
+        const int c = sel[(size_t)m * B + j];
+        double ss = 0.0, best = -1.0, bestv = 0.0;
+        for (int i = off[m]; i < off[m + 1]; ++i) {
+          const double v = X[(size_t)i * B + c];
+          ss += v * v;
+          if (std::fabs(v) > best) {
+            best = std::fabs(v);
+            bestv = v;
+          }
+        }
+        const double sc = (bestv < 0.0 ? -1.0 : 1.0) / std::sqrt(ss);
+        for (int i = off[m]; i < off[m + 1]; ++i) out_vecs[(size_t)i * ldv + j] = X[(size_t)i * B + c] * sc;
+        out_vals[(size_t)m * ldv + j] = theta[(size_t)m * B + c];
+      }
+    }
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+// result_i: per mesh [status, n_out, k_final, outer_iters, total_degree, block]; result_d: [max_residual]
+int hostsim_eigs(const int* rp, const int* cols, const double* w, const double* deg, const double* dinv,
+                 const double* pts, int n_rows, const int* off, int n_meshes, int symmetric,
+                 const int* zero_rows, int block, int k0, int n_needed, int k_buffer, double min_eig,
+                 double tol, int max_outer, double amp_target, int max_degree, double beta, int ldv,
+                 double* eig_vals, double* eig_vecs, int* result_i, double* result_d) {
+  HostBackend be;
+  be.rp = rp; be.cols = cols; be.w = w; be.deg = deg; be.dinv = dinv; be.pts = pts; be.off = off;
+  be.zr = zero_rows; be.N = n_rows; be.M = n_meshes; be.B = block; be.sym = symmetric != 0;
+  be.out_vals = eig_vals; be.out_vecs = eig_vecs; be.ldv = ldv;
+  fb::SolveParams p;
+  p.k0 = k0; p.n_needed = n_needed; p.k_buffer = k_buffer; p.min_eig = min_eig; p.tol = tol;
+  p.max_outer = max_outer; p.amp_target = amp_target; p.max_degree = max_degree; p.beta = beta; p.ldv = ldv;
+  std::vector<fb::MeshResult> r(n_meshes);
+  const int rc = fb::chfsi_solve(be, p, r.data());
+  for (int m = 0; m < n_meshes; ++m) {
+    int* ri = result_i + 6 * m;
+    ri[0] = r[m].status; ri[1] = r[m].n_out; ri[2] = r[m].k_final; ri[3] = r[m].outer_iters;
+    ri[4] = r[m].total_degree; ri[5] = r[m].block;
+    result_d[m] = r[m].max_residual;
+  }
+  return rc;
+}
+
+int hostsim_rr_sym(double* g, double* h, double* w, double* theta, int b) {
+  std::vector<double> y((size_t)b * b);
+  std::vector<int> rank(b);
+  fb::SeqPar par;
+  return fb::rayleigh_ritz_sym(g, h, y.data(), w, theta, rank.data(), b, par);
+}
+
+int hostsim_eig_general(const double* a, int n, double* evals_ri, double* evecs_ri) {
+  std::vector<fb::cplx> ev(n), vec((size_t)n * n);
+  const int rc = fb::eig_general(a, n, ev.data(), vec.data());
+  for (int i = 0; i < n; ++i) {
+    evals_ri[2 * i] = ev[i].real();
+    evals_ri[2 * i + 1] = ev[i].imag();
+  }
+  for (int i = 0; i < n * n; ++i) {
+    evecs_ri[2 * i] = vec[i].real();
+    evecs_ri[2 * i + 1] = vec[i].imag();
+  }
+  return rc;
+}
+
+double hostsim_edge_weight(const double* p1, const double* p2) { return fb::edge_weight(p1, p2); }
+}
