@@ -1,0 +1,163 @@
+/* libfocusr_b200 -- C ABI of the B200 (sm_100a) spectral-correspondence hot path of PyFOCUSR.
+ *
+ * The reference (gattia/pyfocusr) has no FFI: its boundary is the Python class API
+ * (pyfocusr/focusr.py:22-69, pyfocusr/graph.py:18-34, pyfocusr/eigsort.py:9-22).  The Python
+ * drop-in classes in pyfocusr_b200/ keep that API and bind the entry points below with ctypes
+ * (pyfocusr_b200/_lib.py); each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it except
+ *     focusr_laplacian_build (validates triangle indices) and focusr_eigs_smallest (reads Ritz
+ *     values back to drive the outer loop), which synchronise it;
+ *   - the library never allocates device memory: callers pass workspaces sized by the matching
+ *     *_workspace_bytes() function (PyTorch's caching allocator owns all HBM);
+ *   - return value 0 = success; otherwise an error code and focusr_last_error() describes it;
+ *   - dense matrices are row-major; eigenvector / feature blocks are [n_points][ld];
+ *   - a "batch" is a set of meshes concatenated into one block-diagonal graph: vertex ids in
+ *     `tris` are global, `mesh_point_off[m] .. mesh_point_off[m+1]` are mesh m's rows.
+ */
+#ifndef FOCUSR_B200_H
+#define FOCUSR_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* focusr_stream_t;
+
+const char* focusr_last_error(void);
+int focusr_version(void);
+/* kernels launched by this library since load (bench.py's `gpu_launches`) */
+unsigned long long focusr_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  Laplacian assembly.  Replaces Graph.get_weighted_adjacency_matrix (graph.py:148-178: the
+ * Python loop over cells x edges filling a lil_matrix), get_degree_matrix (graph.py:216-219).
+ * Output: canonical CSR of the weighted adjacency A (columns ascending, duplicates collapsed),
+ * degree d = A.sum(axis=1) (sequential ascending-column sum, bit-identical to scipy) and
+ * 1/(d+1e-8).  `cols`/`weights` need capacity 3*n_tris.  `mesh_info` is [n_meshes][4] int:
+ * {nnz(A), one-way entries (A_ij stored, A_ji not), zero-degree rows, non-finite weights}.
+ * ------------------------------------------------------------------------------------------- */
+size_t focusr_laplacian_workspace_bytes(int n_points, int n_tris);
+int focusr_laplacian_build(const double* points, const int* tris, int n_points, int n_tris,
+                           const int* mesh_point_off, int n_meshes, int* row_ptr, int* cols,
+                           double* weights, double* degree, double* degree_inv, int* mesh_info,
+                           void* workspace, size_t workspace_bytes, focusr_stream_t stream);
+
+/* L = D~^-1 (D - A) as CSR with sorted columns and explicit zeros dropped, i.e. what
+ * Graph.get_laplacian_matrix (graph.py:221-226) produces after sort_indices().  The solver does
+ * not need it (it applies L from A, d, 1/(d+1e-8)); it exists for Graph.laplacian_matrix.
+ * `l_cols`/`l_vals` need capacity nnz(A) + n_points. */
+int focusr_laplacian_csr(const int* row_ptr, const int* cols, const double* weights,
+                         const double* degree, const double* degree_inv, int n_points,
+                         int* l_row_ptr, int* l_cols, double* l_vals, void* workspace,
+                         size_t workspace_bytes, focusr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K5  Graph.mean_filter_graph (graph.py:320-354): values <- M^iterations values with
+ * M = diag(1/(1+d)) (A + I), for rows [row_begin, row_end) of the batch graph (values are
+ * indexed by global row).  Accumulation order and rounding reproduce scipy's CSR product
+ * bit-for-bit (descending columns, multiply then add).  `scratch` is one more
+ * [n_points][n_cols] buffer; the result lands in values_out (values_in is not modified).
+ * ------------------------------------------------------------------------------------------- */
+int focusr_mean_filter(const int* row_ptr, const int* cols, const double* weights,
+                       const double* degree, int row_begin, int row_end, const double* values_in,
+                       double* values_out, double* scratch, int n_cols, int iterations,
+                       focusr_stream_t stream);
+
+/* out[i][:] = in[idx[i]][:]  (focusr.py:387 `smoothed_target_coords[corresponding_idx, :]`;
+ * focusr.py:429-431 nearest-neighbour positions).  `idx_base[i]` (nullable) is added to idx[i]. */
+int focusr_gather_rows(const double* in, const long long* idx, const int* idx_base, int n_rows,
+                       int n_cols, double* out, focusr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  recursive_eig (graph.py:357-389) = scipy eigs(L, k, sigma=1e-10, which="LM", ncv=4k) +
+ * retry while fewer than n_k_needed eigenvalues exceed min_eig_val.  Returns, per mesh, the
+ * eigenpairs with eigenvalue > min_eig_val among the k_final smallest, ascending, eigenvectors
+ * with unit 2-norm and the largest-magnitude entry positive.  SYNCHRONISES the stream (once per
+ * outer iteration).  `mesh_info_host` is focusr_laplacian_build's mesh_info copied to the host.
+ * result_i_host [n_meshes][8]: {status, n_found, k_final, outer_iterations, total_filter_degree,
+ * block_size, symmetric, restarts};  result_d_host [n_meshes][2]: {max_residual, 0}.
+ * status: 0 ok, 1 not converged, 2 block too small, 3 numerical breakdown, 4 ldv too small.
+ * ------------------------------------------------------------------------------------------- */
+size_t focusr_eigs_workspace_bytes(int n_points, int n_meshes, int max_mesh_points, int block_size);
+int focusr_eigs_block_size(int k, int n_k_needed, int k_buffer, int max_one_way, int max_zero_rows);
+int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weights,
+                         const double* degree, const double* degree_inv, const double* points,
+                         int n_points, const int* mesh_point_off_host, int n_meshes,
+                         const int* mesh_info_host, int k, int n_k_needed, int k_buffer,
+                         double min_eig_val, double tol, int max_outer, int block_size,
+                         double* eig_vals, double* eig_vecs, int ldv, int* result_i_host,
+                         double* result_d_host, void* workspace, size_t workspace_bytes,
+                         focusr_stream_t stream);
+
+/* y = L x for a dense block of n_cols vectors (n_cols a multiple of 8, <= 96), used by tests and
+ * residual checks: y[i][:] = dinv_i (d_i x_i - sum_j w_ij x_j). */
+int focusr_laplacian_apply(const int* row_ptr, const int* cols, const double* weights,
+                           const double* degree, const double* degree_inv,
+                           const int* mesh_point_off, int n_meshes, int max_mesh_points,
+                           const double* x, double* y, int n_cols, focusr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * B2  eigenvector normalisation (graph.py:254-257): per mesh, per column j < n_cols[m]:
+ * v <- (v - min v) / ptp(v) - 0.5.   In place on vecs [n_points][ld].
+ * ------------------------------------------------------------------------------------------- */
+int focusr_normalize_columns(double* vecs, int n_points, int ld, const int* mesh_point_off,
+                             int n_meshes, const int* n_cols, focusr_stream_t stream);
+
+/* C5  eigsort's flip + reorder (eigsort.py:108-122), applied to every mesh m of the given offset
+ * table:  new[:, dst[m][t]] = sign[m][t] * old[:, src[m][t]] for t < n_moves (sign = +1/-1), other
+ * columns unchanged.  A mesh that must stay as it is gets the identity (dst = src, sign = +1). */
+int focusr_flip_permute_columns(double* vecs, int n_points, int ld, const int* mesh_point_off,
+                                int n_meshes, int max_mesh_points, const int* dst, const int* src,
+                                const int* sign, int n_moves, focusr_stream_t stream);
+
+/* D1  spectral coordinates (focusr.py:492-508): out[i][u] = vecs[i][u] * weights[m][u], u < ns;
+ * out is [n_points][ns]. */
+int focusr_spectral_coords(const double* vecs, int n_points, int ld, const int* mesh_point_off,
+                           int n_meshes, int max_mesh_points, const double* weights, int ns,
+                           double* out, focusr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * C1, C3, C4  eigsort cost matrices (eigsort.py:34-41, 162-233) for n_pairs (target, source)
+ * pairs.  Pair p uses mesh t_mesh[p] / s_mesh[p] of the batch, sample rows idx_t[p][0..n_samp_t)
+ * and idx_s[p][..] (local row ids = Graph.rand_idxs).  Outputs [n_pairs][n][n] each:
+ * c_hist / c_hist_f (1-D Wasserstein distance of log(v + 0.5 + eps), source flipped for _f) and
+ * c_spatial / c_spatial_f (RMS difference at xyz nearest neighbours / n_samp_t); nn_idx
+ * [n_pairs][n_samp_t] is the nearest sampled source point of each sampled target point.
+ * c_lambda, min/compare, the n x n assignment and the flip list stay on the host.
+ * ------------------------------------------------------------------------------------------- */
+size_t focusr_eigsort_workspace_bytes(int n_pairs, int n_samp_t, int n_samp_s, int n_features);
+int focusr_eigsort_costs(const double* vecs, int ld, const double* points,
+                         const int* mesh_point_off, const int* t_mesh, const int* s_mesh,
+                         int n_pairs, const long long* idx_t, const long long* idx_s, int n_samp_t,
+                         int n_samp_s, int n_features, double* c_hist, double* c_hist_f,
+                         double* c_spatial, double* c_spatial_f, long long* nn_idx, void* workspace,
+                         size_t workspace_bytes, focusr_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4  exact k-nearest neighbours (scipy KDTree(refs).query(queries, k), p=2: focusr.py:351-353,
+ * 409-413; eigsort.py:203-204).  fp64 brute force on direct differences sum_c (q_c - r_c)^2 in
+ * column order without FMA; ties go to the lower index.  Segmented: segment s searches
+ * refs[ref_off[s]..ref_off[s+1]) for queries[query_off[s]..query_off[s+1]); returned indices are
+ * local to the segment.  idx [n_queries][k], dist [n_queries][k] (Euclidean, nullable).
+ * ------------------------------------------------------------------------------------------- */
+int focusr_knn(const double* refs, int ld_refs, const int* ref_off, const double* queries,
+               int ld_queries, const int* query_off, int n_segments, int max_queries_per_segment,
+               int dim, int k, long long* idx, double* dist, focusr_stream_t stream);
+
+/* E3  get_weighted_final_node_locations (focusr.py:401-426) from the k=3 neighbours:
+ * coincident neighbour -> its target point, else inverse-distance weighted mean of the three
+ * target points.  idx3 is local to the segment of `target_points` starting at point_base[i]
+ * (nullable = 0). */
+int focusr_weighted_positions(const long long* idx3, const double* dist3,
+                              const double* target_points, const int* point_base, int n_queries,
+                              double* out, focusr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOCUSR_B200_H */

@@ -1,0 +1,746 @@
+// K2: smallest-k eigenpairs of the mesh Laplacian on the B200 -- the CUDA backend of the block
+// solver in chfsi_driver.hpp.  Replaces scipy's shift-invert ARPACK + SuperLU call
+// (reference graph.py:357-389) with factorisation-free Chebyshev-filtered subspace iteration.
+//
+// Kernels in this file (the CSR SpMM of the filter itself is in spmm.cu):
+//   k_gram    tall-skinny Gram pair G = X^T g X, H = X^T h Z per mesh with FP64 tensor-core
+//             DMMA (mma.sync.m8n8k4.f64: tcgen05 has no f64 kind);
+//   k_rr_sym  one warp per mesh: Cholesky + congruence + cyclic Jacobi in shared memory;
+//   k_rotate  X <- X W (DMMA) fused with the residual norms ||L x - theta x||;
+//   k_write_pairs  unit-norm, sign-fixed eigenvectors into the caller's [n_points][ldv] block.
+// All reductions use fixed trees / fixed chunk order: results are bit-reproducible run to run.
+#include <vector>
+
+#include "chfsi_driver.hpp"
+#include "common.cuh"
+#include "rowops.h"
+#include "spmm.cuh"
+
+namespace fb {
+
+constexpr int GRAM_ROWS = 1024;  // rows per CTA (8 warps x 128 rows)
+constexpr int GRAM_THREADS = 256;
+
+__device__ __forceinline__ long long dkey(double v) {
+  const long long b = __double_as_longlong(v);
+  return b >= 0 ? b : (b ^ 0x7fffffffffffffffLL);
+}
+__device__ __forceinline__ double dkey_inv(long long k) {
+  return __longlong_as_double(k >= 0 ? k : (k ^ 0x7fffffffffffffffLL));
+}
+
+__global__ void k_bbox_init(long long* lo, long long* hi, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    lo[i] = 0x7fffffffffffffffLL;
+    hi[i] = (long long)0x8000000000000000ULL;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_bbox(const double* __restrict__ points, const int* __restrict__ mesh_off, long long* lo, long long* hi) {
+  const int mesh = blockIdx.y;
+  const int r0 = mesh_off[mesh] + blockIdx.x * GRAM_ROWS;
+  const int r1 = min(mesh_off[mesh + 1], r0 + GRAM_ROWS);
+  long long mn[3] = {0x7fffffffffffffffLL, 0x7fffffffffffffffLL, 0x7fffffffffffffffLL};
+  long long mx[3] = {(long long)0x8000000000000000ULL, (long long)0x8000000000000000ULL, (long long)0x8000000000000000ULL};
+  for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const long long k = dkey(points[3 * (size_t)r + a]);
+      mn[a] = min(mn[a], k);
+      mx[a] = max(mx[a], k);
+    }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[a] = min(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = max(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+    if ((threadIdx.x & 31) == 0 && r0 < r1) {
+      atomicMin(&lo[3 * mesh + a], mn[a]);
+      atomicMax(&hi[3 * mesh + a], mx[a]);
+    }
+  }
+}
+
+template <int B>
+__global__ void __launch_bounds__(256)
+k_init_block(const double* __restrict__ points, const double* __restrict__ degree,
+             const int* __restrict__ mesh_off, const long long* __restrict__ lo,
+             const long long* __restrict__ hi, double* __restrict__ x) {
+  const int mesh = blockIdx.y;
+  const int m0 = mesh_off[mesh];
+  const int r0 = m0 + blockIdx.x * GRAM_ROWS;
+  const int r1 = min(mesh_off[mesh + 1], r0 + GRAM_ROWS);
+  if (r0 >= r1) return;
+  double c[3], scale = 0.0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const double l = dkey_inv(lo[3 * mesh + a]), h = dkey_inv(hi[3 * mesh + a]);
+    c[a] = 0.5 * (l + h);
+    scale = fmax(scale, 0.5 * (h - l));
+  }
+  if (!(scale > 0.0)) scale = 1.0;
+  for (long long t = threadIdx.x; t < (long long)(r1 - r0) * B; t += blockDim.x) {
+    const int r = r0 + (int)(t / B), col = (int)(t % B);
+    double v = 0.0;
+    if (degree[r] != 0.0) {  // zero-degree rows stay pinned at 0 (exact null vectors, handled analytically)
+      const double px = (points[3 * (size_t)r] - c[0]) / scale;
+      const double py = (points[3 * (size_t)r + 1] - c[1]) / scale;
+      const double pz = (points[3 * (size_t)r + 2] - c[2]) / scale;
+      v = start_block_value(col, px, py, pz, (uint32_t)(r - m0), 1u);
+    }
+    x[(size_t)r * B + col] = v;
+  }
+}
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// G[p][q] = sum_r X[r][p] g_r X[r][q],  H[p][q] = sum_r X[r][p] h_r Z[r][q]  per (mesh, chunk).
+// blockIdx.z picks a group of QT column tiles (8 columns each) so the accumulators fit registers.
+// As an MMA: D(8x8) += A(8x4) B(4x8) with A[p][r'] = X[r+r'][p], B[r'][q] = g X[r+r'][q]; for
+// m8n8k4 lane l holds A[l>>2][l&3], B[l&3][l>>2] and D[l>>2][2*(l&3)+{0,1}].
+template <int B, int QT>
+__global__ void __launch_bounds__(GRAM_THREADS)
+k_gram(const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ degree,
+       const double* __restrict__ degree_inv, const int* __restrict__ mesh_off, int sym,
+       double* __restrict__ partial, int chunks_max) {
+  constexpr int PT = B / 8;
+  const int mesh = blockIdx.y, chunk = blockIdx.x, q0 = blockIdx.z * QT;
+  const int r0 = mesh_off[mesh] + chunk * GRAM_ROWS;
+  const int r1 = min(mesh_off[mesh + 1], r0 + GRAM_ROWS);
+  if (r0 >= r1) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rr = lane & 3, cc = lane >> 2;
+  double accg[PT][QT][2], acch[PT][QT][2];
+#pragma unroll
+  for (int a = 0; a < PT; ++a)
+#pragma unroll
+    for (int b = 0; b < QT; ++b) accg[a][b][0] = accg[a][b][1] = acch[a][b][0] = acch[a][b][1] = 0.0;
+  const int w0 = r0 + warp * (GRAM_ROWS / 8);
+  const int w1 = min(r1, w0 + GRAM_ROWS / 8);
+  for (int r = w0; r < w1; r += 4) {
+    const int row = r + rr;
+    const bool valid = row < w1;
+    double gw = 0.0, hw = 0.0;
+    if (valid) {
+      gw = sym ? degree[row] + 1e-8 : 1.0;
+      hw = sym ? 1.0 : degree_inv[row];
+    }
+    double xs[PT], xq[QT], zq[QT];
+#pragma unroll
+    for (int t = 0; t < PT; ++t) xs[t] = valid ? x[(size_t)row * B + 8 * t + cc] : 0.0;
+#pragma unroll
+    for (int t = 0; t < QT; ++t) {
+      const bool qv = valid && (q0 + t) < PT;
+      xq[t] = qv ? x[(size_t)row * B + 8 * (q0 + t) + cc] * gw : 0.0;
+      zq[t] = qv ? z[(size_t)row * B + 8 * (q0 + t) + cc] * hw : 0.0;
+    }
+#pragma unroll
+    for (int a = 0; a < PT; ++a)
+#pragma unroll
+      for (int b = 0; b < QT; ++b) {
+        dmma884(accg[a][b][0], accg[a][b][1], xs[a], xq[b]);
+        dmma884(acch[a][b][0], acch[a][b][1], xs[a], zq[b]);
+      }
+  }
+  // deterministic cross-warp reduction: warps add their tiles in warp order
+  __shared__ double red[2][B][QT * 8];
+  for (int w = 0; w < GRAM_THREADS / 32; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int a = 0; a < PT; ++a)
+#pragma unroll
+        for (int b = 0; b < QT; ++b)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int p = 8 * a + cc, q = 8 * b + 2 * rr + e;
+            if (w == 0) {
+              red[0][p][q] = accg[a][b][e];
+              red[1][p][q] = acch[a][b][e];
+            } else {
+              red[0][p][q] += accg[a][b][e];
+              red[1][p][q] += acch[a][b][e];
+            }
+          }
+    }
+    __syncthreads();
+  }
+  double* dst = partial + ((size_t)mesh * chunks_max + chunk) * 2 * B * B;
+  for (int t = threadIdx.x; t < 2 * B * QT * 8; t += GRAM_THREADS) {
+    const int mat = t / (B * QT * 8), rem = t % (B * QT * 8);
+    const int p = rem / (QT * 8), ql = rem % (QT * 8);
+    const int q = 8 * q0 + ql;
+    if (q < B) dst[(size_t)mat * B * B + p * B + q] = red[mat][p][ql];
+  }
+}
+
+// One warp per mesh: sum the chunk partials in chunk order, then the b x b Rayleigh-Ritz step.
+__global__ void __launch_bounds__(32)
+k_rr_sym(const double* __restrict__ partial, int chunks_max, const int* __restrict__ mesh_off, int B,
+         double* __restrict__ w_out, double* __restrict__ theta_out, int* __restrict__ info) {
+  extern __shared__ double sm[];
+  double* g = sm;
+  double* h = g + B * B;
+  double* y = h + B * B;
+  double* th = y + B * B;
+  int* rank = reinterpret_cast<int*>(th + B);
+  const int mesh = blockIdx.x, lane = threadIdx.x;
+  const int nchunks = (mesh_off[mesh + 1] - mesh_off[mesh] + GRAM_ROWS - 1) / GRAM_ROWS;
+  const double* src = partial + (size_t)mesh * chunks_max * 2 * B * B;
+  for (int e = lane; e < B * B; e += 32) {
+    double sg = 0.0, sh = 0.0;
+    for (int c = 0; c < nchunks; ++c) {
+      sg += src[(size_t)c * 2 * B * B + e];
+      sh += src[(size_t)c * 2 * B * B + B * B + e];
+    }
+    g[e] = sg;
+    h[e] = sh;
+  }
+  __syncwarp();
+  WarpPar par{lane};
+  const int rc = rayleigh_ritz_sym(g, h, y, w_out + (size_t)mesh * B * B, th, rank, B, par);
+  for (int j = lane; j < B; j += 32) theta_out[(size_t)mesh * B + j] = th[j];
+  if (lane == 0) info[mesh] = rc;
+}
+
+// Non-symmetric path: only the chunk reduction happens on the device; the host does the rest.
+__global__ void k_reduce_gh(const double* __restrict__ partial, int chunks_max,
+                            const int* __restrict__ mesh_off, int B, double* __restrict__ g_out,
+                            double* __restrict__ h_out) {
+  const int mesh = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B * B) return;
+  const int nchunks = (mesh_off[mesh + 1] - mesh_off[mesh] + GRAM_ROWS - 1) / GRAM_ROWS;
+  const double* src = partial + (size_t)mesh * chunks_max * 2 * B * B;
+  double sg = 0.0, sh = 0.0;
+  for (int c = 0; c < nchunks; ++c) {
+    sg += src[(size_t)c * 2 * B * B + e];
+    sh += src[(size_t)c * 2 * B * B + B * B + e];
+  }
+  g_out[(size_t)mesh * B * B + e] = sg;
+  h_out[(size_t)mesh * B * B + e] = sh;
+}
+
+// X <- X W in place, Z' = Z W kept in registers, residual sums of dinv*Z' - theta*X' and X'^2.
+// D(8 rows x 8 cols) += A(8x4) B(4x8): A[r'][k'] = X[r+r'][k+k'] (lane: r' = l>>2, k' = l&3),
+// B[k'][j'] = W[k+k'][j+j'] (lane: k' = l&3, j' = l>>2), D lane: row l>>2, cols 2*(l&3)+{0,1}.
+template <int B>
+__global__ void __launch_bounds__(GRAM_THREADS)
+k_rotate(double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ w,
+         const double* __restrict__ theta, const double* __restrict__ degree_inv,
+         const int* __restrict__ mesh_off, double* __restrict__ partial_res, int chunks_max) {
+  constexpr int WS = (B % 16 == 0) ? B + 8 : B;  // row stride of W in smem: 2-wavefront fragment reads
+  constexpr int KS = B / 4, JT = B / 8;
+  extern __shared__ double sm[];
+  double* ws = sm;                          // [B][WS]
+  double* acc = ws + B * WS;                // [8 warps][2][B]
+  const int mesh = blockIdx.y, chunk = blockIdx.x;
+  const int r0 = mesh_off[mesh] + chunk * GRAM_ROWS;
+  const int r1 = min(mesh_off[mesh + 1], r0 + GRAM_ROWS);
+  if (r0 >= r1) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = threadIdx.x; t < B * B; t += GRAM_THREADS) ws[(t / B) * WS + (t % B)] = w[(size_t)mesh * B * B + t];
+  for (int t = threadIdx.x; t < 8 * 2 * B; t += GRAM_THREADS) acc[t] = 0.0;
+  __syncthreads();
+  const int kq = lane & 3, rq = lane >> 2;
+  double* my_num = acc + (warp * 2 + 0) * B;
+  double* my_den = acc + (warp * 2 + 1) * B;
+  const int w0 = r0 + warp * (GRAM_ROWS / 8);
+  const int w1 = min(r1, w0 + GRAM_ROWS / 8);
+  for (int rb = w0; rb < w1; rb += 8) {
+    const int row = rb + rq;
+    const bool valid = row < w1;
+    double xa[KS], za[KS];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      xa[ks] = valid ? x[(size_t)row * B + 4 * ks + kq] : 0.0;
+      za[ks] = valid ? z[(size_t)row * B + 4 * ks + kq] : 0.0;
+    }
+    const double di = valid ? degree_inv[row] : 0.0;
+#pragma unroll
+    for (int tj = 0; tj < JT; ++tj) {
+      double cx0 = 0.0, cx1 = 0.0, cz0 = 0.0, cz1 = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const double bf = ws[(4 * ks + kq) * WS + 8 * tj + rq];
+        dmma884(cx0, cx1, xa[ks], bf);
+        dmma884(cz0, cz1, za[ks], bf);
+      }
+      const int c0 = 8 * tj + 2 * kq;
+      if (valid) *reinterpret_cast<double2*>(x + (size_t)row * B + c0) = make_double2(cx0, cx1);
+      const double t0 = theta[(size_t)mesh * B + c0], t1 = theta[(size_t)mesh * B + c0 + 1];
+      const double e0 = di * cz0 - t0 * cx0, e1 = di * cz1 - t1 * cx1;
+      double n0 = e0 * e0, n1 = e1 * e1, d0 = cx0 * cx0, d1 = cx1 * cx1;
+      // sum over the 8 rows of the tile (lanes with equal l&3), fixed tree
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        n0 += __shfl_xor_sync(0xffffffffu, n0, o);
+        n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+        d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+        d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+      }
+      if (rq == 0) {
+        my_num[c0] += n0;
+        my_num[c0 + 1] += n1;
+        my_den[c0] += d0;
+        my_den[c0 + 1] += d1;
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  double* dst = partial_res + ((size_t)mesh * chunks_max + chunk) * 2 * B;
+  for (int t = threadIdx.x; t < 2 * B; t += GRAM_THREADS) {
+    double s = 0.0;
+    for (int wv = 0; wv < 8; ++wv) s += acc[(wv * 2 + t / B) * B + (t % B)];
+    dst[t] = s;
+  }
+}
+
+__global__ void k_residual(const double* __restrict__ partial_res, int chunks_max,
+                           const int* __restrict__ mesh_off, int B, double* __restrict__ res) {
+  const int mesh = blockIdx.x;
+  const int nchunks = (mesh_off[mesh + 1] - mesh_off[mesh] + GRAM_ROWS - 1) / GRAM_ROWS;
+  for (int j = threadIdx.x; j < B; j += blockDim.x) {
+    double n = 0.0, d = 0.0;
+    for (int c = 0; c < nchunks; ++c) {
+      n += partial_res[((size_t)mesh * chunks_max + c) * 2 * B + j];
+      d += partial_res[((size_t)mesh * chunks_max + c) * 2 * B + B + j];
+    }
+    res[(size_t)mesh * B + j] = sqrt(n / d);
+  }
+}
+
+// Output of a converged mesh: column j of eig_vecs = X[:, sel[j]] / ||.||_2, sign such that the
+// entry of largest magnitude (lowest row on ties) is positive; eig_vals[j] = theta[sel[j]].
+__global__ void __launch_bounds__(256)
+k_write_pairs(const double* __restrict__ x, const double* __restrict__ theta, int B,
+              const int* __restrict__ mesh_off, const int* __restrict__ flags,
+              const int* __restrict__ sel, const int* __restrict__ n_out, double* __restrict__ eig_vals,
+              double* __restrict__ eig_vecs, int ldv, int mesh_base) {
+  const int mesh = blockIdx.y, j = blockIdx.x;
+  if (!flags[mesh] || j >= n_out[mesh]) return;
+  const int c = sel[(size_t)mesh * B + j];
+  const int r0 = mesh_off[mesh], r1 = mesh_off[mesh + 1];
+  double ss = 0.0, best = -1.0, bestv = 0.0;
+  int besti = 0x7fffffff;
+  for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+    const double v = x[(size_t)r * B + c];
+    ss += v * v;
+    const double a = fabs(v);
+    if (a > best) {
+      best = a;
+      bestv = v;
+      besti = r;
+    }
+  }
+  __shared__ double s_ss[256], s_best[256], s_bestv[256];
+  __shared__ int s_besti[256];
+  s_ss[threadIdx.x] = ss;
+  s_best[threadIdx.x] = best;
+  s_bestv[threadIdx.x] = bestv;
+  s_besti[threadIdx.x] = besti;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s_ss[threadIdx.x] += s_ss[threadIdx.x + o];
+      const double ob = s_best[threadIdx.x + o];
+      const int oi = s_besti[threadIdx.x + o];
+      if (ob > s_best[threadIdx.x] || (ob == s_best[threadIdx.x] && oi < s_besti[threadIdx.x])) {
+        s_best[threadIdx.x] = ob;
+        s_bestv[threadIdx.x] = s_bestv[threadIdx.x + o];
+        s_besti[threadIdx.x] = oi;
+      }
+    }
+    __syncthreads();
+  }
+  const double scale = (s_bestv[0] < 0.0 ? -1.0 : 1.0) / sqrt(s_ss[0]);
+  for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x)
+    eig_vecs[(size_t)r * ldv + j] = x[(size_t)r * B + c] * scale;
+  if (threadIdx.x == 0) eig_vals[(size_t)(mesh_base + mesh) * ldv + j] = theta[(size_t)mesh * B + c];
+}
+
+// ---------------------------------------------------------------------------------------------
+// pinned host staging (grow-only, process lifetime)
+// ---------------------------------------------------------------------------------------------
+struct PinnedPool {
+  void* p = nullptr;
+  size_t cap = 0;
+  void* get(size_t bytes) {
+    if (bytes > cap) {
+      if (p) cudaFreeHost(p);
+      p = nullptr;
+      cap = 0;
+      if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+      cap = bytes;
+    }
+    return p;
+  }
+};
+static thread_local PinnedPool g_pin_small, g_pin_tables;
+
+template <int B>
+struct GramCfg {
+  static constexpr int QT = (B <= 32) ? B / 8 : (B <= 64 ? 2 : 1);
+};
+
+struct CudaBackend {
+  // graph of this run (rows are the run's meshes; pointers are global, offsets select the run)
+  SpmmGraph g;
+  const double* points;
+  const int* off_host;   // [M+1] global row offsets of the run's meshes
+  const int* info_host;  // [M][4]
+  int M, B, mesh_base;
+  bool sym;
+  cudaStream_t stream;
+  // workspace
+  double *X, *Y, *Xn, *partial, *partial_res, *W, *theta, *res, *G, *H, *alpha, *gamma, *center;
+  long long *lo, *hi;
+  int *flags, *sel, *n_out, *rr_info;
+  int chunks_max, table_cap;
+  // outputs
+  double* eig_vals;
+  double* eig_vecs;
+  int ldv;
+  int err = FB_OK;
+
+  int n_meshes() const { return M; }
+  int block() const { return B; }
+  bool symmetric() const { return sym; }
+  int zero_rows(int m) const { return info_host[4 * m + 2]; }
+
+  void fail(cudaError_t e, const char* what) {
+    if (e != cudaSuccess && err == FB_OK) {
+      set_error("eigs: %s -> %s", what, cudaGetErrorString(e));
+      err = FB_ERR_CUDA;
+    }
+  }
+  void check(const char* what) { fail(cudaGetLastError(), what); }
+
+  template <int BB>
+  void init_block_t() {
+    dim3 grid(chunks_max, M);
+    k_init_block<BB><<<grid, 256, 0, stream>>>(points, g.degree, g.mesh_off, lo, hi, X);
+  }
+  template <int BB>
+  void gram_t() {
+    constexpr int QT = GramCfg<BB>::QT;
+    dim3 grid(chunks_max, M, (BB / 8 + QT - 1) / QT);
+    k_gram<BB, QT><<<grid, GRAM_THREADS, 0, stream>>>(X, Xn, g.degree, g.degree_inv, g.mesh_off, sym ? 1 : 0,
+                                                      partial, chunks_max);
+  }
+  template <int BB>
+  void rotate_t() {
+    constexpr int WS = (BB % 16 == 0) ? BB + 8 : BB;
+    const size_t smem = sizeof(double) * ((size_t)BB * WS + 16 * BB);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_rotate<BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      attr_set = true;
+    }
+    dim3 grid(chunks_max, M);
+    k_rotate<BB><<<grid, GRAM_THREADS, smem, stream>>>(X, Xn, W, theta, g.degree_inv, g.mesh_off, partial_res, chunks_max);
+  }
+#define FB_DISPATCH_B(fn)                \
+  switch (B) {                           \
+    case 8: fn<8>(); break;              \
+    case 16: fn<16>(); break;            \
+    case 24: fn<24>(); break;            \
+    case 32: fn<32>(); break;            \
+    case 40: fn<40>(); break;            \
+    case 48: fn<48>(); break;            \
+    case 56: fn<56>(); break;            \
+    case 64: fn<64>(); break;            \
+    case 72: fn<72>(); break;            \
+    case 80: fn<80>(); break;            \
+    case 88: fn<88>(); break;            \
+    case 96: fn<96>(); break;            \
+    default: break;                      \
+  }
+
+  void init_block() {
+    k_bbox_init<<<div_up(3 * M, 256), 256, 0, stream>>>(lo, hi, 3 * M);
+    dim3 grid(chunks_max, M);
+    k_bbox<<<grid, 256, 0, stream>>>(points, g.mesh_off, lo, hi);
+    FB_DISPATCH_B(init_block_t)
+    FB_COUNT_LAUNCH(3);
+    check("init_block");
+  }
+  void apply_DmA() {  // Z (stored in Xn) = (D - A) X
+    launch_spmm(1, B, g, X, X, Xn, nullptr, nullptr, nullptr, 0, 0, stream);
+    check("apply_DmA");
+  }
+  void gram() {
+    FB_DISPATCH_B(gram_t)
+    FB_COUNT_LAUNCH(1);
+    check("gram");
+  }
+  int rr_sym() {
+    const size_t smem = sizeof(double) * ((size_t)3 * B * B + B) + sizeof(int) * B;
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+      cudaFuncSetAttribute(k_rr_sym, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      attr_smem = smem;
+    }
+    k_rr_sym<<<M, 32, smem, stream>>>(partial, chunks_max, g.mesh_off, B, W, theta, rr_info);
+    FB_COUNT_LAUNCH(1);
+    check("rr_sym");
+    return 0;
+  }
+  void get_GH(double* gh, double* hh) {
+    dim3 grid(div_up(B * B, 256), M);
+    k_reduce_gh<<<grid, 256, 0, stream>>>(partial, chunks_max, g.mesh_off, B, G, H);
+    FB_COUNT_LAUNCH(1);
+    check("reduce_gh");
+    const size_t bytes = sizeof(double) * (size_t)M * B * B;
+    fail(cudaMemcpyAsync(gh, G, bytes, cudaMemcpyDeviceToHost, stream), "D2H G");
+    fail(cudaMemcpyAsync(hh, H, bytes, cudaMemcpyDeviceToHost, stream), "D2H H");
+    fail(cudaStreamSynchronize(stream), "sync after G/H");
+  }
+  void set_W_theta(const double* wv, const double* th) {
+    // pageable host memory: the copy is staged by the runtime before the call returns
+    fail(cudaMemcpyAsync(W, wv, sizeof(double) * (size_t)M * B * B, cudaMemcpyHostToDevice, stream), "H2D W");
+    fail(cudaMemcpyAsync(theta, th, sizeof(double) * (size_t)M * B, cudaMemcpyHostToDevice, stream), "H2D theta");
+  }
+  void rotate_and_residual() {
+    FB_DISPATCH_B(rotate_t)
+    k_residual<<<M, 128, 0, stream>>>(partial_res, chunks_max, g.mesh_off, B, res);
+    FB_COUNT_LAUNCH(2);
+    check("rotate");
+  }
+  void get_theta_res(double* th, double* rs) {
+    const size_t bytes = sizeof(double) * (size_t)M * B;
+    double* pin = (double*)g_pin_small.get(2 * bytes);
+    if (!pin) {
+      fail(cudaErrorMemoryAllocation, "pinned staging");
+      return;
+    }
+    fail(cudaMemcpyAsync(pin, theta, bytes, cudaMemcpyDeviceToHost, stream), "D2H theta");
+    fail(cudaMemcpyAsync(pin + (size_t)M * B, res, bytes, cudaMemcpyDeviceToHost, stream), "D2H res");
+    fail(cudaStreamSynchronize(stream), "sync after theta/res");
+    memcpy(th, pin, bytes);
+    memcpy(rs, pin + (size_t)M * B, bytes);
+  }
+  void filter(int deg, const double* al, const double* ga, const double* ce) {
+    // tables are uploaded in chunks of table_cap steps; pinned staging holds every chunk of this
+    // filter until the next synchronisation (get_theta_res of the next outer iteration)
+    const size_t total = (size_t)M * deg;
+    double* pin = (double*)g_pin_tables.get(sizeof(double) * (2 * total + M));
+    if (!pin) {
+      fail(cudaErrorMemoryAllocation, "pinned tables");
+      return;
+    }
+    double* pc = pin + 2 * total;
+    memcpy(pc, ce, sizeof(double) * M);
+    fail(cudaMemcpyAsync(center, pc, sizeof(double) * M, cudaMemcpyHostToDevice, stream), "H2D center");
+    double* cur = X;   // Y_k
+    double* prev = Y;  // Y_{k-1} (unused at step 0)
+    double* next = Xn;
+    size_t pin_off = 0;
+    for (int s0 = 0; s0 < deg; s0 += table_cap) {
+      const int len = std::min(table_cap, deg - s0);
+      double* pa = pin + pin_off;
+      double* pg = pa + (size_t)M * len;
+      pin_off += 2 * (size_t)M * len;
+      for (int m = 0; m < M; ++m) {
+        memcpy(pa + (size_t)m * len, al + (size_t)m * deg + s0, sizeof(double) * len);
+        memcpy(pg + (size_t)m * len, ga + (size_t)m * deg + s0, sizeof(double) * len);
+      }
+      fail(cudaMemcpyAsync(alpha, pa, sizeof(double) * (size_t)M * len, cudaMemcpyHostToDevice, stream), "H2D alpha");
+      fail(cudaMemcpyAsync(gamma, pg, sizeof(double) * (size_t)M * len, cudaMemcpyHostToDevice, stream), "H2D gamma");
+      for (int s = 0; s < len; ++s) {
+        launch_spmm(0, B, g, cur, prev, next, alpha, gamma, center, s, len, stream);
+        double* t = prev;
+        prev = cur;
+        cur = next;
+        next = t;
+      }
+    }
+    // rotate names so that X is the filtered block again
+    double* nx = cur;
+    double* ny = prev;
+    double* nn = next;
+    X = nx;
+    Y = ny;
+    Xn = nn;
+    check("filter");
+  }
+  void finalize(const int* fl, const int* sl, const int* no) {
+    fail(cudaMemcpyAsync(flags, fl, sizeof(int) * M, cudaMemcpyHostToDevice, stream), "H2D flags");
+    fail(cudaMemcpyAsync(sel, sl, sizeof(int) * (size_t)M * B, cudaMemcpyHostToDevice, stream), "H2D sel");
+    fail(cudaMemcpyAsync(n_out, no, sizeof(int) * M, cudaMemcpyHostToDevice, stream), "H2D n_out");
+    dim3 grid(std::min(B, ldv), M);
+    k_write_pairs<<<grid, 256, 0, stream>>>(X, theta, B, g.mesh_off, flags, sel, n_out, eig_vals, eig_vecs, ldv, mesh_base);
+    FB_COUNT_LAUNCH(1);
+    check("write_pairs");
+    // the host arrays are reused by the driver right after this call returns
+    fail(cudaStreamSynchronize(stream), "sync after finalize");
+  }
+};
+
+static size_t eigs_ws_layout(int n_rows, int n_meshes, int max_mesh_rows, int B, CudaBackend* be, void* ws, size_t ws_bytes) {
+  Carver cv(ws, ws_bytes);
+  const int chunks_max = div_up(max_mesh_rows, GRAM_ROWS);
+  const int table_cap = std::max(64, std::min(8192, (1 << 20) / std::max(1, n_meshes)));
+  double* X = cv.take<double>((size_t)n_rows * B);
+  double* Y = cv.take<double>((size_t)n_rows * B);
+  double* Xn = cv.take<double>((size_t)n_rows * B);
+  double* partial = cv.take<double>((size_t)n_meshes * chunks_max * 2 * B * B);
+  double* partial_res = cv.take<double>((size_t)n_meshes * chunks_max * 2 * B);
+  double* W = cv.take<double>((size_t)n_meshes * B * B);
+  double* G = cv.take<double>((size_t)n_meshes * B * B);
+  double* H = cv.take<double>((size_t)n_meshes * B * B);
+  double* theta = cv.take<double>((size_t)n_meshes * B);
+  double* res = cv.take<double>((size_t)n_meshes * B);
+  double* alpha = cv.take<double>((size_t)n_meshes * table_cap);
+  double* gamma = cv.take<double>((size_t)n_meshes * table_cap);
+  double* center = cv.take<double>((size_t)n_meshes);
+  long long* lo = cv.take<long long>((size_t)3 * n_meshes);
+  long long* hi = cv.take<long long>((size_t)3 * n_meshes);
+  int* flags = cv.take<int>((size_t)n_meshes);
+  int* sel = cv.take<int>((size_t)n_meshes * B);
+  int* n_out = cv.take<int>((size_t)n_meshes);
+  int* rr_info = cv.take<int>((size_t)n_meshes);
+  int* off = cv.take<int>((size_t)n_meshes + 1);
+  if (be) {
+    be->X = X; be->Y = Y; be->Xn = Xn; be->partial = partial; be->partial_res = partial_res;
+    be->W = W; be->G = G; be->H = H; be->theta = theta; be->res = res; be->alpha = alpha;
+    be->gamma = gamma; be->center = center; be->lo = lo; be->hi = hi; be->flags = flags;
+    be->sel = sel; be->n_out = n_out; be->rr_info = rr_info; be->g.mesh_off = off;
+    be->chunks_max = chunks_max; be->table_cap = table_cap;
+  }
+  return cv.used + 256;
+}
+
+}  // namespace fb
+
+using namespace fb;
+
+extern "C" {
+
+size_t focusr_eigs_workspace_bytes(int n_points, int n_meshes, int max_mesh_points, int block_size) {
+  return eigs_ws_layout(n_points, n_meshes, max_mesh_points, block_size, nullptr, nullptr, 0);
+}
+
+int focusr_eigs_block_size(int k, int n_k_needed, int k_buffer, int max_one_way, int max_zero_rows) {
+  // pinned pairs needed if the null space is {constant} + zero rows
+  int k_cur = k;
+  const int z = max_zero_rows + 1;
+  while (k_cur - (z < k_cur ? z : k_cur) < n_k_needed) k_cur += k_buffer + n_k_needed;
+  const int kp = k_cur - max_zero_rows > 1 ? k_cur - max_zero_rows : 1;
+  int b = kp + (kp / 2 > 8 ? kp / 2 : 8);
+  if (max_one_way > 0) b += 8 + 2 * (max_one_way < 8 ? max_one_way : 8);
+  b = (b + 7) / 8 * 8;
+  if (b < 16) b = 16;
+  if (b > 96) b = 96;
+  return b;
+}
+
+int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weights, const double* degree,
+                         const double* degree_inv, const double* points, int n_points,
+                         const int* mesh_point_off_host, int n_meshes, const int* mesh_info_host, int k,
+                         int n_k_needed, int k_buffer, double min_eig_val, double tol, int max_outer,
+                         int block_size, double* eig_vals, double* eig_vecs, int ldv, int* result_i_host,
+                         double* result_d_host, void* workspace, size_t workspace_bytes,
+                         focusr_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  FB_REQUIRE(n_points > 0 && n_meshes > 0 && k >= 1 && n_k_needed >= 1 && ldv >= 1, "eigs: bad sizes");
+  FB_REQUIRE(mesh_point_off_host[0] == 0 && mesh_point_off_host[n_meshes] == n_points,
+             "eigs: mesh offsets must cover [0, n_points)");
+  int max_oneway = 0, max_zero = 0, max_rows = 0;
+  for (int m = 0; m < n_meshes; ++m) {
+    max_oneway = std::max(max_oneway, mesh_info_host[4 * m + 1]);
+    max_zero = std::max(max_zero, mesh_info_host[4 * m + 2]);
+    max_rows = std::max(max_rows, mesh_point_off_host[m + 1] - mesh_point_off_host[m]);
+    FB_REQUIRE(mesh_info_host[4 * m + 3] == 0,
+               "eigs: mesh %d has %d non-finite edge weights (zero-length edges, graph.py:177-178)", m,
+               mesh_info_host[4 * m + 3]);
+  }
+  const int B = block_size > 0 ? block_size
+                               : focusr_eigs_block_size(k, n_k_needed, k_buffer, max_oneway, max_zero);
+  FB_REQUIRE(spmm_block_supported(B), "eigs: block size %d unsupported (multiples of 8 up to 96)", B);
+  FB_REQUIRE(max_rows > B, "eigs: a mesh has fewer vertices (%d) than the block size (%d)", max_rows, B);
+
+  SolveParams p;
+  p.k0 = k;
+  p.n_needed = n_k_needed;
+  p.k_buffer = k_buffer;
+  p.min_eig = min_eig_val;
+  p.tol = tol > 0.0 ? tol : 1e-10;
+  p.max_outer = max_outer > 0 ? max_outer : 60;
+  p.amp_target = 1e3;
+  p.max_degree = 16384;
+  p.beta = 2.0;
+  p.ldv = ldv;
+
+  // contiguous runs of meshes with the same symmetry class are solved as one batch
+  int rc_all = FB_OK;
+  std::vector<MeshResult> results(n_meshes);
+  int m0 = 0;
+  while (m0 < n_meshes) {
+    const bool sym = mesh_info_host[4 * m0 + 1] == 0;
+    int m1 = m0 + 1;
+    while (m1 < n_meshes && (mesh_info_host[4 * m1 + 1] == 0) == sym) ++m1;
+    const int M = m1 - m0;
+    CudaBackend be;
+    be.g = SpmmGraph{row_ptr, cols, weights, degree, degree_inv, nullptr, M, 0};
+    int run_max = 0;
+    for (int m = m0; m < m1; ++m)
+      run_max = std::max(run_max, mesh_point_off_host[m + 1] - mesh_point_off_host[m]);
+    be.g.max_mesh_rows = run_max;
+    const int run_rows = mesh_point_off_host[m1] - mesh_point_off_host[m0];
+    const size_t need = eigs_ws_layout(run_rows, M, run_max, B, &be, workspace, workspace_bytes);
+    if (need > workspace_bytes) {
+      set_error("eigs: workspace too small (%zu < %zu)", workspace_bytes, need);
+      return FB_ERR_WORKSPACE;
+    }
+    // X/Y/Xn index rows globally: shift the base so that row r of the batch maps into the run's block
+    const size_t shift = (size_t)mesh_point_off_host[m0] * B;
+    be.X -= shift;
+    be.Y -= shift;
+    be.Xn -= shift;
+    be.points = points;
+    be.off_host = mesh_point_off_host + m0;
+    be.info_host = mesh_info_host + 4 * m0;
+    be.M = M;
+    be.B = B;
+    be.mesh_base = m0;
+    be.sym = sym;
+    be.stream = stream;
+    be.eig_vals = eig_vals;
+    be.eig_vecs = eig_vecs;
+    be.ldv = ldv;
+    FB_CUDA(cudaMemcpyAsync(const_cast<int*>(be.g.mesh_off), mesh_point_off_host + m0, sizeof(int) * (M + 1),
+                            cudaMemcpyHostToDevice, stream));
+    const int rc = chfsi_solve(be, p, results.data() + m0);
+    if (be.err != FB_OK) return be.err;
+    FB_CUDA(cudaStreamSynchronize(stream));
+    for (int m = m0; m < m1; ++m) {
+      int* ri = result_i_host + 8 * m;
+      ri[0] = results[m].status;
+      ri[1] = results[m].n_out;
+      ri[2] = results[m].k_final;
+      ri[3] = results[m].outer_iters;
+      ri[4] = results[m].total_degree;
+      ri[5] = B;
+      ri[6] = sym ? 1 : 0;
+      ri[7] = 0;
+      result_d_host[2 * m] = results[m].max_residual;
+      result_d_host[2 * m + 1] = 0.0;
+    }
+    rc_all = std::max(rc_all, rc);
+    m0 = m1;
+  }
+  if (rc_all != FB_OK)
+    set_error("eigs: solver status %d (1 not converged, 2 block too small, 3 breakdown, 4 ldv too small); "
+              "see result_i_host", rc_all);
+  return rc_all;
+}
+}

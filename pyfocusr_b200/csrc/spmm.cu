@@ -1,0 +1,277 @@
+// CSR x dense-block kernels: the hot loop of the eigen-solver (one fused SpMM + Chebyshev
+// three-term update per filter degree) and the graph smoothing of Graph.mean_filter_graph.
+//
+// Layout: the block of b vectors is row-major [n_points][b], so gathering neighbour j's row is one
+// contiguous 8*b-byte read (128 B for b = 16 = one L2 line) and the matrix (int32 column + fp64
+// weight per stored entry) is streamed exactly once per pass.  TPR threads cooperate on a row,
+// each owning b/(2*TPR) double2 slices; all TPR threads read the same (col, weight) entry, which
+// the LSU serves as one broadcast.  Algorithmic bytes per filter degree and mesh:
+// 12*nnz + 16*N (degree, 1/degree~) + 3 * 8*b*N (read Y, read X_prev, write X_next).
+//
+// These paths are HBM/L2-bandwidth-bound fp64 work with ~0.3 flop/byte; there is no GEMM shape
+// here, so no tensor cores (see DESIGN.md "what bounds each kernel").
+#include "common.cuh"
+#include "rowops.h"
+#include "spmm.cuh"
+
+namespace fb {
+
+constexpr int SPMM_THREADS = 256;
+constexpr int SPMM_ROWS_PER_BLOCK = 256;
+
+// MODE 0: out = alpha * (L y - c y) - gamma * x_prev        (Chebyshev step)
+// MODE 1: out = (D - A) y
+// MODE 2: out = L y = dinv * (D - A) y
+template <int B, int TPR, int MODE>
+__global__ void __launch_bounds__(SPMM_THREADS)
+k_spmm(const int* __restrict__ row_ptr, const int* __restrict__ cols, const double* __restrict__ weights,
+       const double* __restrict__ degree, const double* __restrict__ degree_inv,
+       const int* __restrict__ mesh_off, const double* __restrict__ y, const double* __restrict__ x_prev,
+       double* __restrict__ out, const double* __restrict__ alpha, const double* __restrict__ gamma,
+       const double* __restrict__ center, int step, int n_steps) {
+  constexpr int VPT = B / (2 * TPR);
+  static_assert(VPT * 2 * TPR == B, "block size must be a multiple of 2*TPR");
+  const int mesh = blockIdx.y;
+  const int r0 = mesh_off[mesh] + blockIdx.x * SPMM_ROWS_PER_BLOCK;
+  const int r1 = min(mesh_off[mesh + 1], r0 + SPMM_ROWS_PER_BLOCK);
+  if (r0 >= r1) return;
+  double al = 1.0, ga = 0.0, cc = 0.0;
+  if (MODE == 0) {
+    al = alpha[(size_t)mesh * n_steps + step];
+    ga = gamma[(size_t)mesh * n_steps + step];
+    cc = center[mesh];
+  }
+  const int g = threadIdx.x / TPR, t = threadIdx.x % TPR;
+  for (int row = r0 + g; row < r1; row += SPMM_THREADS / TPR) {
+    double2 acc[VPT];
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) acc[v] = make_double2(0.0, 0.0);
+    const int p0 = row_ptr[row], p1 = row_ptr[row + 1];
+#pragma unroll 4
+    for (int p = p0; p < p1; ++p) {
+      const int c = cols[p];
+      const double w = weights[p];
+      const double2* src = reinterpret_cast<const double2*>(y + (size_t)c * B);
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) {
+        const double2 a = __ldg(src + t + v * TPR);
+        acc[v].x = fma(w, a.x, acc[v].x);
+        acc[v].y = fma(w, a.y, acc[v].y);
+      }
+    }
+    const double d = degree[row];
+    const double di = degree_inv[row];
+    const double2* yr = reinterpret_cast<const double2*>(y + (size_t)row * B);
+    const double2* xr = reinterpret_cast<const double2*>(x_prev + (size_t)row * B);
+    double2* o = reinterpret_cast<double2*>(out + (size_t)row * B);
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      const double2 yv = __ldg(yr + t + v * TPR);
+      double2 r;
+      if (MODE == 1) {
+        r.x = d * yv.x - acc[v].x;
+        r.y = d * yv.y - acc[v].y;
+      } else if (MODE == 2) {
+        r.x = di * (d * yv.x - acc[v].x);
+        r.y = di * (d * yv.y - acc[v].y);
+      } else {
+        const double lx = di * (d * yv.x - acc[v].x);
+        const double ly = di * (d * yv.y - acc[v].y);
+        r.x = al * (lx - cc * yv.x);
+        r.y = al * (ly - cc * yv.y);
+        if (ga != 0.0) {  // step 0 has no predecessor: x_prev may be uninitialised memory
+          const double2 xv = __ldg(xr + t + v * TPR);
+          r.x -= ga * xv.x;
+          r.y -= ga * xv.y;
+        }
+      }
+      o[t + v * TPR] = r;
+    }
+  }
+}
+
+template <int B, int TPR>
+static int launch_spmm_b(int mode, const SpmmGraph& g, const double* y, const double* x_prev, double* out,
+                         const double* alpha, const double* gamma, const double* center, int step,
+                         int n_steps, cudaStream_t stream) {
+  dim3 grid(div_up(g.max_mesh_rows, SPMM_ROWS_PER_BLOCK), g.n_meshes);
+  if (mode == 0)
+    k_spmm<B, TPR, 0><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv,
+                                                         g.mesh_off, y, x_prev, out, alpha, gamma, center, step, n_steps);
+  else if (mode == 1)
+    k_spmm<B, TPR, 1><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv,
+                                                         g.mesh_off, y, x_prev, out, alpha, gamma, center, step, n_steps);
+  else
+    k_spmm<B, TPR, 2><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv,
+                                                         g.mesh_off, y, x_prev, out, alpha, gamma, center, step, n_steps);
+  FB_COUNT_LAUNCH(1);
+  return FB_OK;
+}
+
+bool spmm_block_supported(int b) {
+  switch (b) {
+    case 8: case 16: case 24: case 32: case 40: case 48: case 56: case 64: case 72: case 80: case 88: case 96:
+      return true;
+    default:
+      return false;
+  }
+}
+
+int launch_spmm(int mode, int b, const SpmmGraph& g, const double* y, const double* x_prev, double* out,
+                const double* alpha, const double* gamma, const double* center, int step, int n_steps,
+                cudaStream_t stream) {
+#define FB_CASE(BB, TT) \
+  case BB:              \
+    return launch_spmm_b<BB, TT>(mode, g, y, x_prev, out, alpha, gamma, center, step, n_steps, stream);
+  switch (b) {
+    FB_CASE(8, 4)
+    FB_CASE(16, 8)
+    FB_CASE(24, 4)
+    FB_CASE(32, 8)
+    FB_CASE(40, 4)
+    FB_CASE(48, 8)
+    FB_CASE(56, 4)
+    FB_CASE(64, 16)
+    FB_CASE(72, 4)
+    FB_CASE(80, 8)
+    FB_CASE(88, 4)
+    FB_CASE(96, 16)
+    default:
+      set_error("spmm: unsupported block size %d (multiples of 8 up to 96)", b);
+      return FB_ERR_UNSUPPORTED;
+  }
+#undef FB_CASE
+}
+
+// ---------------------------------------------------------------------------------------------
+// Graph.mean_filter_graph (graph.py:349-354).  scipy stores each row of
+// average_mat = diag(1/(1+d)) @ (A + I) in DESCENDING column order and `average_mat @ x`
+// accumulates y += a*x in stored order (multiply, then add); one thread per row walks the row of A
+// backwards and splices the diagonal in at its sorted position, which reproduces that bit for bit.
+// ---------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256)
+k_mean_filter(const int* __restrict__ row_ptr, const int* __restrict__ cols, const double* __restrict__ weights,
+              const double* __restrict__ degree, int row_begin, int row_end, const double* __restrict__ x,
+              double* __restrict__ out, int n_cols_rt) {
+  const int i = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= row_end) return;
+  const int nc = C > 0 ? C : n_cols_rt;
+  const double dsm = FB_DIV(1.0, FB_ADD(1.0, degree[i]));
+  const int p0 = row_ptr[i], p1 = row_ptr[i + 1];
+  constexpr int CMAX = C > 0 ? C : 8;
+  double acc[CMAX];
+#pragma unroll
+  for (int k = 0; k < CMAX; ++k) acc[k] = 0.0;
+  bool diag_done = false;
+  for (int p = p1 - 1; p >= p0; --p) {
+    const int j = cols[p];
+    if (!diag_done && j < i) {
+      const double* xi = x + (size_t)i * nc;
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k)
+        if (k < nc) acc[k] = FB_ADD(acc[k], FB_MUL(dsm, xi[k]));
+      diag_done = true;
+    }
+    double val;
+    if (j == i) {
+      val = FB_MUL(dsm, FB_ADD(weights[p], 1.0));
+      diag_done = true;
+    } else {
+      val = FB_MUL(dsm, weights[p]);
+    }
+    const double* xj = x + (size_t)j * nc;
+#pragma unroll
+    for (int k = 0; k < CMAX; ++k)
+      if (k < nc) acc[k] = FB_ADD(acc[k], FB_MUL(val, xj[k]));
+  }
+  if (!diag_done) {
+    const double* xi = x + (size_t)i * nc;
+#pragma unroll
+    for (int k = 0; k < CMAX; ++k)
+      if (k < nc) acc[k] = FB_ADD(acc[k], FB_MUL(dsm, xi[k]));
+  }
+  double* o = out + (size_t)i * nc;
+#pragma unroll
+  for (int k = 0; k < CMAX; ++k)
+    if (k < nc) o[k] = acc[k];
+}
+
+__global__ void k_gather_rows(const double* __restrict__ in, const long long* __restrict__ idx,
+                              const int* __restrict__ idx_base, int n_rows, int n_cols,
+                              double* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n_rows * n_cols) return;
+  const int i = (int)(t / n_cols), k = (int)(t - (long long)i * n_cols);
+  const long long src = idx[i] + (idx_base ? idx_base[i] : 0);
+  out[t] = in[src * n_cols + k];
+}
+
+__global__ void k_copy_rows(const double* __restrict__ in, double* __restrict__ out, long long begin, long long end) {
+  const long long t = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < end) out[t] = in[t];
+}
+
+}  // namespace fb
+
+using namespace fb;
+
+extern "C" {
+
+int focusr_mean_filter(const int* row_ptr, const int* cols, const double* weights, const double* degree,
+                       int row_begin, int row_end, const double* values_in, double* values_out,
+                       double* scratch, int n_cols, int iterations, focusr_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  FB_REQUIRE(row_end > row_begin && n_cols >= 1 && n_cols <= 8 && iterations >= 0,
+             "mean_filter: need rows, 1 <= n_cols <= 8, iterations >= 0");
+  const int n = row_end - row_begin;
+  const int T = 256;
+  if (iterations == 0) {
+    const long long b = (long long)row_begin * n_cols, e = (long long)row_end * n_cols;
+    k_copy_rows<<<div_up(e - b, T), T, 0, stream>>>(values_in, values_out, b, e);
+    FB_COUNT_LAUNCH(1);
+    FB_LAUNCH_CHECK();
+    return FB_OK;
+  }
+  // ping-pong so that the last iteration writes values_out
+  const double* src = values_in;
+  for (int it = 0; it < iterations; ++it) {
+    double* dst = ((iterations - 1 - it) % 2 == 0) ? values_out : scratch;
+    if (n_cols == 3)
+      k_mean_filter<3><<<div_up(n, T), T, 0, stream>>>(row_ptr, cols, weights, degree, row_begin, row_end, src, dst, 3);
+    else if (n_cols == 1)
+      k_mean_filter<1><<<div_up(n, T), T, 0, stream>>>(row_ptr, cols, weights, degree, row_begin, row_end, src, dst, 1);
+    else
+      k_mean_filter<0><<<div_up(n, T), T, 0, stream>>>(row_ptr, cols, weights, degree, row_begin, row_end, src, dst, n_cols);
+    src = dst;
+  }
+  FB_COUNT_LAUNCH(iterations);
+  FB_LAUNCH_CHECK();
+  return FB_OK;
+}
+
+int focusr_gather_rows(const double* in, const long long* idx, const int* idx_base, int n_rows, int n_cols,
+                       double* out, focusr_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  FB_REQUIRE(n_rows > 0 && n_cols > 0, "gather_rows: empty");
+  const int T = 256;
+  k_gather_rows<<<div_up((long long)n_rows * n_cols, T), T, 0, stream>>>(in, idx, idx_base, n_rows, n_cols, out);
+  FB_COUNT_LAUNCH(1);
+  FB_LAUNCH_CHECK();
+  return FB_OK;
+}
+
+int focusr_laplacian_apply(const int* row_ptr, const int* cols, const double* weights, const double* degree,
+                           const double* degree_inv, const int* mesh_point_off, int n_meshes,
+                           int max_mesh_points, const double* x, double* y, int n_cols,
+                           focusr_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  FB_REQUIRE(n_meshes > 0 && max_mesh_points > 0 && spmm_block_supported(n_cols),
+             "laplacian_apply: n_cols must be a multiple of 8 up to 96");
+  SpmmGraph g{row_ptr, cols, weights, degree, degree_inv, mesh_point_off, n_meshes, max_mesh_points};
+  int rc = launch_spmm(2, n_cols, g, x, x, y, nullptr, nullptr, nullptr, 0, 0, stream);
+  if (rc) return rc;
+  FB_LAUNCH_CHECK();
+  return FB_OK;
+}
+}
