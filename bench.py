@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""Headline benchmark: spectral-embed pairs/sec @15k vertices (BASELINE.json `metric`).
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): synthetic
+perturbed-ellipsoid pairs, geodesic frequency nu=39 -> 15 212 vertices / 30 420 triangles per mesh,
+Focusr defaults (n_spectral_features=3 + 3 extra -> k=7, 5000 ordering samples, 300 + 40 smoothing
+passes), CPD = identity (out of scope).  One "step" = the whole hot path
+(Laplacian assembly -> eigensolve -> normalise -> eigsort -> spectral coords -> KNN -> smoothing ->
+KNN -> k=3 weighted positions) over `--pairs-per-gpu` pairs on every GPU; ranks hold independent
+pairs (no data-path collective), so scaling is weak and 8 GPUs x 128 pairs is the named 1024-pair batch.
+
+  python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1, one rank per GPU)
+  python bench.py --impl reference ...                      the reference's CPU path (oracle port,
+                                                            scipy ARPACK/SuperLU/cKDTree) on all host cores
+
+Prints ONE JSON line (rank 0).  `value` = pairs/s with the vertices already resident in HBM;
+`e2e` = the same through the public API from pinned host buffers with the result read back.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NU = 39
+N_SPECTRAL, N_EXTRA, N_SAMPLES, SMOOTH_T, SMOOTH_S = 3, 3, 5000, 300, 40
+
+
+def make_pairs(n_pairs, first_pair, nu=NU):
+    """Host arrays for `n_pairs` pairs: points [2P*N,3] (targets then sources), global tris, offsets."""
+    from pyfocusr_b200.mesh import icosphere, perturbed_ellipsoid
+
+    base = icosphere(nu)
+    n, f = base.points.shape[0], base.tris.shape[0]
+    pts = np.empty((2 * n_pairs, n, 3))
+    for p in range(n_pairs):
+        i = first_pair + p
+        pts[p] = perturbed_ellipsoid(nu, 2 * i, base=base).points            # target seed 2i
+        pts[n_pairs + p] = perturbed_ellipsoid(nu, 2 * i + 1, base=base).points  # source seed 2i+1
+    off = (np.arange(2 * n_pairs + 1, dtype=np.int64) * n).astype(np.int32)
+    tris = (base.tris.astype(np.int64)[None] + off[:-1, None, None]).reshape(-1, 3).astype(np.int32)
+    return pts.reshape(-1, 3), tris, off, n, f, base
+
+
+def cpu_pair(args):
+    """One pair through the CPU oracle (reference algorithm; see oracle/port.py header)."""
+    i, nu = args
+    from oracle import port
+    from pyfocusr_b200.mesh import icosphere, perturbed_ellipsoid
+
+    base = icosphere(nu)
+    t, s = perturbed_ellipsoid(nu, 2 * i, base=base), perturbed_ellipsoid(nu, 2 * i + 1, base=base)
+    np.random.seed(i)
+    t0 = time.perf_counter()
+    port.spectral_stage(t.points, t.tris, s.points, s.tris, N_SPECTRAL, N_EXTRA, N_SAMPLES,
+                        graph_smoothing_iterations=SMOOTH_T, projection_smooth_iterations=SMOOTH_S)
+    return time.perf_counter() - t0
+
+
+def config_dict(pairs_per_gpu, nu, n):
+    return {"workload": "configs[2]: synthetic perturbed-ellipsoid pairs, nu=%d (%d vertices/mesh), Focusr defaults "
+                        "(k=7, 5000 samples, smoothing 300/40), CPD=identity" % (nu, n),
+            "pairs_per_gpu_per_step": pairs_per_gpu, "vertices_per_mesh": n,
+            "l2": "working set >> L2 (batched CSR + blocks ~ %.1f GB per GPU): no flush needed" % (pairs_per_gpu * 2 * 12e6 / 1e9)}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+
+    from pyfocusr_b200.mesh import icosphere
+
+    cores = os.cpu_count() or 1
+    n = icosphere(a.nu).points.shape[0]
+    pairs_per_step = cores
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for w in range(a.warmup):
+            pool.map(cpu_pair, [(w * pairs_per_step + j, a.nu) for j in range(min(2, pairs_per_step))])
+        t0 = time.perf_counter()
+        for s in range(a.steps):
+            pool.map(cpu_pair, [(1000 + s * pairs_per_step + j, a.nu) for j in range(pairs_per_step)])
+        dt = time.perf_counter() - t0
+    value = a.steps * pairs_per_step / dt
+    sample = "%d pairs per step, one pair per process on %d host cores (scipy eigs/cKDTree are single-threaded)" % (
+        pairs_per_step, cores)
+    line = {"impl": "reference", "metric": "spectral-embed pairs/sec @15k verts", "value": value, "unit": "pairs/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(a.pairs_per_gpu, a.nu, n),
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for ln in self.f.read().strip().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        os.unlink(self.f.name)
+        return out
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    from pyfocusr_b200 import SpectralBatch, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    P = a.pairs_per_gpu
+    pts, tris, off, n, f, _ = make_pairs(P, rank * P, a.nu)
+    pts_pin = torch.from_numpy(pts).pin_memory()
+    tris_dev = torch.from_numpy(tris).cuda()
+    pts_dev = pts_pin.cuda()
+    sb = SpectralBatch(N_SPECTRAL, N_EXTRA, N_SAMPLES, SMOOTH_T, SMOOTH_S, seed=rank)
+    rng = np.random.RandomState(rank)
+    sizes = np.diff(off)
+    idx_t, idx_s = sb.sample_indices(sizes[:P], rng), sb.sample_indices(sizes[P:], rng)
+    lib = _lib.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return sb.run(pts_dev, tris_dev, off, P, idx_t=idx_t, idx_s=idx_s)
+
+    h2d = pts_pin.numel() * 8
+    d2h = [0]
+
+    def step_e2e():
+        out = sb.run(pts_pin, tris_dev, off, P, idx_t=idx_t, idx_s=idx_s)  # H2D of the vertices inside
+        fi = out["final_idx"].cpu()
+        wp = out["weighted_avg_transformed_points"].cpu()
+        d2h[0] = fi.numel() * 8 + wp.numel() * 8
+        return out
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(a.warmup):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    lib.focusr_profile_reset()
+    l0 = _lib.launch_count()
+    ms = timed(step_resident, a.steps)
+    launches = _lib.launch_count() - l0
+    prof = np.zeros(4)
+    lib.focusr_profile_get(prof.ctypes.data)
+    clocks = sampler.stop() if sampler else None
+    step_e2e()
+    ms_e2e = timed(step_e2e, a.steps)
+    # per-stage breakdown (one extra, untimed step)
+    sb.run(pts_dev, tris_dev, off, P, idx_t=idx_t, idx_s=idx_s, record_events=True)
+    stages = {k: round(v, 3) for k, v in sb.timings.items()}
+    lt = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(lt)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    value = world * P * a.steps / (ms / 1e3)
+    e2e = world * P * a.steps / (ms_e2e / 1e3)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    achieved = prof[2] / (prof[0] / 1e3) / 1e9 if prof[0] > 0 else None
+    roofline = {"kernel": "k_spmm<16,8,0> (Chebyshev filter step: CSR SpMM + three-term update)", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                "traffic": None, "peak_source": peak_src, "launches": int(prof[1]),
+                "avg_launch_ms": (prof[0] / prof[1]) if prof[1] else None,
+                "bytes_per_launch": (prof[2] / prof[1]) if prof[1] else None,
+                "share_of_step": (prof[0] / ms) if ms else None}
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        t0 = time.perf_counter()
+        times = [cpu_pair((5000 + j, a.nu)) for j in range(a.cpu_pairs)]
+        cpu = {"value": len(times) / sum(times), "unit": "pairs/s", "cores": 1, "kind": "port",
+               "sample": "%d pairs of the same workload, oracle/port.py (reference algorithm: scipy eigs shift-invert, "
+                         "cKDTree, sparse smoothing) in one process, %.1f s" % (len(times), time.perf_counter() - t0)}
+    line = {"metric": "spectral-embed pairs/sec @15k verts", "value": value, "unit": "pairs/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(P, a.nu, n), "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h[0] * world,
+                    "ms_per_step": ms_e2e / a.steps},
+            "gpu_launches": int(lt.item()), "roofline": roofline, "cpu_baseline": cpu, "stage_ms": stages}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs-per-gpu", type=int, default=128)
+    ap.add_argument("--nu", type=int, default=NU)
+    ap.add_argument("--cpu-pairs", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    return run_reference(a) if a.impl == "reference" else run_ours(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

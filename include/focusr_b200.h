@@ -90,9 +90,16 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
                          int n_points, const int* mesh_point_off_host, int n_meshes,
                          const int* mesh_info_host, int k, int n_k_needed, int k_buffer,
                          double min_eig_val, double tol, int max_outer, int block_size,
+                         double spectrum_upper_bound,
                          double* eig_vals, double* eig_vecs, int ldv, int* result_i_host,
                          double* result_d_host, void* workspace, size_t workspace_bytes,
                          focusr_stream_t stream);
+
+/* Live profile of the dominant kernel, the Chebyshev SpMM filter step (CUDA events on the launching
+ * stream around every filter application since the last reset): out4_host = {milliseconds,
+ * launches, algorithmic bytes (12 nnz + 20 N + 24 b N per launch), 0}.  bench.py's roofline line. */
+void focusr_profile_reset(void);
+void focusr_profile_get(double* out4_host);
 
 /* y = L x for a dense block of n_cols vectors (n_cols a multiple of 8, <= 96), used by tests and
  * residual checks: y[i][:] = dinv_i (d_i x_i - sum_j w_ij x_j). */

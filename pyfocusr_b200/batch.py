@@ -1,0 +1,165 @@
+"""Batched spectral-correspondence stage: many (target, source) mesh pairs per launch.
+
+This is the throughput path of BASELINE.json config 3 ("batch of 1024 synthetic 15k-vertex mesh
+pairs sharded across 1/2/4/8 B200").  It is the same sequence ``Focusr.__init__`` +
+``Focusr.align_maps`` run for one pair (reference focusr.py:134-169, 514-562, CPD = identity as
+in BASELINE.md section 3), but every kernel works on the block-diagonal graph of all 2P meshes, so
+one SpMM launch streams gigabytes instead of 1.3 MB and nothing but the n x n eigsort decisions
+(P x 36 numbers) visits the host between the upload of the vertices and the download of the
+correspondences.
+
+Mesh order inside the batch graph: targets 0..P-1, then sources 0..P-1.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _device, _lib
+from ._device import DeviceGraph
+from .eigsort import c_lambda_matrix, decide_matches, moves_from_matches
+
+__all__ = ["SpectralBatch"]
+
+
+class SpectralBatch:
+    def __init__(self, n_spectral_features=3, n_extra_spectral=3, n_coords_spectral_ordering=5000,
+                 graph_smoothing_iterations=300, projection_smooth_iterations=40,
+                 target_eigenmap_as_reference=True, get_weighted_spectral_coords=True, tol=1e-10,
+                 block_size=0, seed=0):
+        self.ns = int(n_spectral_features)
+        self.n = int(n_spectral_features + n_extra_spectral)
+        self.n_samples = int(n_coords_spectral_ordering)
+        self.graph_smoothing_iterations = int(graph_smoothing_iterations)
+        self.projection_smooth_iterations = int(projection_smooth_iterations)
+        self.target_as_reference = bool(target_eigenmap_as_reference)
+        self.weighted = bool(get_weighted_spectral_coords)
+        self.tol = float(tol)
+        self.block_size = int(block_size)
+        self.seed = int(seed)
+        self.timings = {}
+
+    # ------------------------------------------------------------------------------------------
+    def sample_indices(self, sizes, rng=None):
+        """Graph.get_list_rand_idxs (graph.py:274-290) for every mesh; all meshes must yield the
+        same count (n_samples <= every size, or n_samples > every size)."""
+        rng = rng or np.random.RandomState(self.seed)
+        out = []
+        for sz in sizes:
+            if self.n_samples > sz:
+                out.append(np.arange(sz, dtype=np.int64))
+            else:
+                out.append(rng.choice(sz, size=self.n_samples, replace=False).astype(np.int64))
+        lens = {len(o) for o in out}
+        if len(lens) != 1:
+            raise ValueError("meshes of a batch must yield the same number of ordering samples")
+        return np.stack(out)
+
+    # ------------------------------------------------------------------------------------------
+    def run(self, points, tris, mesh_off_host, n_pairs, idx_t=None, idx_s=None, record_events=False,
+            keep_presort=False):
+        """points: torch tensor [n_points_total, 3] float64 (host pinned or device), meshes in the
+        order targets then sources; tris: int32 [n_tris_total, 3] with GLOBAL vertex ids;
+        mesh_off_host: int32 [2P+1].  Returns a dict of device tensors + host metadata."""
+        torch = _lib.require_cuda()
+        P = int(n_pairs)
+        ev = []
+
+        def mark(name):
+            if record_events:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                ev.append((name, e))
+
+        mark("start")
+        g = DeviceGraph.from_device(points, tris, mesh_off_host)
+        mark("laplacian")
+        n, ns = self.n, self.ns
+        vals, vecs, info = g.eigs_smallest(k=n + 1, n_k_needed=n, k_buffer=1, tol=self.tol,
+                                           block_size=self.block_size)
+        n_found = info["n_found"]
+        if int(n_found.min()) < n:
+            raise RuntimeError("a mesh returned fewer than %d eigenpairs" % n)
+        g.normalize_columns(vecs, n_found)
+        mark("eigensolve")
+
+        off = g.mesh_off_host
+        sizes = np.diff(off)
+        if idx_t is None:
+            rng = np.random.RandomState(self.seed)
+            idx_t = self.sample_indices(sizes[:P], rng)
+            idx_s = self.sample_indices(sizes[P:], rng)
+        t_mesh = np.arange(P, dtype=np.int32)
+        s_mesh = np.arange(P, 2 * P, dtype=np.int32)
+        ch, chf, cs, csf, _ = _device.eigsort_costs(g, vecs, t_mesh, s_mesh, idx_t, idx_s, n)
+        costs = torch.stack([ch, chf, cs, csf]).cpu().numpy()  # [4][P][n][n]
+        vals_h = vals.cpu().numpy()
+        # host: n x n decisions per pair (eigsort.py:66-105, focusr.py:459-490)
+        dst = np.tile(np.arange(n, dtype=np.int32), (2 * P, 1))
+        src = dst.copy()
+        sign = np.ones((2 * P, n), dtype=np.int32)
+        weights = np.ones((2 * P, ns))
+        Q = np.zeros((P, n))
+        for p in range(P):
+            vt = vals_h[p, : n_found[p]]
+            vs = vals_h[P + p, : n_found[P + p]]
+            cl = c_lambda_matrix(vt, vs, n)
+            q, tm, sm, flipped = decide_matches(cl, costs[0, p], costs[1, p], costs[2, p], costs[3, p],
+                                                self.target_as_reference)
+            d, s, sg = moves_from_matches(tm, sm, flipped, self.target_as_reference)
+            row = P + p if self.target_as_reference else p
+            dst[row, : len(d)], src[row, : len(d)], sign[row, : len(d)] = d, s, sg
+            Q[p] = q
+            if self.weighted:
+                w = q[:ns] * np.max((vs[:ns], vt[:ns]), axis=0)
+                w = np.exp(-(w**2) / (2 * np.mean(w) ** 2))
+                weights[p] = weights[P + p] = w
+        presort = vecs.clone() if keep_presort else None
+        g.flip_permute(vecs, dst, src, sign)
+        coords = g.spectral_coords(vecs, weights, ns)
+        mark("eigsort")
+
+        nt_total = int(off[P])
+        dev = g.device
+        ref_off = g.mesh_off[: P + 1].contiguous()
+        qry_off = (g.mesh_off[P:] - nt_total).contiguous()
+        max_q = int(sizes[P:].max())
+        # CPD would transform target coords here (out of scope; identity)
+        idx0, _ = _device.knn(coords[:nt_total], coords[nt_total:], k=1, ref_off=ref_off, query_off=qry_off,
+                              max_queries=max_q, want_dist=False)
+        mark("knn_initial")
+        smoothed_t = g.mean_filter(g.points, self.graph_smoothing_iterations, 0, nt_total)
+        base_q = torch.repeat_interleave(g.mesh_off[:P], torch.from_numpy(sizes[P:].astype(np.int64)).to(dev)).to(torch.int32)
+        staged = torch.empty_like(g.points)
+        _lib.call("focusr_gather_rows", _lib.ptr(smoothed_t), _lib.ptr(idx0), _lib.ptr(base_q), g.n_points - nt_total, 3,
+                  _lib.ptr(staged[nt_total:]), _lib.stream_ptr())
+        src_proj = g.mean_filter(staged, self.projection_smooth_iterations, nt_total, g.n_points)
+        mark("smoothing")
+        idx1, _ = _device.knn(smoothed_t[:nt_total], src_proj[nt_total:], k=1, ref_off=ref_off, query_off=qry_off,
+                              max_queries=max_q, want_dist=False)
+        idx3, dist3 = _device.knn(smoothed_t[:nt_total], src_proj[nt_total:], k=3, ref_off=ref_off, query_off=qry_off,
+                                  max_queries=max_q)
+        weighted = _device.weighted_positions(idx3, dist3, g.points, base_q)
+        nearest = _device.gather_rows(g.points, idx1[:, 0].contiguous(), base_q)
+        mark("knn_final")
+        if record_events:
+            torch.cuda.synchronize()
+            self.timings = {ev[i][0]: ev[i - 1][1].elapsed_time(ev[i][1]) for i in range(1, len(ev))}
+        return dict(graph=g, eig_vals=vals, eig_vecs=vecs, eigs_info=info, Q=Q, spectral_weights=weights[:P],
+                    coords=coords, initial_idx=idx0[:, 0], smoothed_target_coords=smoothed_t[:nt_total],
+                    source_projected_on_target=src_proj[nt_total:], final_idx=idx1[:, 0], knn3_idx=idx3,
+                    knn3_dist=dist3, weighted_avg_transformed_points=weighted,
+                    nearest_neighbor_transformed_points=nearest, idx_t=idx_t, idx_s=idx_s, costs=costs,
+                    eig_vecs_presort=presort)
+
+    # ------------------------------------------------------------------------------------------
+    def run_meshes(self, targets, sources, **kw):
+        """Convenience: lists of PolyData-like meshes (``.points``, ``.tris``)."""
+        torch = _lib.require_cuda()
+        meshes = list(targets) + list(sources)
+        sizes = [m.points.shape[0] for m in meshes]
+        off = np.zeros(len(meshes) + 1, dtype=np.int32)
+        off[1:] = np.cumsum(sizes)
+        pts = torch.from_numpy(np.ascontiguousarray(np.concatenate([m.points for m in meshes])))
+        tris = torch.from_numpy(np.ascontiguousarray(np.concatenate(
+            [m.tris.astype(np.int64) + int(o) for m, o in zip(meshes, off[:-1])]).astype(np.int32)))
+        return self.run(pts, tris, off, len(targets), **kw)

@@ -386,6 +386,43 @@ struct PinnedPool {
 };
 static thread_local PinnedPool g_pin_small, g_pin_tables;
 
+// Live profile of the dominant kernel (the Chebyshev SpMM step): CUDA events bracket every
+// filter() on the launching stream; the elapsed time is collected at the next synchronisation the
+// driver performs anyway.  bench.py turns {ms, launches, algorithmic bytes} into the roofline line.
+struct FilterProfile {
+  double ms = 0.0;
+  double launches = 0.0;
+  double bytes = 0.0;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  bool pending = false;
+  double pending_launches = 0.0, pending_bytes = 0.0;
+  void begin(cudaStream_t s) {
+    if (!e0) {
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+    }
+    collect();
+    cudaEventRecord(e0, s);
+  }
+  void end(cudaStream_t s, double n_launches, double n_bytes) {
+    cudaEventRecord(e1, s);
+    pending = true;
+    pending_launches = n_launches;
+    pending_bytes = n_bytes;
+  }
+  void collect() {  // call only after the stream has been synchronised past e1
+    if (!pending) return;
+    float t = 0.f;
+    if (cudaEventSynchronize(e1) == cudaSuccess && cudaEventElapsedTime(&t, e0, e1) == cudaSuccess) {
+      ms += t;
+      launches += pending_launches;
+      bytes += pending_bytes;
+    }
+    pending = false;
+  }
+};
+static FilterProfile g_filter_profile;
+
 template <int B>
 struct GramCfg {
   static constexpr int QT = (B <= 32) ? B / 8 : (B <= 64 ? 2 : 1);
@@ -544,6 +581,13 @@ struct CudaBackend {
     double* prev = Y;  // Y_{k-1} (unused at step 0)
     double* next = Xn;
     size_t pin_off = 0;
+    // algorithmic bytes of one step over the run: matrix once (int32 col + fp64 weight per entry,
+    // row_ptr), degree + 1/degree~, and three passes over the [rows][B] block
+    const double rows = (double)(off_host[M] - off_host[0]);
+    double nnz = 0.0;
+    for (int m = 0; m < M; ++m) nnz += info_host[4 * m];
+    const double step_bytes = 12.0 * nnz + 4.0 * rows + 16.0 * rows + 24.0 * (double)B * rows;
+    g_filter_profile.begin(stream);
     for (int s0 = 0; s0 < deg; s0 += table_cap) {
       const int len = std::min(table_cap, deg - s0);
       double* pa = pin + pin_off;
@@ -563,6 +607,7 @@ struct CudaBackend {
         next = t;
       }
     }
+    g_filter_profile.end(stream, (double)deg, (double)deg * step_bytes);
     // rotate names so that X is the filtered block again
     double* nx = cur;
     double* ny = prev;
@@ -625,6 +670,19 @@ using namespace fb;
 
 extern "C" {
 
+void focusr_profile_reset(void) {
+  g_filter_profile.collect();
+  g_filter_profile.ms = g_filter_profile.launches = g_filter_profile.bytes = 0.0;
+}
+
+void focusr_profile_get(double* out4_host) {
+  g_filter_profile.collect();
+  out4_host[0] = g_filter_profile.ms;
+  out4_host[1] = g_filter_profile.launches;
+  out4_host[2] = g_filter_profile.bytes;
+  out4_host[3] = 0.0;
+}
+
 size_t focusr_eigs_workspace_bytes(int n_points, int n_meshes, int max_mesh_points, int block_size) {
   return eigs_ws_layout(n_points, n_meshes, max_mesh_points, block_size, nullptr, nullptr, 0);
 }
@@ -647,7 +705,8 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
                          const double* degree_inv, const double* points, int n_points,
                          const int* mesh_point_off_host, int n_meshes, const int* mesh_info_host, int k,
                          int n_k_needed, int k_buffer, double min_eig_val, double tol, int max_outer,
-                         int block_size, double* eig_vals, double* eig_vecs, int ldv, int* result_i_host,
+                         int block_size, double spectrum_upper_bound, double* eig_vals, double* eig_vecs,
+                         int ldv, int* result_i_host,
                          double* result_d_host, void* workspace, size_t workspace_bytes,
                          focusr_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -677,7 +736,8 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
   p.max_outer = max_outer > 0 ? max_outer : 60;
   p.amp_target = 1e3;
   p.max_degree = 16384;
-  p.beta = 2.0;
+  // Gershgorin bound of the random-walk Laplacian: |L_ii| + sum_j |L_ij| = 2 d / (d + 1e-8) < 2
+  p.beta = spectrum_upper_bound > 0.0 ? spectrum_upper_bound : 2.0;
   p.ldv = ldv;
 
   // contiguous runs of meshes with the same symmetry class are solved as one batch
@@ -722,6 +782,7 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
     const int rc = chfsi_solve(be, p, results.data() + m0);
     if (be.err != FB_OK) return be.err;
     FB_CUDA(cudaStreamSynchronize(stream));
+    g_filter_profile.collect();
     for (int m = m0; m < m1; ++m) {
       int* ri = result_i_host + 8 * m;
       ri[0] = results[m].status;

@@ -1,0 +1,359 @@
+"""Drop-in for ``pyfocusr.Focusr`` (reference ``pyfocusr/focusr.py:22-807``) on the B200 library.
+
+Constructor signature, attribute names and method names follow the reference.  On the hot path
+ the work runs in libfocusr_b200.so: both graphs' Laplacians and spectra,
+eigsort, KNN correspondences (focusr.py:351-366), the 300 + 40 smoothing passes and the second
+KNN (focusr.py:368-396), the k=3 weighted positions (focusr.py:401-426) and the nearest-neighbour
+gather (focusr.py:428-431).  ICP (VTK) and CPD (cycpd) stay on the reference's own libraries:
+they are imported lazily and raise ImportError when absent.  The extra keyword ``registration``
+("cycpd" | "identity", after the reference's last argument) lets the spectral stage run where
+cycpd is not installed, with CPD replaced by the identity as in BASELINE.md section 3.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _device, _lib
+from .eigsort import eigsort
+from .graph import Graph
+from .mesh import PolyData
+
+__all__ = ["Focusr"]
+
+
+def print_header(message, banner_length=72):
+    print("=" * banner_length)
+    print("")
+    print(message)
+    print("")
+    print("=" * banner_length)
+
+
+def _icp_transform_vtk(target, source, transform_mode):
+    try:
+        import vtk  # type: ignore
+    except ImportError as e:  # pragma: no cover - VTK is not in this image
+        raise ImportError(
+            "icp_register_first=True needs VTK (reference vtk_functions.py:12-37); pass "
+            "icp_register_first=False for pre-aligned meshes"
+        ) from e
+    icp = vtk.vtkIterativeClosestPointTransform()
+    if transform_mode == "rigid":
+        icp.GetLandmarkTransform().SetModeToRigidBody()
+    elif transform_mode == "similarity":
+        icp.GetLandmarkTransform().SetModeToSimilarity()
+    else:
+        raise TypeError("Error invalid transform mode")
+    icp.SetTarget(target)
+    icp.SetSource(source)
+    icp.SetMaximumNumberOfIterations(100)
+    icp.StartByMatchingCentroidsOn()
+    icp.Modified()
+    icp.Update()
+    icp.SetMaximumNumberOfLandmarks(1000)
+    tf = vtk.vtkTransformPolyDataFilter()
+    tf.SetInputData(source)
+    tf.SetTransform(icp)
+    tf.Update()
+    return icp, tf.GetOutput()
+
+
+def _mesh_with_points(mesh, points):
+    """Copy of ``mesh`` with its vertices moved to ``points`` (focusr.py:605-625)."""
+    if isinstance(mesh, PolyData):
+        out = mesh.copy()
+        out.points = np.array(points, dtype=np.float64)
+        return out
+    import vtk  # type: ignore  # pragma: no cover
+
+    out = vtk.vtkPolyData()
+    out.DeepCopy(mesh)
+    pts = out.GetPoints()
+    for i in range(points.shape[0]):
+        pts.SetPoint(i, points[i])
+    return out
+
+
+class Focusr(object):
+    def __init__(
+        self,
+        vtk_mesh_target,
+        vtk_mesh_source,
+        icp_register_first=True,
+        icp_registration_mode="rigid",
+        icp_reg_target_to_source=False,
+        n_spectral_features=3,
+        n_extra_spectral=3,
+        target_eigenmap_as_reference=True,
+        norm_physical_and_spectral=True,
+        n_coords_spectral_ordering=5000,
+        n_coords_spectral_registration=5000,
+        rigid_before_non_rigid_reg=True,
+        rigid_reg_max_iterations=100,
+        rigid_tolerance=1e-8,
+        non_rigid_max_iterations=1000,
+        non_rigid_tolerance=1e-8,
+        non_rigid_alpha=0.5,
+        non_rigid_beta=3.0,
+        non_rigid_n_eigens=100,
+        include_points_as_features=False,
+        get_weighted_spectral_coords=True,
+        graph_smoothing_iterations=300,
+        feature_smoothing_iterations=40,
+        smooth_correspondences=True,
+        return_average_final_points=True,
+        return_nearest_final_points=True,
+        return_transformed_mesh=True,
+        projection_smooth_iterations=40,
+        feature_weights=None,
+        initial_correspondence_type="kd",
+        final_correspondence_type="kd",
+        list_features_to_calc=["curvature"],
+        list_features_to_get_from_mesh=[],
+        use_features_as_coords=False,
+        use_features_in_graph=False,
+        include_features_in_adj_matrix=False,
+        G_matrix_p_function="exp",
+        norm_node_features_std=True,
+        norm_node_features_cap_std=3,
+        norm_node_features_0_1=True,
+        verbose=False,
+        registration="cycpd",
+    ):
+        self.verbose = verbose
+        self.registration = registration
+        self.n_spectral_features = n_spectral_features
+        self.n_extra_spectral = n_extra_spectral
+        self.n_total_spectral_features = self.n_spectral_features + self.n_extra_spectral
+        self.target_eigenmap_as_reference = target_eigenmap_as_reference
+        self.norm_physical_and_spectral = norm_physical_and_spectral
+        self.include_points_as_features = include_points_as_features
+        self.get_weighted_spectral_coords = get_weighted_spectral_coords
+        self.feature_smoothing_iterations = feature_smoothing_iterations
+        self.n_coords_spectral_registration = n_coords_spectral_registration
+        self.rigid_before_non_rigid_reg = rigid_before_non_rigid_reg
+        self.rigid_reg_max_iterations = rigid_reg_max_iterations
+        self.rigid_tolerance = rigid_tolerance
+        self.non_rigid_max_iterations = non_rigid_max_iterations
+        self.non_rigid_tolerance = non_rigid_tolerance
+        self.non_rigid_alpha = non_rigid_alpha
+        self.non_rigid_beta = non_rigid_beta
+        self.non_rigid_n_eigens = non_rigid_n_eigens
+        self.initial_correspondence_type = initial_correspondence_type
+        self.smooth_correspondences = smooth_correspondences
+        self.return_average_final_points = return_average_final_points
+        self.return_nearest_final_points = return_nearest_final_points
+        self.graph_smoothing_iterations = graph_smoothing_iterations
+        self.projection_smooth_iterations = projection_smooth_iterations
+        self.final_correspondence_type = final_correspondence_type
+        self.return_transformed_mesh = return_transformed_mesh
+        for ctype in (initial_correspondence_type, final_correspondence_type):
+            if ctype == "hungarian":
+                raise NotImplementedError(
+                    "the O(N^3) 'hungarian' correspondence (focusr.py:340-349) is outside the B200 hot path; use 'kd'"
+                )
+            if ctype != "kd":
+                raise ValueError("correspondence type must be 'kd' or 'hungarian'")
+
+        # focusr.py:110-131 (ICP stays on VTK)
+        if icp_register_first is True:
+            if icp_reg_target_to_source is True:
+                icp, vtk_mesh_target = _icp_transform_vtk(vtk_mesh_source, vtk_mesh_target, icp_registration_mode)
+            else:
+                icp, vtk_mesh_source = _icp_transform_vtk(vtk_mesh_target, vtk_mesh_source, icp_registration_mode)
+            self._icp_transform = icp
+
+        graph_kwargs = dict(
+            n_spectral_features=self.n_total_spectral_features,
+            n_rand_samples=n_coords_spectral_ordering,
+            list_features_to_calc=list_features_to_calc,
+            list_features_to_get_from_mesh=list_features_to_get_from_mesh,
+            feature_weights=feature_weights,
+            include_features_in_G_matrix=use_features_in_graph,
+            include_features_in_adj_matrix=include_features_in_adj_matrix,
+            G_matrix_p_function=G_matrix_p_function,
+            norm_node_features_std=norm_node_features_std,
+            norm_node_features_cap_std=norm_node_features_cap_std,
+            norm_node_features_0_1=norm_node_features_0_1,
+        )
+        # focusr.py:134-169
+        self.graph_target = Graph(vtk_mesh_target, **graph_kwargs)
+        self.graph_target.get_graph_spectrum()
+        self.graph_source = Graph(vtk_mesh_source, **graph_kwargs)
+        self.graph_source.get_graph_spectrum()
+
+        # focusr.py:174-208
+        self.Q = None
+        self.spec_weights = None
+        self.spectral_weights = None
+        self.source_spectral_coords = None
+        self.target_spectral_coords = None
+        self.source_extra_features = None
+        self.target_extra_features = None
+        self.use_features_as_coords = use_features_as_coords
+        self.source_spectral_coords_after_rigid = None
+        self.source_spectral_coords_b4_reg = None
+        self.rigid_params = None
+        self.non_rigid_params = None
+        self.smoothed_target_coords = None
+        self.source_projected_on_target = None
+        self.weighted_avg_transformed_mesh = None
+        self.nearest_neighbour_transformed_mesh = None
+        self.corresponding_target_idx_for_each_source_pt = None
+        self.nearest_neighbor_transformed_points = None
+        self.weighted_avg_transformed_points = None
+        self.average_mesh = None
+
+    # ------------------------------------------------------------------ focusr.py:271-295
+    def append_pts_to_spectral_coords(self):
+        if self.norm_physical_and_spectral is True:
+            self.source_spectral_coords = np.concatenate(
+                (self.source_spectral_coords, self.graph_source.normed_points), axis=1)
+            self.target_spectral_coords = np.concatenate(
+                (self.target_spectral_coords, self.graph_target.normed_points), axis=1)
+        else:
+            self.source_spectral_coords = np.concatenate(
+                (self.source_spectral_coords * self.graph_source.mean_pts_scale_range, self.graph_source.points), axis=1)
+            self.target_spectral_coords = np.concatenate(
+                (self.target_spectral_coords * self.graph_target.mean_pts_scale_range, self.graph_target.points), axis=1)
+
+    def append_features_to_spectral_coords(self):
+        raise NotImplementedError("extra node features as coordinates (focusr.py:218-269) are outside the hot path")
+
+    # ------------------------------------------------------------------ focusr.py:297-334 (CPD: cycpd)
+    def register_target_to_source(self, reg_type="deformable"):
+        if self.registration == "identity":
+            return
+        try:
+            import cycpd  # type: ignore
+        except ImportError as e:
+            raise ImportError(
+                "CPD stays on the reference's cycpd path (focusr.py:297-334) and cycpd is not installed; "
+                "construct Focusr(..., registration='identity') to run the spectral stage without it"
+            ) from e
+        x = self.source_spectral_coords[self.graph_source.get_list_rand_idxs(self.n_coords_spectral_registration), :]
+        y = self.target_spectral_coords[self.graph_target.get_list_rand_idxs(self.n_coords_spectral_registration), :]
+        if reg_type == "deformable":
+            reg = cycpd.deformable_registration(
+                X=x, Y=y, num_eig=self.non_rigid_n_eigens, max_iterations=self.non_rigid_max_iterations,
+                tolerance=self.non_rigid_tolerance, alpha=self.non_rigid_alpha, beta=self.non_rigid_beta,
+                verbose=self.verbose)
+            _, self.non_rigid_params = reg.register()
+        elif reg_type == "affine":
+            reg = cycpd.affine_registration(X=x, Y=y, max_iterations=self.rigid_reg_max_iterations,
+                                            tolerance=self.rigid_tolerance)
+            _, self.rigid_params = reg.register()
+        self.target_spectral_coords = reg.transform_point_cloud(self.target_spectral_coords)
+
+    # ------------------------------------------------------------------ focusr.py:340-366
+    def get_hungarian_correspondence(self, target_pts, spectral_pts):
+        raise NotImplementedError("'hungarian' correspondence is outside the B200 hot path")
+
+    def get_kd_correspondence(self, target_pts, spectral_pts):
+        torch = _lib.require_cuda()
+        refs = torch.from_numpy(np.ascontiguousarray(target_pts, dtype=np.float64)).cuda()
+        qs = torch.from_numpy(np.ascontiguousarray(spectral_pts, dtype=np.float64)).cuda()
+        idx, _ = _device.knn(refs, qs, k=1, want_dist=False)
+        self.corresponding_target_idx_for_each_source_pt = idx[:, 0].cpu().numpy()
+
+    def get_initial_correspondences(self):
+        self.get_kd_correspondence(self.target_spectral_coords, self.source_spectral_coords)
+
+    # ------------------------------------------------------------------ focusr.py:368-396
+    def get_smoothed_correspondences(self):
+        self.smoothed_target_coords = self.graph_target.mean_filter_graph(
+            self.graph_target.points, iterations=self.graph_smoothing_iterations)
+        self.source_projected_on_target = self.graph_source.mean_filter_graph(
+            self.smoothed_target_coords[self.corresponding_target_idx_for_each_source_pt, :],
+            iterations=self.projection_smooth_iterations)
+        self.get_kd_correspondence(self.smoothed_target_coords, self.source_projected_on_target)
+
+    # ------------------------------------------------------------------ focusr.py:401-431
+    def get_weighted_final_node_locations(self, n_closest_pts=3):
+        if n_closest_pts != 3:
+            raise NotImplementedError("the reference only ever uses n_closest_pts=3")
+        torch = _lib.require_cuda()
+        refs = torch.from_numpy(np.ascontiguousarray(self.smoothed_target_coords)).cuda()
+        qs = torch.from_numpy(np.ascontiguousarray(self.source_projected_on_target)).cuda()
+        tp = torch.from_numpy(np.ascontiguousarray(self.graph_target.points)).cuda()
+        idx3, dist3 = _device.knn(refs, qs, k=3)
+        self.weighted_avg_transformed_points = _device.weighted_positions(idx3, dist3, tp).cpu().numpy()
+
+    def get_nearest_neighbour_final_node_locations(self):
+        self.nearest_neighbor_transformed_points = self.graph_target.points[
+            self.corresponding_target_idx_for_each_source_pt, :]
+
+    # ------------------------------------------------------------------ focusr.py:433-453
+    def get_average_shape(self, align_type="weighted"):
+        if align_type == "nearest":
+            new = self.graph_target.points[self.corresponding_target_idx_for_each_source_pt]
+        else:
+            new = self.weighted_avg_transformed_points
+        self.average_mesh = _mesh_with_points(self.graph_source.vtk_mesh, (self.graph_source.points + new) / 2)
+
+    # ------------------------------------------------------------------ focusr.py:459-508
+    def calc_c_weighting_spectral(self):
+        self.spectral_weights = self.Q[: self.n_spectral_features] * np.max(
+            (self.graph_source.eig_vals[: self.n_spectral_features],
+             self.graph_target.eig_vals[: self.n_spectral_features]), axis=0)
+        sigma = np.mean(self.spectral_weights)
+        self.spectral_weights = np.exp(-(self.spectral_weights**2) / (2 * sigma**2))
+
+    def calc_weighted_spectral_coords(self):
+        self.calc_c_weighting_spectral()
+        self.source_spectral_coords = (
+            self.graph_source.eig_vecs[:, : self.n_spectral_features] * self.spectral_weights[None, :])
+        self.target_spectral_coords = (
+            self.graph_target.eig_vecs[:, : self.n_spectral_features] * self.spectral_weights[None, :])
+
+    def calc_spectral_coords(self):
+        if self.get_weighted_spectral_coords is True:
+            self.calc_weighted_spectral_coords()
+        else:
+            self.source_spectral_coords = self.graph_source.eig_vecs[:, : self.n_spectral_features]
+            self.target_spectral_coords = self.graph_target.eig_vecs[:, : self.n_spectral_features]
+
+    # ------------------------------------------------------------------ focusr.py:514-568
+    def align_maps(self):
+        eig_map_sorter = eigsort(graph_target=self.graph_target, graph_source=self.graph_source,
+                                 n_features=self.n_total_spectral_features,
+                                 target_as_reference=self.target_eigenmap_as_reference)
+        self.Q = eig_map_sorter.sort_eigenmaps()
+        self.calc_spectral_coords()
+        if (self.graph_source.n_extra_features > 0) & (self.use_features_as_coords is True):
+            self.append_features_to_spectral_coords()
+        if self.include_points_as_features is True:
+            self.append_pts_to_spectral_coords()
+        self.source_spectral_coords_b4_reg = np.copy(self.source_spectral_coords)
+        if self.rigid_before_non_rigid_reg is True:
+            self.register_target_to_source(reg_type="affine")
+            self.source_spectral_coords_after_rigid = np.copy(self.source_spectral_coords)
+        self.register_target_to_source("deformable")
+        self.get_initial_correspondences()
+        if self.smooth_correspondences is True:
+            self.get_smoothed_correspondences()
+        if self.return_average_final_points is True:
+            self.get_weighted_final_node_locations()
+        if self.return_nearest_final_points is True:
+            self.get_nearest_neighbour_final_node_locations()
+        if self.return_transformed_mesh is True:
+            if self.return_average_final_points is True:
+                self.get_source_mesh_transformed_weighted_avg()
+            if self.return_nearest_final_points is True:
+                self.get_source_mesh_transformed_nearest_neighbour()
+
+    # ------------------------------------------------------------------ focusr.py:605-625
+    def get_source_mesh_transformed_weighted_avg(self):
+        self.weighted_avg_transformed_mesh = _mesh_with_points(
+            self.graph_source.vtk_mesh, self.weighted_avg_transformed_points)
+
+    def get_source_mesh_transformed_nearest_neighbour(self):
+        self.nearest_neighbour_transformed_mesh = _mesh_with_points(
+            self.graph_source.vtk_mesh, self.nearest_neighbor_transformed_points)
+
+    # viewers (focusr.py:646-795) need itkwidgets: out of scope
+    def view_aligned_spectral_coords(self, *a, **k):
+        raise ImportError("itkwidgets viewers are not part of the B200 hot path")
+
+    view_meshes = view_meshes_colored_by_spectral_correspondences = view_aligned_smoothed_spectral_coords = (
+        view_aligned_spectral_coords)
