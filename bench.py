@@ -33,15 +33,15 @@ NU = 39
 N_SPECTRAL, N_EXTRA, N_SAMPLES, SMOOTH_T, SMOOTH_S = 3, 3, 5000, 300, 40
 
 
-def make_pairs(n_pairs, first_pair, nu=NU):
-    """Host arrays for `n_pairs` pairs: points [2P*N,3] (targets then sources), global tris, offsets."""
+def make_pairs(pair_ids, nu=NU):
+    """Host arrays for the given pair ids: points [2P*N,3] (targets then sources), global tris, offsets."""
     from pyfocusr_b200.mesh import icosphere, perturbed_ellipsoid
 
     base = icosphere(nu)
     n, f = base.points.shape[0], base.tris.shape[0]
+    n_pairs = len(pair_ids)
     pts = np.empty((2 * n_pairs, n, 3))
-    for p in range(n_pairs):
-        i = first_pair + p
+    for p, i in enumerate(pair_ids):
         pts[p] = perturbed_ellipsoid(nu, 2 * i, base=base).points            # target seed 2i
         pts[n_pairs + p] = perturbed_ellipsoid(nu, 2 * i + 1, base=base).points  # source seed 2i+1
     off = (np.arange(2 * n_pairs + 1, dtype=np.int64) * n).astype(np.int32)
@@ -149,20 +149,17 @@ class ClockSampler:
 
 def run_ours(a):
     import torch
-    import torch.distributed as dist
 
     from pyfocusr_b200 import SpectralBatch, _lib
+    from pyfocusr_b200 import dist as fdist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, local, world = fdist.world()
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    fdist.init("nccl")
     P = a.pairs_per_gpu
-    pts, tris, off, n, f, _ = make_pairs(P, rank * P, a.nu)
+    # pair i of the global batch lives on rank i mod world; no data-path collective
+    pts, tris, off, n, f, _ = make_pairs(fdist.pair_shard(P * world, rank, world), a.nu)
     pts_pin = torch.from_numpy(pts).pin_memory()
     tris_dev = torch.from_numpy(tris).cuda()
     pts_dev = pts_pin.cuda()
@@ -172,10 +169,7 @@ def run_ours(a):
     idx_t, idx_s = sb.sample_indices(sizes[:P], rng), sb.sample_indices(sizes[P:], rng)
     lib = _lib.load()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    barrier = fdist.barrier
 
     def step_resident():
         return sb.run(pts_dev, tris_dev, off, P, idx_t=idx_t, idx_s=idx_s)
@@ -198,10 +192,7 @@ def run_ours(a):
             fn()
         e1.record()
         barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return fdist.all_reduce_max(e0.elapsed_time(e1))  # device time, slowest rank
 
     for _ in range(a.warmup):
         step_resident()
@@ -218,12 +209,9 @@ def run_ours(a):
     # per-stage breakdown (one extra, untimed step)
     sb.run(pts_dev, tris_dev, off, P, idx_t=idx_t, idx_s=idx_s, record_events=True)
     stages = {k: round(v, 3) for k, v in sb.timings.items()}
-    lt = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(lt)
+    total_launches = fdist.all_reduce_sum(launches)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        fdist.finalize()
         return 0
 
     value = world * P * a.steps / (ms / 1e3)
@@ -253,10 +241,9 @@ def run_ours(a):
             "config": config_dict(P, a.nu, n), "clocks": clocks,
             "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h[0] * world,
                     "ms_per_step": ms_e2e / a.steps},
-            "gpu_launches": int(lt.item()), "roofline": roofline, "cpu_baseline": cpu, "stage_ms": stages}
+            "gpu_launches": int(total_launches), "roofline": roofline, "cpu_baseline": cpu, "stage_ms": stages}
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    fdist.finalize()
     return 0
 
 
@@ -268,7 +255,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs-per-gpu", type=int, default=128)
     ap.add_argument("--nu", type=int, default=NU)
-    ap.add_argument("--cpu-pairs", type=int, default=3)
+    ap.add_argument("--cpu-pairs", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     return run_reference(a) if a.impl == "reference" else run_ours(a)

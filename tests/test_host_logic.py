@@ -1,0 +1,231 @@
+"""Host-side logic without a GPU: the solver driver (through the plain-loop test double in
+tests/hostsim), mesh IO / generators, eigsort's n x n decisions, and the C ABI surface."""
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+from oracle import port
+from pyfocusr_b200 import mesh as fmesh
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------------------------------------ dense kernels
+@pytest.mark.parametrize("b", [8, 16, 24, 40, 96])
+def test_rayleigh_ritz_sym_matches_lapack(hostsim, b):
+    rng = np.random.RandomState(b)
+    x = rng.standard_normal((300, b)) * np.logspace(0, 3, b)[None, :]  # graded columns, as after a filter
+    d = rng.uniform(1, 3, 300)
+    s = rng.standard_normal((300, 300))
+    g = x.T @ (d[:, None] * x)
+    h = x.T @ (s + s.T) @ x
+    h = 0.5 * (h + h.T)
+    ref = sla.eigh(h, g, eigvals_only=True)
+    gg, hh, w, th = g.copy(), h.copy(), np.zeros((b, b)), np.zeros(b)
+    rc = hostsim.hostsim_rr_sym(gg, hh, w, th, b)
+    assert rc >> 8 == 0 and (rc & 0xFF) < 30
+    assert np.max(np.abs(th - ref)) <= 1e-11 * np.max(np.abs(ref))
+    assert np.max(np.abs(w.T @ g @ w - np.eye(b))) <= 1e-10
+    assert np.all(np.diff(th) >= 0)
+
+
+@pytest.mark.parametrize("n", [2, 7, 32, 64])
+def test_eig_general_matches_numpy(hostsim, n):
+    rng = np.random.RandomState(n)
+    a = np.ascontiguousarray(rng.standard_normal((n, n)))
+    ev, vec = np.zeros(2 * n), np.zeros(2 * n * n)
+    assert hostsim.hostsim_eig_general(a, n, ev, vec) == 0
+    e = ev[0::2] + 1j * ev[1::2]
+    v = (vec[0::2] + 1j * vec[1::2]).reshape(n, n)
+    ref = np.linalg.eigvals(a)
+    assert max(np.min(np.abs(ref - x)) for x in e) <= 1e-11 * np.max(np.abs(ref))
+    assert np.max(np.abs(a @ v - v * e[None, :])) <= 1e-11 * np.max(np.abs(ref))
+
+
+def test_edge_weight_matches_numpy(hostsim):
+    rng = np.random.RandomState(0)
+    for _ in range(200):
+        p1, p2 = rng.standard_normal(3) * 50, rng.standard_normal(3) * 50
+        assert hostsim.hostsim_edge_weight(p1, p2) == 1.0 / np.sqrt(np.sum(np.square(p1 - p2)))
+
+
+# ------------------------------------------------------------------------------------------------ solver driver
+def _solve(hostsim, meshes, k0, n_needed, block, ldv=32, tol=1e-10):
+    rps, cols, ws, degs, pts, offs, zrs = [], [], [], [], [], [0], []
+    nnz = 0
+    sym = True
+    for m in meshes:
+        a = port.adjacency(m.points, m.tris)
+        deg = port.row_sums_sequential(a)
+        rps.append(a.indptr[:-1].astype(np.int64) + nnz)
+        cols.append(a.indices.astype(np.int64) + offs[-1])
+        ws.append(a.data)
+        degs.append(deg)
+        pts.append(m.points)
+        nnz += a.nnz
+        offs.append(offs[-1] + m.points.shape[0])
+        zrs.append(int(np.sum(deg == 0)))
+        pat = (a != 0).astype(np.int8)
+        sym &= (pat - pat.multiply(pat.T)).nnz == 0
+    rp = np.concatenate(rps + [np.array([nnz])]).astype(np.int32)
+    deg = np.concatenate(degs)
+    M, N = len(meshes), offs[-1]
+    vals, vecs = np.zeros((M, ldv)), np.zeros((N, ldv))
+    ri, rd = np.zeros(6 * M, np.int32), np.zeros(M)
+    rc = hostsim.hostsim_eigs(rp, np.concatenate(cols).astype(np.int32), np.concatenate(ws), deg, port.degree_inv(deg),
+                              np.ascontiguousarray(np.concatenate(pts)), N, np.array(offs, np.int32), M, int(sym),
+                              np.array(zrs, np.int32), block, k0, n_needed, 1, 1e-10, tol, 60, 1e3, 4096, 2.0, ldv,
+                              vals, vecs, ri, rd)
+    return rc, vals, vecs, ri.reshape(M, 6), offs, sym
+
+
+def _check(mesh, vals, vecs, n):
+    lap = port.laplacian(port.adjacency(mesh.points, mesh.tris))
+    rv, rvec = port.recursive_eig(lap, n + 1, n, 1)
+    o = np.argsort(rv)
+    rv, rvec = rv[o], rvec[:, o]
+    assert vals.size == rv.size
+    assert np.max(np.abs(vals - rv) / rv) <= 1e-6           # BASELINE.json tolerance
+    for i in range(rv.size):
+        r = rvec[:, i] / np.linalg.norm(rvec[:, i])
+        assert min(np.linalg.norm(vecs[:, i] - r), np.linalg.norm(vecs[:, i] + r)) <= 1e-5
+
+
+def test_driver_symmetric_batch(hostsim, shipped_meshes):
+    ms = [shipped_meshes["target_mesh"], shipped_meshes["source_mesh"]]
+    rc, vals, vecs, ri, offs, sym = _solve(hostsim, ms, 7, 6, 16)
+    assert rc == 0 and sym and ri[:, 0].tolist() == [0, 0] and ri[:, 1].tolist() == [6, 6] and ri[:, 2].tolist() == [7, 7]
+    for k, m in enumerate(ms):
+        _check(m, vals[k, :6], vecs[offs[k]:offs[k + 1], :6], 6)
+
+
+def test_driver_nonsymmetric_with_retry(hostsim, shipped_meshes):
+    """15k source: 8 one-way entries (complex eigenvalue pairs), 2 unreferenced vertices -> k=14, 11 pairs."""
+    m = shipped_meshes["source_mesh_15k"]
+    rc, vals, vecs, ri, offs, sym = _solve(hostsim, [m], 7, 6, 48)
+    assert rc == 0 and not sym and ri[0, 0] == 0 and ri[0, 1] == 11 and ri[0, 2] == 14
+    _check(m, vals[0, :11], vecs[:, :11], 6)
+
+
+def test_driver_isolated_vertices_symmetric(hostsim):
+    """Zero-degree rows are pinned and counted analytically."""
+    base = fmesh.perturbed_ellipsoid(8, 4)
+    pts = np.concatenate([base.points, [[0.0, 0.0, 0.0], [1.0, 2.0, 3.0]]])
+    m = fmesh.PolyData(pts, base.tris)
+    rc, vals, vecs, ri, offs, sym = _solve(hostsim, [m], 7, 6, 24)
+    assert rc == 0 and sym and ri[0, 2] == 14 and ri[0, 1] == 11  # 3 null eigenvalues: 14 - 3
+    _check(m, vals[0, :11], vecs[:, :11], 6)
+    assert np.all(vecs[-2:, :11] == 0.0)
+
+
+def test_driver_reports_small_block(hostsim):
+    m = fmesh.icosphere(8)  # exact 3/5/7-fold multiplets; block 16 = 1+3+5+7 cuts right at a multiplet edge
+    rc, vals, vecs, ri, offs, sym = _solve(hostsim, [m], 11, 10, 16)
+    assert ri[0, 0] in (2, 0)
+    rc, vals, vecs, ri, offs, sym = _solve(hostsim, [m], 11, 10, 32)
+    assert rc == 0 and ri[0, 1] == 10
+
+
+# ------------------------------------------------------------------------------------------------ meshes
+def test_icosphere_and_vtk_roundtrip(tmp_path):
+    for nu in (1, 2, 7):
+        s = fmesh.icosphere(nu)
+        assert s.points.shape == (10 * nu * nu + 2, 3) and s.tris.shape == (20 * nu * nu, 3)
+        assert np.allclose(np.linalg.norm(s.points, axis=1), 1.0)
+        a = port.adjacency(s.points, s.tris)
+        assert (abs(a - a.T)).nnz == 0 and a.nnz == 3 * s.tris.shape[0]  # closed, consistently oriented
+    m = fmesh.perturbed_ellipsoid(5, 1)
+    path = tmp_path / "m.vtk"
+    with open(path, "w") as f:
+        f.write("# vtk DataFile Version 4.2\nvtk output\nASCII\nDATASET POLYDATA\nPOINTS %d double\n" % m.points.shape[0])
+        f.write("\n".join(" ".join(repr(float(v)) for v in p) for p in m.points))
+        f.write("\nPOLYGONS %d %d\n" % (m.tris.shape[0], 4 * m.tris.shape[0]))
+        f.write("\n".join("3 %d %d %d" % tuple(t) for t in m.tris))
+        f.write("\nPOINT_DATA %d\nSCALARS thickness double\nLOOKUP_TABLE default\n" % m.points.shape[0])
+        f.write(" ".join("%d.5" % i for i in range(m.points.shape[0])) + "\n")
+    r = fmesh.read_vtk_mesh(str(path))
+    assert np.array_equal(r.points, m.points) and np.array_equal(r.tris, m.tris)
+    assert r.point_scalars["thickness"][3] == 3.5
+    # generic accessor path (what a foreign vtkPolyData-like object goes through)
+
+    class Foreign:
+        def __init__(self, m):
+            self._m = m
+
+        def __getattr__(self, name):
+            if name in ("points", "tris"):
+                raise AttributeError(name)
+            return getattr(self._m, name)
+
+    p, t = fmesh.mesh_arrays(Foreign(m))
+    assert np.array_equal(p, m.points) and np.array_equal(t, m.tris)
+    assert m.GetCell(0).GetEdge(2).GetPointId(1) == m.tris[0, 0]
+
+
+# ------------------------------------------------------------------------------------------------ eigsort decisions
+def test_decide_matches_and_moves(golden):
+    from pyfocusr_b200.eigsort import c_lambda_matrix, decide_matches, moves_from_matches
+
+    for tag, n in (("5k", 6), ("15k", 6), ("5k_n13", 13)):
+        cl = c_lambda_matrix(golden[tag + "_t_eig_vals"], golden[tag + "_s_eig_vals"], n)
+        assert np.array_equal(cl, golden[tag + "_c_lambda"])
+        for ref_is_target in (True, False):
+            q, tm, sm, fl = decide_matches(cl, golden[tag + "_c_hist"], golden[tag + "_c_hist_f"], golden[tag + "_c_spatial"],
+                                           golden[tag + "_c_spatial_f"], ref_is_target)
+            q2, tm2, sm2, fl2 = port.eigen_sort_decide(cl, golden[tag + "_c_hist"], golden[tag + "_c_hist_f"],
+                                                       golden[tag + "_c_spatial"], golden[tag + "_c_spatial_f"], ref_is_target)
+            assert np.array_equal(q, q2) and np.array_equal(tm, tm2) and np.array_equal(sm, sm2) and fl == fl2
+            # the (dst, src, sign) move list applied to random columns == the reference's flip + fancy-index copy
+            rng = np.random.RandomState(0)
+            vt, vs = rng.standard_normal((50, n + 2)), rng.standard_normal((40, n + 3))
+            et, es = vt.copy(), vs.copy()
+            port.eigen_sort_apply(et, es, tm, sm, fl, ref_is_target)
+            d, s, sg = moves_from_matches(tm, sm, fl, ref_is_target)
+            mine = (vs if ref_is_target else vt).copy()
+            old = mine.copy()
+            mine[:, d] = old[:, s] * sg[None, :]
+            assert np.array_equal(mine, es if ref_is_target else et)
+        if tag == "5k":
+            assert np.array_equal(q2 if not ref_is_target else q2, q2)
+
+
+# ------------------------------------------------------------------------------------------------ C ABI surface
+def test_library_exports_every_declared_symbol():
+    import ctypes
+
+    from pyfocusr_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "focusr_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(focusr_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name + " is declared in include/focusr_b200.h but not exported"
+        assert name in _lib.SIGNATURES, name + " has no ctypes signature in pyfocusr_b200/_lib.py"
+    assert sorted(_lib.SIGNATURES) == declared
+    loaded = _lib.load()
+    assert loaded.focusr_version() >= 100 and loaded.focusr_last_error() is not None
+    assert loaded.focusr_eigs_block_size(7, 6, 1, 0, 0) == 16 and loaded.focusr_eigs_block_size(7, 6, 1, 4, 2) == 40
+
+
+def test_product_never_imports_the_oracle_and_has_no_cpu_fallback():
+    pkg = os.path.join(ROOT, "pyfocusr_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn
+                assert "hostsim" not in src or fn in ("dense_small.h", "chfsi_driver.hpp", "rowops.h"), fn
+    import torch
+
+    if not torch.cuda.is_available():
+        from pyfocusr_b200 import Graph, _lib
+
+        with pytest.raises(RuntimeError):
+            _lib.require_cuda()
+        g = Graph(fmesh.icosphere(2), n_rand_samples=5)
+        with pytest.raises(RuntimeError):
+            g.get_graph_spectrum()  # fails loudly: no CPU path
