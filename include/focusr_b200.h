@@ -151,10 +151,17 @@ int focusr_eigsort_costs(const double* vecs, int ld, const double* points,
  * column order without FMA; ties go to the lower index.  Segmented: segment s searches
  * refs[ref_off[s]..ref_off[s+1]) for queries[query_off[s]..query_off[s+1]); returned indices are
  * local to the segment.  idx [n_queries][k], dist [n_queries][k] (Euclidean, nullable).
+ * With a workspace (focusr_knn_workspace_bytes) and segments of 512..16384 points the search visits
+ * Morton-ordered reference tiles and skips those whose bounding box lies beyond the current k-th
+ * best: same arithmetic, same tie rule, bit-identical output, far fewer distance evaluations.
+ * workspace = NULL selects plain brute force.
  * ------------------------------------------------------------------------------------------- */
-int focusr_knn(const double* refs, int ld_refs, const int* ref_off, const double* queries,
-               int ld_queries, const int* query_off, int n_segments, int max_queries_per_segment,
-               int dim, int k, long long* idx, double* dist, focusr_stream_t stream);
+size_t focusr_knn_workspace_bytes(int n_refs_total, int n_queries_total, int n_segments, int dim);
+int focusr_knn(const double* refs, int ld_refs, const int* ref_off, int n_refs_total,
+               int max_refs_per_segment, const double* queries, int ld_queries, const int* query_off,
+               int n_queries_total, int max_queries_per_segment, int n_segments, int dim, int k,
+               long long* idx, double* dist, void* workspace, size_t workspace_bytes,
+               focusr_stream_t stream);
 
 /* E3  get_weighted_final_node_locations (focusr.py:401-426) from the k=3 neighbours:
  * coincident neighbour -> its target point, else inverse-distance weighted mean of the three

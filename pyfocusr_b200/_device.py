@@ -199,22 +199,31 @@ class DeviceGraph:
 # ---------------------------------------------------------------------------------------------
 # free functions on device tensors
 # ---------------------------------------------------------------------------------------------
-def knn(refs, queries, k=1, ref_off=None, query_off=None, max_queries=None, want_dist=True):
+def knn(refs, queries, k=1, ref_off=None, query_off=None, max_queries=None, max_refs=None, want_dist=True,
+        brute_force=False):
     """Exact k-NN of ``queries`` in ``refs`` (device [n][dim] float64, row-major, contiguous).
-    Optional segment offset tensors (device int32) make it batched; indices are segment-local."""
+    Optional segment offset tensors (device int32) make it batched; indices are segment-local.
+    ``brute_force=True`` skips the (bit-identical) bounding-box pruning."""
     torch = _torch()
+    lib = _lib.load()
     dev = refs.device
-    nq, dim = int(queries.shape[0]), int(queries.shape[1])
+    nq, dim, nr = int(queries.shape[0]), int(queries.shape[1]), int(refs.shape[0])
     if ref_off is None:
-        ref_off = torch.tensor([0, int(refs.shape[0])], dtype=torch.int32, device=dev)
+        ref_off = torch.tensor([0, nr], dtype=torch.int32, device=dev)
         query_off = torch.tensor([0, nq], dtype=torch.int32, device=dev)
-        max_queries = nq
+        max_queries, max_refs = nq, nr
+    if max_refs is None:
+        max_refs = int(torch.diff(ref_off).max().item())
     n_seg = int(ref_off.shape[0]) - 1
     idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
     dist = torch.empty((nq, k), dtype=torch.float64, device=dev) if want_dist else None
-    _lib.call("focusr_knn", _lib.ptr(refs), int(refs.stride(0)), _lib.ptr(ref_off), _lib.ptr(queries),
-              int(queries.stride(0)), _lib.ptr(query_off), n_seg, int(max_queries), dim, int(k), _lib.ptr(idx),
-              _lib.ptr(dist), _lib.stream_ptr())
+    ws, ws_bytes = None, 0
+    if not brute_force:
+        ws_bytes = int(lib.focusr_knn_workspace_bytes(nr, nq, n_seg, dim))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _lib.call("focusr_knn", _lib.ptr(refs), int(refs.stride(0)), _lib.ptr(ref_off), nr, int(max_refs),
+              _lib.ptr(queries), int(queries.stride(0)), _lib.ptr(query_off), nq, int(max_queries), n_seg, dim,
+              int(k), _lib.ptr(idx), _lib.ptr(dist), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
     return idx, dist
 
 

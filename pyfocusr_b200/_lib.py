@@ -42,7 +42,8 @@ SIGNATURES = {
     "focusr_eigsort_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "focusr_eigsort_costs": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp,
                                   _vp, _sz, _vp]),
-    "focusr_knn": (_i, [_vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "focusr_knn_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "focusr_knn": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "focusr_weighted_positions": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
 }
 

@@ -122,10 +122,10 @@ class SpectralBatch:
         dev = g.device
         ref_off = g.mesh_off[: P + 1].contiguous()
         qry_off = (g.mesh_off[P:] - nt_total).contiguous()
-        max_q = int(sizes[P:].max())
+        max_q, max_r = int(sizes[P:].max()), int(sizes[:P].max())
         # CPD would transform target coords here (out of scope; identity)
         idx0, _ = _device.knn(coords[:nt_total], coords[nt_total:], k=1, ref_off=ref_off, query_off=qry_off,
-                              max_queries=max_q, want_dist=False)
+                              max_queries=max_q, max_refs=max_r, want_dist=False)
         mark("knn_initial")
         smoothed_t = g.mean_filter(g.points, self.graph_smoothing_iterations, 0, nt_total)
         base_q = torch.repeat_interleave(g.mesh_off[:P], torch.from_numpy(sizes[P:].astype(np.int64)).to(dev)).to(torch.int32)
@@ -134,10 +134,11 @@ class SpectralBatch:
                   _lib.ptr(staged[nt_total:]), _lib.stream_ptr())
         src_proj = g.mean_filter(staged, self.projection_smooth_iterations, nt_total, g.n_points)
         mark("smoothing")
-        idx1, _ = _device.knn(smoothed_t[:nt_total], src_proj[nt_total:], k=1, ref_off=ref_off, query_off=qry_off,
-                              max_queries=max_q, want_dist=False)
+        # one k=3 search serves both focusr.py:391-392 (k=1: its first column, same distances and tie
+        # rule) and focusr.py:409-413 (k=3)
         idx3, dist3 = _device.knn(smoothed_t[:nt_total], src_proj[nt_total:], k=3, ref_off=ref_off, query_off=qry_off,
-                                  max_queries=max_q)
+                                  max_queries=max_q, max_refs=max_r)
+        idx1 = idx3[:, :1]
         weighted = _device.weighted_positions(idx3, dist3, g.points, base_q)
         nearest = _device.gather_rows(g.points, idx1[:, 0].contiguous(), base_q)
         mark("knn_final")

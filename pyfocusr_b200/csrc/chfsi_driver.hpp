@@ -332,7 +332,18 @@ int chfsi_solve(BE& be, const SolveParams& p, MeshResult* out) {
       last_a[m] = a;
       last_alow[m] = std::min(th[0], 0.0);
       a_prev[m] = a;
-      deg = std::max(deg, cheb_degree(a, thk, p.beta, p.amp_target, p.max_degree));
+      // Amplification of the slowest wanted pair for this pass.  The residual of a Ritz pair drops by
+      // about that factor per pass, so once the block has settled (outer >= 1) the pass is sized to
+      // land a little below the tolerance in one go instead of the fixed default; the cap keeps the
+      // Gram matrix of the filtered (Ritz-rotated, hence graded) block factorisable.
+      double amp = p.amp_target;
+      const double worst = out[m].max_residual;
+      if (outer >= 1 && worst > 0.0 && worst < 1e-2) {
+        const double need = worst / (0.05 * p.tol);
+        const double cap = sym ? 1e7 : 1e4;
+        if (need <= cap) amp = std::max(need, 30.0);
+      }
+      deg = std::max(deg, cheb_degree(a, thk, p.beta, amp, p.max_degree));
     }
     if (n_done >= M) break;
     alpha.resize((size_t)M * deg);

@@ -328,6 +328,7 @@ size_t focusr_eigsort_workspace_bytes(int n_pairs, int n_samp_t, int n_samp_s, i
   b += align_up(sizeof(double) * (size_t)n_pairs * n_samp_s * 3);
   b += align_up(sizeof(double) * (size_t)n_pairs * 3 * n_features * s_max);  // sorted columns
   b += align_up(sizeof(int) * ((size_t)n_pairs + 1)) * 2;                    // segment offsets
+  b += knn_pruned_workspace_bytes((long long)n_pairs * n_samp_s, (long long)n_pairs * n_samp_t, n_pairs, 3);
   return b + 1024;
 }
 
@@ -350,6 +351,8 @@ int focusr_eigsort_costs(const double* vecs, int ld, const double* points, const
   double* sorted = cv.take<double>((size_t)n_pairs * 3 * n * s_max);
   int* q_off = cv.take<int>((size_t)n_pairs + 1);
   int* r_off = cv.take<int>((size_t)n_pairs + 1);
+  const size_t knn_bytes = knn_pruned_workspace_bytes((long long)n_pairs * n_samp_s, (long long)n_pairs * n_samp_t, n_pairs, 3);
+  char* knn_ws = cv.take<char>(knn_bytes);
   if (!cv.ok()) {
     set_error("eigsort_costs: workspace too small (%zu < %zu)", workspace_bytes, cv.used);
     return FB_ERR_WORKSPACE;
@@ -361,7 +364,12 @@ int focusr_eigsort_costs(const double* vecs, int ld, const double* points, const
   FB_COUNT_LAUNCH(3);
   FB_LAUNCH_CHECK();
   // nearest sampled source point of every sampled target point (eigsort.py:203-204)
-  int rc = launch_knn(pts_s, 3, r_off, pts_t, 3, q_off, n_pairs, n_samp_t, 3, 1, nn_idx, nullptr, stream);
+  int rc;
+  if (knn_pruned_applicable(n_samp_s, n_samp_t, 3, 1))
+    rc = launch_knn_pruned(pts_s, 3, r_off, pts_t, 3, q_off, n_pairs, n_samp_s, n_samp_t, (long long)n_pairs * n_samp_s,
+                           (long long)n_pairs * n_samp_t, 3, 1, nn_idx, nullptr, knn_ws, knn_bytes, stream);
+  else
+    rc = launch_knn(pts_s, 3, r_off, pts_t, 3, q_off, n_pairs, n_samp_t, 3, 1, nn_idx, nullptr, stream);
   if (rc) return rc;
   const size_t smem = sizeof(double) * (size_t)p2;
   static size_t attr_smem = 48 * 1024;

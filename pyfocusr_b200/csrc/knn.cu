@@ -162,9 +162,19 @@ using namespace fb;
 
 extern "C" {
 
-int focusr_knn(const double* refs, int ld_refs, const int* ref_off, const double* queries, int ld_queries,
-               const int* query_off, int n_segments, int max_queries_per_segment, int dim, int k,
-               long long* idx, double* dist, focusr_stream_t stream) {
+size_t focusr_knn_workspace_bytes(int n_refs_total, int n_queries_total, int n_segments, int dim) {
+  return knn_pruned_workspace_bytes(n_refs_total, n_queries_total, n_segments, dim);
+}
+
+int focusr_knn(const double* refs, int ld_refs, const int* ref_off, int n_refs_total, int max_refs_per_segment,
+               const double* queries, int ld_queries, const int* query_off, int n_queries_total,
+               int max_queries_per_segment, int n_segments, int dim, int k, long long* idx, double* dist,
+               void* workspace, size_t workspace_bytes, focusr_stream_t stream) {
+  FB_REQUIRE(n_segments > 0 && n_refs_total > 0 && n_queries_total > 0, "knn: empty input");
+  if (workspace != nullptr && knn_pruned_applicable(max_refs_per_segment, max_queries_per_segment, dim, k))
+    return launch_knn_pruned(refs, ld_refs, ref_off, queries, ld_queries, query_off, n_segments,
+                             max_refs_per_segment, max_queries_per_segment, n_refs_total, n_queries_total, dim, k,
+                             idx, dist, workspace, workspace_bytes, (cudaStream_t)stream);
   return launch_knn(refs, ld_refs, ref_off, queries, ld_queries, query_off, n_segments,
                     max_queries_per_segment, dim, k, idx, dist, (cudaStream_t)stream);
 }

@@ -494,3 +494,35 @@ def test_batch_equals_oracle_and_single(torch, synth):
     o1 = single.run_meshes(t[:1], s[:1], idx_t=out["idx_t"][:1], idx_s=out["idx_s"][:1])
     assert np.array_equal(o1["final_idx"].cpu().numpy(), fin[: n_s[0]])
     assert np.array_equal(o1["weighted_avg_transformed_points"].cpu().numpy(), wavg[: n_s[0]])
+
+
+def test_knn_pruned_is_bit_identical_to_brute_force(torch, shipped_meshes, synth):
+    """Morton-tile pruning must change nothing: indices AND distances equal the brute-force kernel's
+    (and the oracle's) on surfaces, clustered points with duplicates, and higher dimensions."""
+    from oracle import port
+    from pyfocusr_b200 import _device
+
+    rng = np.random.RandomState(7)
+    mt, ms = shipped_meshes["target_mesh_15k"], shipped_meshes["source_mesh_15k"]
+    cases = [(mt.points, ms.points, 3), (synth["ell39"].points, synth["ell39"].points + 0.01, 1)]
+    cl = rng.standard_normal((40, 3))[rng.randint(0, 40, 6000)] + 0.01 * rng.standard_normal((6000, 3))
+    cl[3000:3100] = cl[:100]                                   # exact duplicates -> ties
+    cases.append((cl, np.concatenate([cl[:2000], rng.standard_normal((1500, 3))]), 3))
+    cases.append((rng.standard_normal((5000, 10)) * np.logspace(0, -2, 10), rng.standard_normal((4000, 10)) * np.logspace(0, -2, 10), 3))
+    cases.append((rng.standard_normal((3000, 13)), rng.standard_normal((900, 13)), 8))
+    for refs, qs, k in cases:
+        r, q = torch.from_numpy(np.ascontiguousarray(refs)).cuda(), torch.from_numpy(np.ascontiguousarray(qs)).cuda()
+        i_p, d_p = _device.knn(r, q, k=k)
+        i_b, d_b = _device.knn(r, q, k=k, brute_force=True)
+        assert torch.equal(i_p, i_b) and torch.equal(d_p, d_b), (refs.shape, k)
+    d_ref, i_ref = port.knn_bruteforce(cases[2][0], cases[2][1], 3)
+    i_p, d_p = _device.knn(torch.from_numpy(cases[2][0]).cuda(), torch.from_numpy(cases[2][1]).cuda(), k=3)
+    assert np.array_equal(i_p.cpu().numpy(), i_ref) and np.array_equal(d_p.cpu().numpy(), d_ref)
+    # ragged batched segments through the pruned path
+    sizes_r, sizes_q = [700, 5000, 1200], [900, 600, 5000]
+    refs, qs = rng.standard_normal((sum(sizes_r), 3)), rng.standard_normal((sum(sizes_q), 3))
+    ro = torch.tensor(np.concatenate([[0], np.cumsum(sizes_r)]), dtype=torch.int32).cuda()
+    qo = torch.tensor(np.concatenate([[0], np.cumsum(sizes_q)]), dtype=torch.int32).cuda()
+    a = _device.knn(torch.from_numpy(refs).cuda(), torch.from_numpy(qs).cuda(), k=3, ref_off=ro, query_off=qo, max_queries=5000, max_refs=5000)
+    b = _device.knn(torch.from_numpy(refs).cuda(), torch.from_numpy(qs).cuda(), k=3, ref_off=ro, query_off=qo, max_queries=5000, max_refs=5000, brute_force=True)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
