@@ -168,6 +168,8 @@ def run_ours(a):
     sizes = np.diff(off)
     idx_t, idx_s = sb.sample_indices(sizes[:P], rng), sb.sample_indices(sizes[P:], rng)
     lib = _lib.load()
+    if os.environ.get("FOCUSR_SPMM_VARIANT"):  # A/B knob for kernel experiments (csrc/spmm.cu)
+        lib.focusr_set_tuning(0, int(os.environ["FOCUSR_SPMM_VARIANT"]))
 
     barrier = fdist.barrier
 

@@ -101,6 +101,10 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
 void focusr_profile_reset(void);
 void focusr_profile_get(double* out4_host);
 
+/* Tuning knobs (experiments and A/B profiling).  key 0: variant of the filter-step kernel for b = 16
+ * (0 = default; see csrc/spmm.cu). */
+int focusr_set_tuning(int key, int value);
+
 /* y = L x for a dense block of n_cols vectors (n_cols a multiple of 8, <= 96), used by tests and
  * residual checks: y[i][:] = dinv_i (d_i x_i - sum_j w_ij x_j). */
 int focusr_laplacian_apply(const int* row_ptr, const int* cols, const double* weights,

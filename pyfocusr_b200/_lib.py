@@ -33,6 +33,7 @@ SIGNATURES = {
     "focusr_eigs_block_size": (_i, [_i, _i, _i, _i, _i]),
     "focusr_eigs_smallest": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _d, _d, _i, _i, _d,
                                   _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+    "focusr_set_tuning": (_i, [_i, _i]),
     "focusr_profile_reset": (None, []),
     "focusr_profile_get": (None, [_vp]),
     "focusr_laplacian_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp]),

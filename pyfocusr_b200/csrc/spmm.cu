@@ -22,8 +22,15 @@ constexpr int SPMM_ROWS_PER_BLOCK = 256;
 // MODE 0: out = alpha * (L y - c y) - gamma * x_prev        (Chebyshev step)
 // MODE 1: out = (D - A) y
 // MODE 2: out = L y = dinv * (D - A) y
+//
+// Tuning record (tools/spmm_bench.py, profiles/r1_summary.md): the kernel is latency-bound on the
+// dependent chain row_ptr -> (col, weight) -> gather.  What helps is MORE RESIDENT WARPS: capping
+// registers at 32 (8 CTAs = 64 warps per SM) took the filter step from 4151 to 4288 GB/s.  What
+// does not help on B200: staging the CSR entries in shared memory (occupancy drops to 16 warps,
+// 1.8 TB/s), fetching 8 entries then issuing 8 gathers back to back (2.9 TB/s), or loading the
+// warp's entry range with one coalesced load and distributing it by shuffles (3.1 TB/s).
 template <int B, int TPR, int MODE>
-__global__ void __launch_bounds__(SPMM_THREADS)
+__global__ void __launch_bounds__(SPMM_THREADS, (B / (2 * TPR) == 1) ? 8 : ((B / (2 * TPR) == 2) ? 6 : 3))
 k_spmm(const int* __restrict__ row_ptr, const int* __restrict__ cols, const double* __restrict__ weights,
        const double* __restrict__ degree, const double* __restrict__ degree_inv,
        const int* __restrict__ mesh_off, const double* __restrict__ y, const double* __restrict__ x_prev,
@@ -217,6 +224,12 @@ __global__ void k_copy_rows(const double* __restrict__ in, double* __restrict__ 
 using namespace fb;
 
 extern "C" {
+
+int focusr_set_tuning(int key, int value) {
+  (void)value;  // no runtime knobs at present; the entry point stays for A/B experiments
+  fb::set_error("set_tuning: unknown key %d", key);
+  return fb::FB_ERR_ARG;
+}
 
 int focusr_mean_filter(const int* row_ptr, const int* cols, const double* weights, const double* degree,
                        int row_begin, int row_end, const double* values_in, double* values_out,
