@@ -168,8 +168,9 @@ def run_ours(a):
     sizes = np.diff(off)
     idx_t, idx_s = sb.sample_indices(sizes[:P], rng), sb.sample_indices(sizes[P:], rng)
     lib = _lib.load()
-    if os.environ.get("FOCUSR_SPMM_VARIANT"):  # A/B knob for kernel experiments (csrc/spmm.cu)
-        lib.focusr_set_tuning(0, int(os.environ["FOCUSR_SPMM_VARIANT"]))
+    for kv in os.environ.get("FOCUSR_TUNING", "").split(","):  # A/B knobs, e.g. FOCUSR_TUNING=1=64 (L2 budget MB)
+        if "=" in kv:
+            lib.focusr_set_tuning(int(kv.split("=")[0]), int(kv.split("=")[1]))
 
     barrier = fdist.barrier
 
@@ -230,6 +231,18 @@ def run_ours(a):
                 "avg_launch_ms": (prof[0] / prof[1]) if prof[1] else None,
                 "bytes_per_launch": (prof[2] / prof[1]) if prof[1] else None,
                 "share_of_step": (prof[0] / ms) if ms else None}
+    # DRAM traffic of the same kernel from an `ncu --set full` capture of this command (committed
+    # under profiles/): dram__bytes_read.sum + dram__bytes_write.sum per launch
+    tpath = os.path.join(ROOT, "profiles", "filter_traffic.json")
+    if os.path.exists(tpath):
+        rec = json.load(open(tpath)).get(str(P))
+        if rec:
+            roofline["traffic"] = rec["dram_bytes_per_launch"]
+            roofline["traffic_source"] = rec["source"]
+    knn_q = P * n  # queries per KNN call and GPU
+    secondary = {"spmv_filter_hbm_gbs": achieved,
+                 "knn_queries_per_s": {"initial_k1_d3": knn_q / (stages["knn_initial"] / 1e3) if stages.get("knn_initial") else None,
+                                       "final_k3_d3": knn_q / (stages["knn_final"] / 1e3) if stages.get("knn_final") else None}}
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
         t0 = time.perf_counter()
@@ -243,7 +256,7 @@ def run_ours(a):
             "config": config_dict(P, a.nu, n), "clocks": clocks,
             "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h[0] * world,
                     "ms_per_step": ms_e2e / a.steps},
-            "gpu_launches": int(total_launches), "roofline": roofline, "cpu_baseline": cpu, "stage_ms": stages}
+            "gpu_launches": int(total_launches), "roofline": roofline, "cpu_baseline": cpu, "stage_ms": stages, "secondary_metrics": secondary}
     print(json.dumps(line))
     fdist.finalize()
     return 0

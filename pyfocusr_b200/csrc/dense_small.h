@@ -28,6 +28,29 @@ struct SeqPar {
 };
 
 #if defined(__CUDACC__)
+// a whole CTA owns the matrix (large blocks, one mesh): red is blockDim.x doubles of shared scratch
+struct BlockPar {
+  double* red;
+  template <class F>
+  __device__ __forceinline__ void for_n(int n, F f) const {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) f(i);
+  }
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
+  __device__ __forceinline__ double sum(double v) const {
+    __syncthreads();
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    const double r = red[0];
+    __syncthreads();
+    return r;
+  }
+  __device__ __forceinline__ int lane() const { return threadIdx.x; }
+};
+
 struct WarpPar {
   int lane_;
   template <class F>
@@ -119,11 +142,14 @@ FB_HD void congruence_upper(double* h, const double* r, int b, const Par& par) {
   par.sync();
 }
 
-// Cyclic Jacobi eigen-decomposition of the symmetric matrix a (row-major, full storage).
-// On return diag(a) holds the eigenvalues and the columns of y the eigenvectors (a_in = y D y^T).
-// Returns the number of sweeps used.
+// Jacobi eigen-decomposition of the symmetric matrix a (row-major, full storage) with the
+// round-robin ("chess tournament") parallel ordering: each of the m-1 rounds of a sweep applies
+// m/2 rotations on disjoint index pairs, so all threads of the warp / CTA owning the matrix work at
+// once (column phase A <- A J, Y <- Y J, then row phase A <- J^T A).  On return diag(a) holds the
+// eigenvalues and the columns of y the eigenvectors (a_in = y D y^T).
+// rot: 2*(b/2+1) doubles (cos, sin per pair), pq: 2*(b/2+1) ints.  Returns the number of sweeps.
 template <class Par>
-FB_HD int jacobi_sym(double* a, double* y, int b, const Par& par) {
+FB_HD int jacobi_sym(double* a, double* y, int b, double* rot, int* pq, const Par& par) {
   par.for_n(b, [&](int i) {
     for (int j = 0; j < b; ++j) y[i * b + j] = (i == j) ? 1.0 : 0.0;
   });
@@ -134,49 +160,72 @@ FB_HD int jacobi_sym(double* a, double* y, int b, const Par& par) {
   });
   const double normf = sqrt(par.sum(loc));
   const double thr = 1e-17 * normf;
+  const int m = (b + 1) & ~1;  // players (one bye if b is odd)
+  const int half = m / 2;
+  double* cs = rot;
+  double* sn = rot + half;
+  int* pp = pq;
+  int* qq = pq + half;
   int sweep = 0;
   for (; sweep < 40; ++sweep) {
-    int rotations = 0;
-    for (int p = 0; p < b - 1; ++p) {
-      for (int q = p + 1; q < b; ++q) {
-        par.sync();
-        const double apq = a[p * b + q];
-        if (!(fabs(apq) > thr)) continue;
-        const double app = a[p * b + p];
-        const double aqq = a[q * b + q];
-        ++rotations;
-        const double tau = (aqq - app) / (2.0 * apq);
-        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-        const double c = 1.0 / sqrt(1.0 + t * t);
-        const double s = t * c;
-        par.sync();
-        par.for_n(b, [&](int i) {
-          if (i != p && i != q) {
-            const double aip = a[i * b + p];
-            const double aiq = a[i * b + q];
-            const double nip = c * aip - s * aiq;
-            const double niq = s * aip + c * aiq;
-            a[i * b + p] = nip;
-            a[p * b + i] = nip;
-            a[i * b + q] = niq;
-            a[q * b + i] = niq;
+    double nrot = 0.0;  // rotations applied in this sweep (every thread's own count, summed below)
+    for (int r = 0; r < m - 1; ++r) {
+      par.for_n(half, [&](int k) {
+        const int x = (r + k) % (m - 1);
+        const int z = (k == 0) ? (m - 1) : (r - k + (m - 1)) % (m - 1);
+        const int p = x < z ? x : z, q = x < z ? z : x;
+        double c = 1.0, s = 0.0;
+        if (q < b) {
+          const double apq = a[p * b + q];
+          if (fabs(apq) > thr) {
+            const double tau = (a[q * b + q] - a[p * b + p]) / (2.0 * apq);
+            const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+            c = 1.0 / sqrt(1.0 + t * t);
+            s = t * c;
           }
-          const double yip = y[i * b + p];
-          const double yiq = y[i * b + q];
+        }
+        cs[k] = c;
+        sn[k] = s;
+        pp[k] = p;
+        qq[k] = q;
+        if (s != 0.0) nrot += 1.0;
+      });
+      par.sync();
+      par.for_n(half * b, [&](int e) {  // column phase
+        const int k = e / b, i = e - k * b;
+        const int p = pp[k], q = qq[k];
+        const double c = cs[k], s = sn[k];
+        if (q < b && s != 0.0) {
+          const double aip = a[i * b + p], aiq = a[i * b + q];
+          a[i * b + p] = c * aip - s * aiq;
+          a[i * b + q] = s * aip + c * aiq;
+          const double yip = y[i * b + p], yiq = y[i * b + q];
           y[i * b + p] = c * yip - s * yiq;
           y[i * b + q] = s * yip + c * yiq;
-        });
-        par.sync();
-        if (par.lane() == 0) {
-          a[p * b + p] = app - t * apq;
-          a[q * b + q] = aqq + t * apq;
+        }
+      });
+      par.sync();
+      par.for_n(half * b, [&](int e) {  // row phase
+        const int k = e / b, j = e - k * b;
+        const int p = pp[k], q = qq[k];
+        const double c = cs[k], s = sn[k];
+        if (q < b && s != 0.0) {
+          const double apj = a[p * b + j], aqj = a[q * b + j];
+          a[p * b + j] = c * apj - s * aqj;
+          a[q * b + j] = s * apj + c * aqj;
+        }
+      });
+      par.sync();
+      par.for_n(half, [&](int k) {  // the annihilated pair, exactly
+        const int p = pp[k], q = qq[k];
+        if (q < b && sn[k] != 0.0) {
           a[p * b + q] = 0.0;
           a[q * b + p] = 0.0;
         }
-      }
+      });
+      par.sync();
     }
-    par.sync();
-    if (rotations == 0) break;
+    if (!(par.sum(nrot) > 0.0)) break;  // a full sweep without a rotation: every |a_pq| <= thr
   }
   par.sync();
   return sweep;
@@ -215,14 +264,15 @@ FB_HD void ritz_basis(const double* r, const double* y, const double* a, const i
 
 // Whole symmetric Rayleigh-Ritz step:  given G = X^T D X (SPD) and H = X^T (D-A) X (symmetric),
 // find W (b x b) and theta ascending with  (X W)^T D (X W) = I,  (X W)^T (D-A) (X W) = diag(theta).
-// g, h are overwritten (g <- R, h <- rotated); y, w are b*b scratch/outputs; rank is b ints.
+// g, h are overwritten (g <- R, h <- rotated); y, w are b*b scratch/outputs; rank is b ints;
+// rot (b+2 doubles) and pq (b+2 ints) are scratch of the Jacobi rounds.
 // Returns (#clamped pivots << 8) | #sweeps.
 template <class Par>
 FB_HD int rayleigh_ritz_sym(double* g, double* h, double* y, double* w, double* theta, int* rank,
-                            int b, const Par& par) {
+                            double* rot, int* pq, int b, const Par& par) {
   const int bad = cholesky_upper(g, theta, b, par);
   congruence_upper(h, g, b, par);
-  const int sweeps = jacobi_sym(h, y, b, par);
+  const int sweeps = jacobi_sym(h, y, b, rot, pq, par);
   rank_ascending(h, rank, b, par);
   ritz_basis(g, y, h, rank, w, theta, b, par);
   return (bad << 8) | sweeps;

@@ -5,7 +5,7 @@
 // Kernels in this file (the CSR SpMM of the filter itself is in spmm.cu):
 //   k_gram    tall-skinny Gram pair G = X^T g X, H = X^T h Z per mesh with FP64 tensor-core
 //             DMMA (mma.sync.m8n8k4.f64: tcgen05 has no f64 kind);
-//   k_rr_sym  one warp per mesh: Cholesky + congruence + cyclic Jacobi in shared memory;
+//   k_rr_sym  one warp (or CTA) per mesh: Cholesky + congruence + round-robin Jacobi in shared memory;
 //   k_rotate  X <- X W (DMMA) fused with the residual norms ||L x - theta x||;
 //   k_write_pairs  unit-norm, sign-fixed eigenvectors into the caller's [n_points][ldv] block.
 // All reductions use fixed trees / fixed chunk order: results are bit-reproducible run to run.
@@ -181,8 +181,11 @@ k_gram(const double* __restrict__ x, const double* __restrict__ z, const double*
   }
 }
 
-// One warp per mesh: sum the chunk partials in chunk order, then the b x b Rayleigh-Ritz step.
-__global__ void __launch_bounds__(32)
+// One warp (NT = 32, many small meshes in flight) or one CTA (NT = 256, large blocks) per mesh: sum
+// the chunk partials in chunk order, then the b x b Rayleigh-Ritz step in shared memory
+// (Cholesky, congruence, round-robin Jacobi: dense_small.h).
+template <int NT>
+__global__ void __launch_bounds__(NT)
 k_rr_sym(const double* __restrict__ partial, int chunks_max, const int* __restrict__ mesh_off, int B,
          double* __restrict__ w_out, double* __restrict__ theta_out, int* __restrict__ info) {
   extern __shared__ double sm[];
@@ -190,11 +193,14 @@ k_rr_sym(const double* __restrict__ partial, int chunks_max, const int* __restri
   double* h = g + B * B;
   double* y = h + B * B;
   double* th = y + B * B;
-  int* rank = reinterpret_cast<int*>(th + B);
-  const int mesh = blockIdx.x, lane = threadIdx.x;
+  double* rot = th + B;
+  double* red = rot + (B + 2);
+  int* rank = reinterpret_cast<int*>(red + NT);
+  int* pq = rank + B;
+  const int mesh = blockIdx.x, tid = threadIdx.x;
   const int nchunks = (mesh_off[mesh + 1] - mesh_off[mesh] + GRAM_ROWS - 1) / GRAM_ROWS;
   const double* src = partial + (size_t)mesh * chunks_max * 2 * B * B;
-  for (int e = lane; e < B * B; e += 32) {
+  for (int e = tid; e < B * B; e += NT) {
     double sg = 0.0, sh = 0.0;
     for (int c = 0; c < nchunks; ++c) {
       sg += src[(size_t)c * 2 * B * B + e];
@@ -203,11 +209,18 @@ k_rr_sym(const double* __restrict__ partial, int chunks_max, const int* __restri
     g[e] = sg;
     h[e] = sh;
   }
-  __syncwarp();
-  WarpPar par{lane};
-  const int rc = rayleigh_ritz_sym(g, h, y, w_out + (size_t)mesh * B * B, th, rank, B, par);
-  for (int j = lane; j < B; j += 32) theta_out[(size_t)mesh * B + j] = th[j];
-  if (lane == 0) info[mesh] = rc;
+  __syncthreads();
+  int rc;
+  if (NT == 32) {
+    WarpPar par{tid};
+    rc = rayleigh_ritz_sym(g, h, y, w_out + (size_t)mesh * B * B, th, rank, rot, pq, B, par);
+  } else {
+    BlockPar par{red};
+    rc = rayleigh_ritz_sym(g, h, y, w_out + (size_t)mesh * B * B, th, rank, rot, pq, B, par);
+  }
+  __syncthreads();
+  for (int j = tid; j < B; j += NT) theta_out[(size_t)mesh * B + j] = th[j];
+  if (tid == 0) info[mesh] = rc;
 }
 
 // Non-symmetric path: only the chunk reduction happens on the device; the host does the rest.
@@ -423,6 +436,11 @@ struct FilterProfile {
 };
 static FilterProfile g_filter_profile;
 
+// focusr_set_tuning(1, MB): L2 budget for blocking the filter over groups of meshes (0 = off)
+// Measured on B200 (gpurun_out/bench_l2_*.log, 128 pairs): 0 -> 641 pairs/s, 64 MB -> 548, 32 MB -> 341: groups
+// that fit L2 are < 1 wave of CTAs and the kernel is latency-bound, so blocking loses.  Default off.
+int g_l2_budget_mb = 0;
+
 template <int B>
 struct GramCfg {
   static constexpr int QT = (B <= 32) ? B / 8 : (B <= 64 ? 2 : 1);
@@ -520,13 +538,22 @@ struct CudaBackend {
     check("gram");
   }
   int rr_sym() {
-    const size_t smem = sizeof(double) * ((size_t)3 * B * B + B) + sizeof(int) * B;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-      cudaFuncSetAttribute(k_rr_sym, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      attr_smem = smem;
+    // one warp per mesh while the matrices are small or the meshes many; a whole CTA per mesh otherwise
+    const bool wide = B > 32 || (B > 16 && M < 64);
+    const int nt = wide ? 256 : 32;
+    const size_t smem = sizeof(double) * ((size_t)3 * B * B + B + (B + 2) + nt) + sizeof(int) * (2 * B + 2);
+    static size_t attr_smem[2] = {0, 0};
+    if (smem > attr_smem[wide]) {
+      if (wide)
+        cudaFuncSetAttribute(k_rr_sym<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      else
+        cudaFuncSetAttribute(k_rr_sym<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      attr_smem[wide] = smem;
     }
-    k_rr_sym<<<M, 32, smem, stream>>>(partial, chunks_max, g.mesh_off, B, W, theta, rr_info);
+    if (wide)
+      k_rr_sym<256><<<M, 256, smem, stream>>>(partial, chunks_max, g.mesh_off, B, W, theta, rr_info);
+    else
+      k_rr_sym<32><<<M, 32, smem, stream>>>(partial, chunks_max, g.mesh_off, B, W, theta, rr_info);
     FB_COUNT_LAUNCH(1);
     check("rr_sym");
     return 0;
@@ -599,8 +626,32 @@ struct CudaBackend {
       }
       fail(cudaMemcpyAsync(alpha, pa, sizeof(double) * (size_t)M * len, cudaMemcpyHostToDevice, stream), "H2D alpha");
       fail(cudaMemcpyAsync(gamma, pg, sizeof(double) * (size_t)M * len, cudaMemcpyHostToDevice, stream), "H2D gamma");
+      // L2 blocking: the three blocks + matrix of one mesh are ~7 MB at 15k vertices, so a group of
+      // meshes that fits the 126 MB L2 is taken through ALL steps of this table chunk before the next
+      // group starts; only the first step of a group streams from HBM.  (Every mesh of the batch runs
+      // the same number of steps, so the buffer rotation below is the same for every group.)
+      double per_mesh = 0.0;
+      for (int m = 0; m < M; ++m)
+        per_mesh = std::max(per_mesh, 12.0 * info_host[4 * m] + (20.0 + 24.0 * B) * (off_host[m + 1] - off_host[m]));
+      int group = M;
+      if (g_l2_budget_mb > 0) group = std::max(1, (int)((double)g_l2_budget_mb * 1048576.0 / per_mesh));
+      if (group >= M || len < 2) {
+        group = M;
+      }
+      for (int m0 = 0; m0 < M; m0 += group) {
+        SpmmGraph gg = g;
+        gg.mesh_off = g.mesh_off + m0;
+        gg.n_meshes = std::min(group, M - m0);
+        double *c2 = cur, *p2 = prev, *n2 = next;
+        for (int s = 0; s < len; ++s) {
+          launch_spmm(0, B, gg, c2, p2, n2, alpha + (size_t)m0 * len, gamma + (size_t)m0 * len, center + m0, s, len, stream);
+          double* t = p2;
+          p2 = c2;
+          c2 = n2;
+          n2 = t;
+        }
+      }
       for (int s = 0; s < len; ++s) {
-        launch_spmm(0, B, g, cur, prev, next, alpha, gamma, center, s, len, stream);
         double* t = prev;
         prev = cur;
         cur = next;

@@ -226,7 +226,10 @@ using namespace fb;
 extern "C" {
 
 int focusr_set_tuning(int key, int value) {
-  (void)value;  // no runtime knobs at present; the entry point stays for A/B experiments
+  if (key == 1) {
+    fb::g_l2_budget_mb = value;
+    return 0;
+  }
   fb::set_error("set_tuning: unknown key %d", key);
   return fb::FB_ERR_ARG;
 }

@@ -21,11 +21,10 @@ __all__ = ["eigsort", "decide_matches", "moves_from_matches"]
 def c_lambda_matrix(eig_vals_t, eig_vals_s, n):
     """eigsort.py:142-160: the gap averages over ALL eigenvalues each graph returned."""
     gap = (np.mean(np.diff(eig_vals_t)) + np.mean(np.diff(eig_vals_s))) / 2
-    c = np.zeros((n, n))
-    for i in range(n):
-        for j in range(n):
-            c[i, j] = np.exp((eig_vals_t[i] - eig_vals_s[j]) ** 2 / (2 * gap**2))
-    return c
+    lt = np.asarray(eig_vals_t)[:n, None]
+    ls = np.asarray(eig_vals_s)[None, :n]
+    # same elementwise operations as the reference's double loop (bitwise equal on the golden vectors)
+    return np.exp((lt - ls) ** 2 / (2 * gap**2))
 
 
 def decide_matches(c_lambda, c_hist, c_hist_f, c_spatial, c_spatial_f, target_as_reference=True):

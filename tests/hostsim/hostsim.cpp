@@ -98,14 +98,14 @@ struct HostBackend {
   }
   int rr_sym() {
     fb::SeqPar par;
-    std::vector<double> y((size_t)B * B);
-    std::vector<int> rank(B);
+    std::vector<double> y((size_t)B * B), rot(B + 2);
+    std::vector<int> rank(B), pq(B + 2);
     int worst = 0;
     for (int m = 0; m < M; ++m) {
       double* g = &G[(size_t)m * B * B];
       double* h = &H[(size_t)m * B * B];
       worst |= fb::rayleigh_ritz_sym(g, h, y.data(), &W[(size_t)m * B * B], &theta[(size_t)m * B],
-                                     rank.data(), B, par);
+                                     rank.data(), rot.data(), pq.data(), B, par);
     }
     return worst;
   }
@@ -219,10 +219,10 @@ int hostsim_eigs(const int* rp, const int* cols, const double* w, const double* 
 }
 
 int hostsim_rr_sym(double* g, double* h, double* w, double* theta, int b) {
-  std::vector<double> y((size_t)b * b);
-  std::vector<int> rank(b);
+  std::vector<double> y((size_t)b * b), rot(b + 2);
+  std::vector<int> rank(b), pq(b + 2);
   fb::SeqPar par;
-  return fb::rayleigh_ritz_sym(g, h, y.data(), w, theta, rank.data(), b, par);
+  return fb::rayleigh_ritz_sym(g, h, y.data(), w, theta, rank.data(), rot.data(), pq.data(), b, par);
 }
 
 int hostsim_eig_general(const double* a, int n, double* evals_ri, double* evecs_ri) {
