@@ -95,6 +95,35 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
                          double* result_d_host, void* workspace, size_t workspace_bytes,
                          focusr_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * K2, row-partitioned across GPUs (BASELINE.json configs[3]): ONE mesh,
+ * rank r owns the contiguous rows [row_begin_global, row_begin_global + n_local) of the symmetric
+ * adjacency.  `cols_local` are remapped columns: j in the local block -> j - row_begin_global,
+ * remote j -> n_local + (position of j in the rank's sorted ghost list, which is grouped by owner).
+ * Before every SpMM the ghost rows of the vector block are refreshed by one grouped
+ * ncclSend/ncclRecv of the boundary rows (`send_idx`: device list of local rows to ship, grouped by
+ * destination; `send_counts_host` / `recv_counts_host` [world]); Gram blocks, residual sums, the
+ * bounding box and the eigenvector norms are all-reduced.  NCCL is resolved at run time from the
+ * already-loaded libnccl.so.2; the library creates its own communicator from a 128-byte unique id
+ * (rank 0: focusr_dist_unique_id, broadcast by the caller, then focusr_dist_init on every rank).
+ * Every rank runs the same driver and sees identical Ritz values, so all control decisions agree.
+ * Outputs: eig_vals [ldv] (identical on all ranks), eig_vecs [n_local][ldv] (this rank's rows).
+ * ------------------------------------------------------------------------------------------- */
+int focusr_dist_unique_id(char* out128_host);
+int focusr_dist_init(const char* id128_host, int rank, int world);
+int focusr_dist_finalize(void);
+size_t focusr_eigs_dist_workspace_bytes(int n_local, int n_ghost, int n_send, int block_size, int world);
+int focusr_eigs_smallest_dist(const int* row_ptr, const int* cols_local, const double* weights,
+                              const double* degree, const double* degree_inv, const double* points,
+                              int n_local, int n_ghost, long long row_begin_global, long long nnz_local,
+                              const int* send_idx, int n_send, const int* send_counts_host,
+                              const int* recv_counts_host, int n_zero_rows_global, int k,
+                              int n_k_needed, int k_buffer, double min_eig_val, double tol,
+                              int max_outer, int block_size, double spectrum_upper_bound,
+                              double* eig_vals, double* eig_vecs, int ldv, int* result_i_host,
+                              double* result_d_host, void* workspace, size_t workspace_bytes,
+                              focusr_stream_t stream);
+
 /* Live profile of the dominant kernel, the Chebyshev SpMM filter step (CUDA events on the launching
  * stream around every filter application since the last reset): out4_host = {milliseconds,
  * launches, algorithmic bytes (12 nnz + 20 N + 24 b N per launch), 0}.  bench.py's roofline line. */

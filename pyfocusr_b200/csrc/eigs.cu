@@ -13,6 +13,7 @@
 
 #include "chfsi_driver.hpp"
 #include "common.cuh"
+#include "nccl_dyn.h"
 #include "rowops.h"
 #include "spmm.cuh"
 
@@ -69,7 +70,7 @@ template <int B>
 __global__ void __launch_bounds__(256)
 k_init_block(const double* __restrict__ points, const double* __restrict__ degree,
              const int* __restrict__ mesh_off, const long long* __restrict__ lo,
-             const long long* __restrict__ hi, double* __restrict__ x) {
+             const long long* __restrict__ hi, double* __restrict__ x, long long row_base) {
   const int mesh = blockIdx.y;
   const int m0 = mesh_off[mesh];
   const int r0 = m0 + blockIdx.x * GRAM_ROWS;
@@ -90,7 +91,7 @@ k_init_block(const double* __restrict__ points, const double* __restrict__ degre
       const double px = (points[3 * (size_t)r] - c[0]) / scale;
       const double py = (points[3 * (size_t)r + 1] - c[1]) / scale;
       const double pz = (points[3 * (size_t)r + 2] - c[2]) / scale;
-      v = start_block_value(col, px, py, pz, (uint32_t)(r - m0), 1u);
+      v = start_block_value(col, px, py, pz, (uint32_t)(r - m0 + row_base), 1u);
     }
     x[(size_t)r * B + col] = v;
   }
@@ -446,6 +447,113 @@ struct GramCfg {
   static constexpr int QT = (B <= 32) ? B / 8 : (B <= 64 ? 2 : 1);
 };
 
+
+// ---------------------------------------------------------------------------------------------
+// row-partitioned solve across GPUs: one mesh, rank r owns a contiguous
+// block of rows; vector blocks carry n_ghost extra rows (copies of the neighbours' boundary rows,
+// grouped by owner rank) refreshed by one grouped ncclSend/ncclRecv before every SpMM.
+// ---------------------------------------------------------------------------------------------
+struct DistCtx {
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  long long row_base = 0;          // global index of local row 0
+  int n_loc = 0, n_ghost = 0, n_send = 0;
+  const int* send_idx = nullptr;   // device [n_send]: local rows to ship, grouped by destination rank
+  const int* send_counts = nullptr;  // host [world]
+  const int* recv_counts = nullptr;  // host [world]
+  double* sendbuf = nullptr;       // device [n_send][B]
+  double* small = nullptr;         // device scratch for all-reduced small blocks
+  int* fake_off = nullptr;         // device {0, 1}: lets the chunk-summing kernels read one chunk
+};
+static ncclComm_t g_dist_comm = nullptr;
+static int g_dist_rank = 0, g_dist_world = 1;
+
+__global__ void k_pack_rows(const double* __restrict__ x, const int* __restrict__ idx, int n, int B,
+                            double* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * B) return;
+  const int i = (int)(t / B), c = (int)(t % B);
+  out[t] = x[(size_t)idx[i] * B + c];
+}
+
+__global__ void k_sum_chunks(const double* __restrict__ partial, int nchunks, int len, double* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= len) return;
+  double s = 0.0;
+  for (int c = 0; c < nchunks; ++c) s += partial[(size_t)c * len + e];
+  out[e] = s;
+}
+
+// per selected column: {sum of squares, max |v|, v at that entry, global row of that entry}
+__global__ void __launch_bounds__(256)
+k_colstats_local(const double* __restrict__ x, int B, int n_rows, const int* __restrict__ sel, int n_out,
+                 long long row_base, double* __restrict__ stats) {
+  const int j = blockIdx.x;
+  if (j >= n_out) return;
+  const int c = sel[j];
+  double ss = 0.0, best = -1.0, bestv = 0.0;
+  long long besti = 0x7fffffffffffffffLL;
+  for (int r = threadIdx.x; r < n_rows; r += blockDim.x) {
+    const double v = x[(size_t)r * B + c];
+    ss += v * v;
+    const double a = fabs(v);
+    if (a > best) {
+      best = a;
+      bestv = v;
+      besti = r + row_base;
+    }
+  }
+  __shared__ double s_ss[256], s_best[256], s_bestv[256];
+  __shared__ long long s_besti[256];
+  s_ss[threadIdx.x] = ss;
+  s_best[threadIdx.x] = best;
+  s_bestv[threadIdx.x] = bestv;
+  s_besti[threadIdx.x] = besti;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s_ss[threadIdx.x] += s_ss[threadIdx.x + o];
+      const double ob = s_best[threadIdx.x + o];
+      const long long oi = s_besti[threadIdx.x + o];
+      if (ob > s_best[threadIdx.x] || (ob == s_best[threadIdx.x] && oi < s_besti[threadIdx.x])) {
+        s_best[threadIdx.x] = ob;
+        s_bestv[threadIdx.x] = s_bestv[threadIdx.x + o];
+        s_besti[threadIdx.x] = oi;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    stats[4 * j + 0] = s_ss[0];
+    stats[4 * j + 1] = s_best[0];
+    stats[4 * j + 2] = s_bestv[0];
+    stats[4 * j + 3] = (double)s_besti[0];  // exact below 2^53
+  }
+}
+
+// gathered [world][B][4] stats -> normalise local rows: unit 2-norm, largest-magnitude entry positive
+__global__ void __launch_bounds__(256)
+k_write_scaled(const double* __restrict__ x, const double* __restrict__ theta, int B, int n_rows,
+               const int* __restrict__ sel, int n_out, const double* __restrict__ gathered, int world,
+               double* __restrict__ eig_vals, double* __restrict__ eig_vecs, int ldv) {
+  const int j = blockIdx.x;
+  if (j >= n_out) return;
+  const int c = sel[j];
+  double ss = 0.0, best = -1.0, bestv = 0.0, besti = 1e300;
+  for (int r = 0; r < world; ++r) {
+    const double* st = gathered + ((size_t)r * B + j) * 4;
+    ss += st[0];
+    if (st[1] > best || (st[1] == best && st[3] < besti)) {
+      best = st[1];
+      bestv = st[2];
+      besti = st[3];
+    }
+  }
+  const double scale = (bestv < 0.0 ? -1.0 : 1.0) / sqrt(ss);
+  for (int r = threadIdx.x; r < n_rows; r += blockDim.x) eig_vecs[(size_t)r * ldv + j] = x[(size_t)r * B + c] * scale;
+  if (threadIdx.x == 0) eig_vals[j] = theta[c];
+}
+
 struct CudaBackend {
   // graph of this run (rows are the run's meshes; pointers are global, offsets select the run)
   SpmmGraph g;
@@ -465,6 +573,7 @@ struct CudaBackend {
   double* eig_vecs;
   int ldv;
   int err = FB_OK;
+  DistCtx* dist = nullptr;  // row-partitioned multi-GPU solve (one mesh); null = everything is local
 
   int n_meshes() const { return M; }
   int block() const { return B; }
@@ -478,11 +587,43 @@ struct CudaBackend {
     }
   }
   void check(const char* what) { fail(cudaGetLastError(), what); }
+  void nccl_check(int rc, const char* what) {
+    if (rc != NCCL_SUCCESS && err == FB_OK) {
+      set_error("eigs (dist): %s -> %s", what, nccl_api().GetErrorString(rc));
+      err = FB_ERR_CUDA;
+    }
+  }
+  // refresh the ghost rows of a [n_loc + n_ghost][B] block from their owners
+  void halo_exchange(double* x) {
+    if (!dist || dist->world == 1) return;
+    NcclApi& api = nccl_api();
+    if (dist->n_send > 0) {
+      k_pack_rows<<<div_up((long long)dist->n_send * B, 256), 256, 0, stream>>>(x, dist->send_idx, dist->n_send, B, dist->sendbuf);
+      FB_COUNT_LAUNCH(1);
+    }
+    nccl_check(api.GroupStart(), "group start");
+    size_t so = 0, ro = 0;
+    for (int p = 0; p < dist->world; ++p) {
+      const int sc = dist->send_counts[p], rcnt = dist->recv_counts[p];
+      if (p != dist->rank) {
+        if (sc > 0) nccl_check(api.Send(dist->sendbuf + so * B, (size_t)sc * B, NCCL_FLOAT64, p, dist->comm, stream), "send");
+        if (rcnt > 0)
+          nccl_check(api.Recv(x + ((size_t)dist->n_loc + ro) * B, (size_t)rcnt * B, NCCL_FLOAT64, p, dist->comm, stream), "recv");
+      }
+      so += sc;
+      ro += rcnt;
+    }
+    nccl_check(api.GroupEnd(), "group end");
+  }
+  void all_reduce(void* buf, size_t count, int dtype, int op, const char* what) {
+    if (!dist || dist->world == 1) return;
+    nccl_check(nccl_api().AllReduce(buf, buf, count, dtype, op, dist->comm, stream), what);
+  }
 
   template <int BB>
   void init_block_t() {
     dim3 grid(chunks_max, M);
-    k_init_block<BB><<<grid, 256, 0, stream>>>(points, g.degree, g.mesh_off, lo, hi, X);
+    k_init_block<BB><<<grid, 256, 0, stream>>>(points, g.degree, g.mesh_off, lo, hi, X, dist ? dist->row_base : 0LL);
   }
   template <int BB>
   void gram_t() {
@@ -524,17 +665,26 @@ struct CudaBackend {
     k_bbox_init<<<div_up(3 * M, 256), 256, 0, stream>>>(lo, hi, 3 * M);
     dim3 grid(chunks_max, M);
     k_bbox<<<grid, 256, 0, stream>>>(points, g.mesh_off, lo, hi);
+    all_reduce(lo, 3 * (size_t)M, NCCL_INT64, NCCL_MIN, "bbox min");
+    all_reduce(hi, 3 * (size_t)M, NCCL_INT64, NCCL_MAX, "bbox max");
     FB_DISPATCH_B(init_block_t)
     FB_COUNT_LAUNCH(3);
     check("init_block");
   }
   void apply_DmA() {  // Z (stored in Xn) = (D - A) X
+    halo_exchange(X);
     launch_spmm(1, B, g, X, X, Xn, nullptr, nullptr, nullptr, 0, 0, stream);
     check("apply_DmA");
   }
   void gram() {
     FB_DISPATCH_B(gram_t)
     FB_COUNT_LAUNCH(1);
+    if (dist) {  // local chunk sums -> [2][B][B], then the sum over ranks
+      const int nchunks = div_up(off_host[1] - off_host[0], GRAM_ROWS);
+      k_sum_chunks<<<div_up(2 * B * B, 256), 256, 0, stream>>>(partial, nchunks, 2 * B * B, dist->small);
+      FB_COUNT_LAUNCH(1);
+      all_reduce(dist->small, 2 * (size_t)B * B, NCCL_FLOAT64, NCCL_SUM, "gram all-reduce");
+    }
     check("gram");
   }
   int rr_sym() {
@@ -550,10 +700,13 @@ struct CudaBackend {
         cudaFuncSetAttribute(k_rr_sym<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       attr_smem[wide] = smem;
     }
+    const double* src = dist ? dist->small : partial;
+    const int cm = dist ? 1 : chunks_max;
+    const int* offs = dist ? dist->fake_off : g.mesh_off;
     if (wide)
-      k_rr_sym<256><<<M, 256, smem, stream>>>(partial, chunks_max, g.mesh_off, B, W, theta, rr_info);
+      k_rr_sym<256><<<M, 256, smem, stream>>>(src, cm, offs, B, W, theta, rr_info);
     else
-      k_rr_sym<32><<<M, 32, smem, stream>>>(partial, chunks_max, g.mesh_off, B, W, theta, rr_info);
+      k_rr_sym<32><<<M, 32, smem, stream>>>(src, cm, offs, B, W, theta, rr_info);
     FB_COUNT_LAUNCH(1);
     check("rr_sym");
     return 0;
@@ -575,7 +728,15 @@ struct CudaBackend {
   }
   void rotate_and_residual() {
     FB_DISPATCH_B(rotate_t)
-    k_residual<<<M, 128, 0, stream>>>(partial_res, chunks_max, g.mesh_off, B, res);
+    if (dist) {
+      const int nchunks = div_up(off_host[1] - off_host[0], GRAM_ROWS);
+      k_sum_chunks<<<div_up(2 * B, 256), 256, 0, stream>>>(partial_res, nchunks, 2 * B, dist->small);
+      all_reduce(dist->small, 2 * (size_t)B, NCCL_FLOAT64, NCCL_SUM, "residual all-reduce");
+      k_residual<<<M, 128, 0, stream>>>(dist->small, 1, dist->fake_off, B, res);
+      FB_COUNT_LAUNCH(1);
+    } else {
+      k_residual<<<M, 128, 0, stream>>>(partial_res, chunks_max, g.mesh_off, B, res);
+    }
     FB_COUNT_LAUNCH(2);
     check("rotate");
   }
@@ -644,6 +805,7 @@ struct CudaBackend {
         gg.n_meshes = std::min(group, M - m0);
         double *c2 = cur, *p2 = prev, *n2 = next;
         for (int s = 0; s < len; ++s) {
+          halo_exchange(c2);
           launch_spmm(0, B, gg, c2, p2, n2, alpha + (size_t)m0 * len, gamma + (size_t)m0 * len, center + m0, s, len, stream);
           double* t = p2;
           p2 = c2;
@@ -672,8 +834,22 @@ struct CudaBackend {
     fail(cudaMemcpyAsync(flags, fl, sizeof(int) * M, cudaMemcpyHostToDevice, stream), "H2D flags");
     fail(cudaMemcpyAsync(sel, sl, sizeof(int) * (size_t)M * B, cudaMemcpyHostToDevice, stream), "H2D sel");
     fail(cudaMemcpyAsync(n_out, no, sizeof(int) * M, cudaMemcpyHostToDevice, stream), "H2D n_out");
-    dim3 grid(std::min(B, ldv), M);
-    k_write_pairs<<<grid, 256, 0, stream>>>(X, theta, B, g.mesh_off, flags, sel, n_out, eig_vals, eig_vecs, ldv, mesh_base);
+    if (dist) {
+      const int cnt = no[0];
+      double* stats = dist->small;                        // [B][4] local
+      double* gathered = dist->small + 4 * (size_t)B;     // [world][B][4]
+      k_colstats_local<<<std::max(cnt, 1), 256, 0, stream>>>(X, B, dist->n_loc, sel, cnt, dist->row_base, stats);
+      if (dist->world > 1)
+        nccl_check(nccl_api().AllGather(stats, gathered, 4 * (size_t)B, NCCL_FLOAT64, dist->comm, stream), "stats all-gather");
+      else
+        fail(cudaMemcpyAsync(gathered, stats, sizeof(double) * 4 * B, cudaMemcpyDeviceToDevice, stream), "stats copy");
+      k_write_scaled<<<std::max(cnt, 1), 256, 0, stream>>>(X, theta, B, dist->n_loc, sel, cnt, gathered, dist->world,
+                                                           eig_vals, eig_vecs, ldv);
+      FB_COUNT_LAUNCH(1);
+    } else {
+      dim3 grid(std::min(B, ldv), M);
+      k_write_pairs<<<grid, 256, 0, stream>>>(X, theta, B, g.mesh_off, flags, sel, n_out, eig_vals, eig_vecs, ldv, mesh_base);
+    }
     FB_COUNT_LAUNCH(1);
     check("write_pairs");
     // the host arrays are reused by the driver right after this call returns
@@ -854,5 +1030,154 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
     set_error("eigs: solver status %d (1 not converged, 2 block too small, 3 breakdown, 4 ldv too small); "
               "see result_i_host", rc_all);
   return rc_all;
+}
+
+// ---------------------------------------------------------------------------------------------
+// row-partitioned multi-GPU solve
+// ---------------------------------------------------------------------------------------------
+int focusr_dist_unique_id(char* out128_host) {
+  NcclApi& api = nccl_api();
+  FB_REQUIRE(api.ok, "dist: libnccl.so.2 could not be loaded");
+  ncclUniqueId id;
+  const int rc = api.GetUniqueId(&id);
+  FB_REQUIRE(rc == NCCL_SUCCESS, "dist: ncclGetUniqueId -> %s", api.GetErrorString(rc));
+  memcpy(out128_host, id.internal, 128);
+  return FB_OK;
+}
+
+int focusr_dist_init(const char* id128_host, int rank, int world) {
+  NcclApi& api = nccl_api();
+  FB_REQUIRE(api.ok, "dist: libnccl.so.2 could not be loaded");
+  FB_REQUIRE(world >= 1 && rank >= 0 && rank < world, "dist: bad rank %d / world %d", rank, world);
+  if (g_dist_comm) {
+    api.CommDestroy(g_dist_comm);
+    g_dist_comm = nullptr;
+  }
+  ncclUniqueId id;
+  memcpy(id.internal, id128_host, 128);
+  const int rc = api.CommInitRank(&g_dist_comm, world, id, rank);
+  FB_REQUIRE(rc == NCCL_SUCCESS, "dist: ncclCommInitRank -> %s", api.GetErrorString(rc));
+  g_dist_rank = rank;
+  g_dist_world = world;
+  return FB_OK;
+}
+
+int focusr_dist_finalize(void) {
+  if (g_dist_comm) {
+    nccl_api().CommDestroy(g_dist_comm);
+    g_dist_comm = nullptr;
+  }
+  g_dist_world = 1;
+  g_dist_rank = 0;
+  return FB_OK;
+}
+
+static size_t dist_extra_layout(int n_send, int B, int world, DistCtx* d, Carver& cv) {
+  double* sendbuf = cv.take<double>((size_t)std::max(n_send, 1) * B);
+  const size_t small_n = std::max((size_t)2 * B * B, (size_t)4 * B * (world + 1));
+  double* small = cv.take<double>(small_n);
+  int* fake_off = cv.take<int>(2);
+  if (d) {
+    d->sendbuf = sendbuf;
+    d->small = small;
+    d->fake_off = fake_off;
+  }
+  return cv.used + 256;
+}
+
+size_t focusr_eigs_dist_workspace_bytes(int n_local, int n_ghost, int n_send, int block_size, int world) {
+  const size_t base = eigs_ws_layout(n_local + n_ghost, 1, n_local, block_size, nullptr, nullptr, 0);
+  Carver cv(nullptr, 0);
+  return align_up(base) + dist_extra_layout(n_send, block_size, world, nullptr, cv) + 1024;
+}
+
+int focusr_eigs_smallest_dist(const int* row_ptr, const int* cols_local, const double* weights,
+                              const double* degree, const double* degree_inv, const double* points,
+                              int n_local, int n_ghost, long long row_begin_global, long long nnz_local,
+                              const int* send_idx, int n_send, const int* send_counts_host,
+                              const int* recv_counts_host, int n_zero_rows_global, int k, int n_k_needed,
+                              int k_buffer, double min_eig_val, double tol, int max_outer, int block_size,
+                              double spectrum_upper_bound, double* eig_vals, double* eig_vecs, int ldv,
+                              int* result_i_host, double* result_d_host, void* workspace,
+                              size_t workspace_bytes, focusr_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  FB_REQUIRE(n_local > 0 && k >= 1 && n_k_needed >= 1 && ldv >= 1, "eigs_dist: bad sizes");
+  FB_REQUIRE(g_dist_world == 1 || g_dist_comm != nullptr, "eigs_dist: call focusr_dist_init first");
+  const int world = g_dist_world;
+  const int B = block_size > 0 ? block_size : focusr_eigs_block_size(k, n_k_needed, k_buffer, 0, n_zero_rows_global);
+  FB_REQUIRE(spmm_block_supported(B), "eigs_dist: block size %d unsupported", B);
+  FB_REQUIRE(n_local > B, "eigs_dist: fewer local rows (%d) than the block size (%d)", n_local, B);
+  SolveParams p;
+  p.k0 = k;
+  p.n_needed = n_k_needed;
+  p.k_buffer = k_buffer;
+  p.min_eig = min_eig_val;
+  p.tol = tol > 0.0 ? tol : 1e-10;
+  p.max_outer = max_outer > 0 ? max_outer : 60;
+  p.amp_target = 1e3;
+  p.max_degree = 16384;
+  p.beta = spectrum_upper_bound > 0.0 ? spectrum_upper_bound : 2.0;
+  p.ldv = ldv;
+
+  DistCtx d;
+  d.comm = g_dist_comm;
+  d.rank = g_dist_rank;
+  d.world = world;
+  d.row_base = row_begin_global;
+  d.n_loc = n_local;
+  d.n_ghost = n_ghost;
+  d.n_send = n_send;
+  d.send_idx = send_idx;
+  d.send_counts = send_counts_host;
+  d.recv_counts = recv_counts_host;
+
+  CudaBackend be;
+  be.g = SpmmGraph{row_ptr, cols_local, weights, degree, degree_inv, nullptr, 1, n_local};
+  const size_t base = eigs_ws_layout(n_local + n_ghost, 1, n_local, B, &be, workspace, workspace_bytes);
+  Carver cv((char*)workspace + align_up(base), workspace_bytes > align_up(base) ? workspace_bytes - align_up(base) : 0);
+  const size_t extra = dist_extra_layout(n_send, B, world, &d, cv);
+  if (align_up(base) + extra > workspace_bytes) {
+    set_error("eigs_dist: workspace too small (%zu < %zu)", workspace_bytes, align_up(base) + extra);
+    return FB_ERR_WORKSPACE;
+  }
+  const int off_host[2] = {0, n_local};
+  const int info_host[4] = {(int)nnz_local, 0, n_zero_rows_global, 0};
+  const int fake[2] = {0, 1};
+  be.points = points;
+  be.off_host = off_host;
+  be.info_host = info_host;
+  be.M = 1;
+  be.B = B;
+  be.mesh_base = 0;
+  be.sym = true;
+  be.stream = stream;
+  be.eig_vals = eig_vals;
+  be.eig_vecs = eig_vecs;
+  be.ldv = ldv;
+  be.dist = &d;
+  FB_CUDA(cudaMemcpyAsync(const_cast<int*>(be.g.mesh_off), off_host, sizeof(off_host), cudaMemcpyHostToDevice, stream));
+  FB_CUDA(cudaMemcpyAsync(d.fake_off, fake, sizeof(fake), cudaMemcpyHostToDevice, stream));
+  // ghost rows of all three blocks start defined (the first exchange overwrites them)
+  FB_CUDA(cudaMemsetAsync(be.X, 0, sizeof(double) * (size_t)(n_local + n_ghost) * B, stream));
+  FB_CUDA(cudaMemsetAsync(be.Y, 0, sizeof(double) * (size_t)(n_local + n_ghost) * B, stream));
+  FB_CUDA(cudaMemsetAsync(be.Xn, 0, sizeof(double) * (size_t)(n_local + n_ghost) * B, stream));
+  FB_CUDA(cudaStreamSynchronize(stream));  // off_host / fake live on this stack frame
+  MeshResult r;
+  const int rc = chfsi_solve(be, p, &r);
+  if (be.err != FB_OK) return be.err;
+  FB_CUDA(cudaStreamSynchronize(stream));
+  g_filter_profile.collect();
+  result_i_host[0] = r.status;
+  result_i_host[1] = r.n_out;
+  result_i_host[2] = r.k_final;
+  result_i_host[3] = r.outer_iters;
+  result_i_host[4] = r.total_degree;
+  result_i_host[5] = B;
+  result_i_host[6] = 1;
+  result_i_host[7] = world;
+  result_d_host[0] = r.max_residual;
+  result_d_host[1] = 0.0;
+  if (rc != FB_OK) set_error("eigs_dist: solver status %d", rc);
+  return rc;
 }
 }
