@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _device, _lib
 from ._device import DeviceGraph
-from .eigsort import c_lambda_matrix, decide_matches, moves_from_matches
+from .eigsort import decide_batch
 
 __all__ = ["SpectralBatch"]
 
@@ -98,21 +98,21 @@ class SpectralBatch:
         src = dst.copy()
         sign = np.ones((2 * P, n), dtype=np.int32)
         weights = np.ones((2 * P, ns))
-        Q = np.zeros((P, n))
-        for p in range(P):
-            vt = vals_h[p, : n_found[p]]
-            vs = vals_h[P + p, : n_found[P + p]]
-            cl = c_lambda_matrix(vt, vs, n)
-            q, tm, sm, flipped = decide_matches(cl, costs[0, p], costs[1, p], costs[2, p], costs[3, p],
-                                                self.target_as_reference)
-            d, s, sg = moves_from_matches(tm, sm, flipped, self.target_as_reference)
-            row = P + p if self.target_as_reference else p
-            dst[row, : len(d)], src[row, : len(d)], sign[row, : len(d)] = d, s, sg
-            Q[p] = q
-            if self.weighted:
-                w = q[:ns] * np.max((vs[:ns], vt[:ns]), axis=0)
-                w = np.exp(-(w**2) / (2 * np.mean(w) ** 2))
-                weights[p] = weights[P + p] = w
+        # eigenvalue gap of every mesh over ALL its returned eigenvalues (graph.py:263-264)
+        if int(n_found.min()) == int(n_found.max()):
+            gaps = np.mean(np.diff(vals_h[:, : int(n_found[0])], axis=1), axis=1)
+        else:
+            gaps = np.array([np.mean(np.diff(vals_h[m, : n_found[m]])) for m in range(2 * P)])
+        gap = (gaps[:P] + gaps[P:]) / 2
+        vt, vs = vals_h[:P, :n], vals_h[P:, :n]
+        cl = np.exp((vt[:, :, None] - vs[:, None, :]) ** 2 / (2 * gap[:, None, None] ** 2))   # eigsort.py:155-160
+        Q, d, s, sg = decide_batch(cl, costs[0], costs[1], costs[2], costs[3], self.target_as_reference)
+        rows = slice(P, 2 * P) if self.target_as_reference else slice(0, P)
+        dst[rows], src[rows], sign[rows] = d, s, sg
+        if self.weighted:  # focusr.py:481-490
+            w = Q[:, :ns] * np.maximum(vs[:, :ns], vt[:, :ns])
+            w = np.exp(-(w**2) / (2 * np.mean(w, axis=1, keepdims=True) ** 2))
+            weights[:P] = weights[P:] = w
         presort = vecs.clone() if keep_presort else None
         g.flip_permute(vecs, dst, src, sign)
         coords = g.spectral_coords(vecs, weights, ns)

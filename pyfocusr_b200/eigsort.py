@@ -62,6 +62,53 @@ def moves_from_matches(target_matches, source_matches, flipped_pairs, target_as_
     return np.array(dst, np.int32), np.array(src, np.int32), np.array(sign, np.int32)
 
 
+_PERMS = {}
+
+
+def _perms(n):
+    if n not in _PERMS:
+        import itertools
+
+        _PERMS[n] = np.array(list(itertools.permutations(range(n))), dtype=np.int64)
+    return _PERMS[n]
+
+
+def decide_batch(c_lambda, c_hist, c_hist_f, c_spatial, c_spatial_f, target_as_reference=True):
+    """``decide_matches`` + ``moves_from_matches`` for P pairs at once (inputs [P][n][n]).
+
+    For n <= 8 the assignment is found by scoring all n! permutations in one vectorised pass -- the
+    same optimum scipy's ``linear_sum_assignment`` returns whenever it is unique (ties have measure
+    zero for these costs; tests/test_host_logic.py checks the two agree) -- otherwise scipy is called
+    per pair.  Returns (Q [P][n], dst, src, sign int32 [P][n])."""
+    c = c_spatial * c_lambda * c_hist
+    c_f = c_spatial_f * c_lambda * c_hist_f
+    q = np.minimum(c, c_f)  # == np.min((c, c_f), axis=0)
+    s = c > c_f
+    P, n, _ = q.shape
+    rows = np.arange(n)
+    if n <= 8:
+        perms = _perms(n)
+        qq = q if target_as_reference else np.swapaxes(q, 1, 2)
+        # sum in row order exactly like the per-pair total scipy minimises
+        tot = np.zeros((P, perms.shape[0]))
+        for i in range(n):
+            tot = tot + qq[:, i, perms[:, i]]
+        assign = perms[np.argmin(tot, axis=1)]          # [P][n]: column matched to row i
+    else:
+        assign = np.empty((P, n), dtype=np.int64)
+        for p in range(P):
+            assign[p] = linear_sum_assignment(q[p] if target_as_reference else q[p].T)[1]
+    if target_as_reference:
+        tm, sm = np.broadcast_to(rows, (P, n)), assign   # target i <-> source assign[i]
+    else:
+        sm, tm = np.broadcast_to(rows, (P, n)), assign   # source i <-> target assign[i]
+    pi = np.arange(P)[:, None]
+    q_pairs = q[pi, tm, sm]
+    sign = np.where(s[pi, tm, sm], -1, 1).astype(np.int32)
+    dst, src = (tm, sm) if target_as_reference else (sm, tm)
+    return q_pairs, np.ascontiguousarray(dst, dtype=np.int32), np.ascontiguousarray(src, dtype=np.int32), sign
+
+
 class eigsort(object):
     def __init__(self, graph_target, graph_source, n_features, target_as_reference=True):
         self.graph_target = graph_target

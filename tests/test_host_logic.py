@@ -229,3 +229,20 @@ def test_product_never_imports_the_oracle_and_has_no_cpu_fallback():
         g = Graph(fmesh.icosphere(2), n_rand_samples=5)
         with pytest.raises(RuntimeError):
             g.get_graph_spectrum()  # fails loudly: no CPU path
+
+
+def test_decide_batch_equals_per_pair_scipy():
+    """The vectorised all-permutations assignment == scipy LSAP + the reference's flip logic, pair by pair."""
+    from pyfocusr_b200.eigsort import decide_batch, decide_matches, moves_from_matches
+
+    rng = np.random.RandomState(5)
+    for n in (3, 6, 8, 10):
+        P = 40
+        mats = [np.exp(rng.standard_normal((P, n, n))) for _ in range(5)]
+        for ref_is_target in (True, False):
+            q, d, s, sg = decide_batch(*mats, ref_is_target)
+            for p in range(P):
+                q1, tm, sm, fl = decide_matches(*[m[p] for m in mats], ref_is_target)
+                d1, s1, sg1 = moves_from_matches(tm, sm, fl, ref_is_target)
+                assert np.array_equal(q[p], q1) and np.array_equal(d[p], d1) and np.array_equal(s[p], s1)
+                assert np.array_equal(sg[p], sg1)
