@@ -164,6 +164,8 @@ def run_ours(a):
     tris_dev = torch.from_numpy(tris).cuda()
     pts_dev = pts_pin.cuda()
     sb = SpectralBatch(N_SPECTRAL, N_EXTRA, N_SAMPLES, SMOOTH_T, SMOOTH_S, seed=rank)
+    if os.environ.get("FOCUSR_SMOOTH_L2_MB"):
+        sb.smooth_l2_bytes = int(os.environ["FOCUSR_SMOOTH_L2_MB"]) << 20
     rng = np.random.RandomState(rank)
     sizes = np.diff(off)
     idx_t, idx_s = sb.sample_indices(sizes[:P], rng), sb.sample_indices(sizes[P:], rng)

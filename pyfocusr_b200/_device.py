@@ -183,16 +183,32 @@ class DeviceGraph:
         return out
 
     # --- K5 -----------------------------------------------------------------------------------
-    def mean_filter(self, values, iterations, row_begin=0, row_end=None):
-        """values: device [n_points][c] (rows outside the range are ignored).  Returns a new tensor."""
+    def mean_filter(self, values, iterations, row_begin=0, row_end=None, l2_group_bytes=0):
+        """values: device [n_points][c] (rows outside the range are ignored).  Returns a new tensor.
+        ``l2_group_bytes`` > 0 runs all iterations on one group of whole meshes after the other, each
+        group's matrix + vectors sized to stay resident in L2 (126 MB on B200)."""
         torch = _torch()
         row_end = self.n_points if row_end is None else row_end
         c = int(values.shape[1])
         out = torch.empty_like(values)
         scratch = torch.empty_like(values)
-        _lib.call("focusr_mean_filter", _lib.ptr(self.row_ptr), _lib.ptr(self.cols), _lib.ptr(self.weights),
-                  _lib.ptr(self.degree), int(row_begin), int(row_end), _lib.ptr(values), _lib.ptr(out), _lib.ptr(scratch),
-                  c, int(iterations), _lib.stream_ptr())
+        ranges = [(int(row_begin), int(row_end))]
+        if l2_group_bytes and iterations > 1:
+            off = self.mesh_off_host
+            ms = [m for m in range(self.n_meshes) if off[m] >= row_begin and off[m + 1] <= row_end]
+            if ms and off[ms[0]] == row_begin and off[ms[-1] + 1] == row_end:
+                ranges, start, acc = [], ms[0], 0.0
+                for m in ms:
+                    need = 12.0 * self.mesh_info_host[m, 0] + (12.0 + 16.0 * c) * (off[m + 1] - off[m])
+                    if acc > 0 and acc + need > l2_group_bytes:
+                        ranges.append((int(off[start]), int(off[m])))
+                        start, acc = m, 0.0
+                    acc += need
+                ranges.append((int(off[start]), int(row_end)))
+        for r0, r1 in ranges:
+            _lib.call("focusr_mean_filter", _lib.ptr(self.row_ptr), _lib.ptr(self.cols), _lib.ptr(self.weights),
+                      _lib.ptr(self.degree), r0, r1, _lib.ptr(values), _lib.ptr(out), _lib.ptr(scratch),
+                      c, int(iterations), _lib.stream_ptr())
         return out
 
 

@@ -36,6 +36,7 @@ class SpectralBatch:
         self.tol = float(tol)
         self.block_size = int(block_size)
         self.seed = int(seed)
+        self.smooth_l2_bytes = 0  # > 0: smoothing runs group by group of meshes that fit L2 (see DeviceGraph.mean_filter)
         self.timings = {}
 
     # ------------------------------------------------------------------------------------------
@@ -127,12 +128,12 @@ class SpectralBatch:
         idx0, _ = _device.knn(coords[:nt_total], coords[nt_total:], k=1, ref_off=ref_off, query_off=qry_off,
                               max_queries=max_q, max_refs=max_r, want_dist=False)
         mark("knn_initial")
-        smoothed_t = g.mean_filter(g.points, self.graph_smoothing_iterations, 0, nt_total)
+        smoothed_t = g.mean_filter(g.points, self.graph_smoothing_iterations, 0, nt_total, self.smooth_l2_bytes)
         base_q = torch.repeat_interleave(g.mesh_off[:P], torch.from_numpy(sizes[P:].astype(np.int64)).to(dev)).to(torch.int32)
         staged = torch.empty_like(g.points)
         _lib.call("focusr_gather_rows", _lib.ptr(smoothed_t), _lib.ptr(idx0), _lib.ptr(base_q), g.n_points - nt_total, 3,
                   _lib.ptr(staged[nt_total:]), _lib.stream_ptr())
-        src_proj = g.mean_filter(staged, self.projection_smooth_iterations, nt_total, g.n_points)
+        src_proj = g.mean_filter(staged, self.projection_smooth_iterations, nt_total, g.n_points, self.smooth_l2_bytes)
         mark("smoothing")
         # one k=3 search serves both focusr.py:391-392 (k=1: its first column, same distances and tie
         # rule) and focusr.py:409-413 (k=3)

@@ -526,3 +526,37 @@ def test_knn_pruned_is_bit_identical_to_brute_force(torch, shipped_meshes, synth
     a = _device.knn(torch.from_numpy(refs).cuda(), torch.from_numpy(qs).cuda(), k=3, ref_off=ro, query_off=qo, max_queries=5000, max_refs=5000)
     b = _device.knn(torch.from_numpy(refs).cuda(), torch.from_numpy(qs).cuda(), k=3, ref_off=ro, query_off=qo, max_queries=5000, max_refs=5000, brute_force=True)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+def test_focusr_dropin_variants_5k(torch, shipped_meshes):
+    """API variants of the drop-in on the 5k pair, each checked against the oracle fed our pre-sort eigenvectors:
+    source as the reference eigenmap, unweighted coordinates, xyz appended as features (d = 6), n_spectral_features=10,
+    more ordering samples than vertices (arange path of graph.py:284-288)."""
+    from oracle import port
+    import pyfocusr_b200 as pyfocusr
+
+    mt, ms = shipped_meshes["target_mesh"], shipped_meshes["source_mesh"]
+    at, as_ = port.adjacency(mt.points, mt.tris), port.adjacency(ms.points, ms.tris)
+    variants = [dict(target_eigenmap_as_reference=False), dict(get_weighted_spectral_coords=False),
+                dict(include_points_as_features=True), dict(include_points_as_features=True, norm_physical_and_spectral=False),
+                dict(n_spectral_features=10, n_extra_spectral=3), dict(n_coords_spectral_ordering=20000),
+                dict(graph_smoothing_iterations=7, projection_smooth_iterations=0, smooth_correspondences=True)]
+    for kw in variants:
+        np.random.seed(3)
+        f = pyfocusr.Focusr(mt, ms, icp_register_first=False, list_features_to_calc=[], registration="identity", **kw)
+        n_spec = kw.get("n_spectral_features", 3)
+        n = n_spec + 3
+        tref = kw.get("target_eigenmap_as_reference", True)
+        vt0, vs0 = f.graph_target.eig_vecs.copy(), f.graph_source.eig_vecs.copy()
+        f.align_maps()
+        srt = port.sort_eigenmaps(mt.points, ms.points, f.graph_target.rand_idxs, f.graph_source.rand_idxs,
+                                  f.graph_target.eig_vals, f.graph_source.eig_vals, vt0, vs0, n, tref)
+        assert np.max(np.abs(f.Q - srt["Q"]) / srt["Q"]) <= 1e-9, kw
+        assert np.array_equal(f.graph_source.eig_vecs, vs0) and np.array_equal(f.graph_target.eig_vecs, vt0), kw
+        assert f.target_spectral_coords.shape[1] == n_spec + (3 if kw.get("include_points_as_features") else 0)
+        cs = port.correspondence_stage(dict(A=at), dict(A=as_), mt.points, ms.points, f.target_spectral_coords,
+                                       f.source_spectral_coords, f.graph_smoothing_iterations, f.projection_smooth_iterations)
+        assert np.array_equal(f.corresponding_target_idx_for_each_source_pt, cs["final_idx"]), kw
+        assert np.array_equal(f.weighted_avg_transformed_points, cs["weighted_avg_transformed_points"]), kw
+        if "n_coords_spectral_ordering" in kw:
+            assert np.array_equal(f.graph_target.rand_idxs, np.arange(5000))
