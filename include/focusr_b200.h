@@ -40,9 +40,12 @@ unsigned long long focusr_launch_count(void);
  * degree d = A.sum(axis=1) (sequential ascending-column sum, bit-identical to scipy) and
  * 1/(d+1e-8).  `cols`/`weights` need capacity 3*n_tris.  `mesh_info` is [n_meshes][4] int:
  * {nnz(A), one-way entries (A_ij stored, A_ji not), zero-degree rows, non-finite weights}.
+ * `points` is [n_points][point_dim]: point_dim = 3 (xyz) by default, or 3 + f when
+ * include_features_in_adj_matrix appends f range-scaled node features to the position
+ * (graph.py:166-175); the edge weight is 1/||p1 - p2|| over all point_dim coordinates.
  * ------------------------------------------------------------------------------------------- */
 size_t focusr_laplacian_workspace_bytes(int n_points, int n_tris);
-int focusr_laplacian_build(const double* points, const int* tris, int n_points, int n_tris,
+int focusr_laplacian_build(const double* points, int point_dim, const int* tris, int n_points, int n_tris,
                            const int* mesh_point_off, int n_meshes, int* row_ptr, int* cols,
                            double* weights, double* degree, double* degree_inv, int* mesh_info,
                            void* workspace, size_t workspace_bytes, focusr_stream_t stream);

@@ -40,6 +40,9 @@ NOTEBOOK_SOURCE = [8.31236570e-04, 1.64152416e-03, 2.11362458e-03, 3.09029787e-0
                    3.88535401e-03, 3.92405051e-03]
 
 
+SCALAR = "thickness_change_(mm)"  # point scalar carried by every shipped mesh (data/*.vtk:34998)
+
+
 def sha(a):
     a = np.ascontiguousarray(a)
     return hashlib.sha256(a.tobytes()).hexdigest()
@@ -108,6 +111,74 @@ def check_graph(ref_g, mesh, tag):
                 n_dup=int(key.size - np.unique(key).size), n_isolated=int(np.sum(deg == 0)))
 
 
+def feature_case(ref, mt, ms):
+    """a mesh scalar as extra node feature, inside the adjacency weights
+    (graph.py:166-175) and appended to the spectral coordinates (focusr.py:218-269)."""
+    tag, n_spec, n = "5k_feat", 3, 6
+    graphs = []
+    for mesh, seed in ((mt, 0), (ms, 1)):
+        np.random.seed(seed)
+        g = quiet(ref.Graph, mesh, n_spectral_features=n, n_rand_samples=5000, list_features_to_calc=[],
+                  list_features_to_get_from_mesh=[SCALAR], feature_weights=np.eye(1), include_features_in_adj_matrix=True)
+        quiet(g.get_graph_spectrum)
+        graphs.append(g)
+    gt, gs = graphs
+    out = {}
+    infos = []
+    for side, g, mesh in (("t", gt, mt), ("s", gs, ms)):
+        feat = port.normalized_node_feature(mesh.point_scalars[SCALAR])
+        assert np.array_equal(feat, g.node_features[0]), side
+        aug = port.feature_augmented_points(mesh.points, [feat])
+        a = port.adjacency(aug, mesh.tris)
+        ar = g.adjacency_matrix.tocsr()
+        ar.sort_indices()
+        assert np.array_equal(ar.indices, a.indices) and np.array_equal(ar.data, a.data), side + " feature adjacency"
+        lap = port.laplacian(a)
+        lr = g.laplacian_matrix.copy()
+        lr.sort_indices()
+        assert np.array_equal(lr.data, lap.data), side
+        out[f"{tag}_{side}_A_sha"] = np.array(sha(a.data) + sha(a.indices) + sha(a.indptr))
+        out[f"{tag}_{side}_eig_vals"] = g.eig_vals.copy()
+        out[f"{tag}_{side}_eig_vecs_raw_normed"] = g.eig_vecs.copy()
+        out[f"{tag}_{side}_rand_idxs"] = np.asarray(g.rand_idxs)
+        infos.append((a, feat))
+    raw_t, raw_s = gt.eig_vecs.copy(), gs.eig_vecs.copy()
+    f = object.__new__(ref.Focusr)
+    f.graph_target, f.graph_source = gt, gs
+    f.n_spectral_features, f.n_extra_spectral, f.n_total_spectral_features = n_spec, 3, n
+    f.target_eigenmap_as_reference = f.get_weighted_spectral_coords = True
+    f.initial_correspondence_type = f.final_correspondence_type = "kd"
+    f.graph_smoothing_iterations, f.projection_smooth_iterations, f.feature_smoothing_iterations = 300, 40, 40
+    sorter = ref.eigsort(graph_target=gt, graph_source=gs, n_features=n, target_as_reference=True)
+    f.Q = quiet(sorter.sort_eigenmaps)
+    f.calc_spectral_coords()
+    quiet(f.append_features_to_spectral_coords)
+    f.get_initial_correspondences()
+    idx0 = np.asarray(f.corresponding_target_idx_for_each_source_pt).copy()
+    f.get_smoothed_correspondences()
+    # port on the same pre-sort vectors
+    vt, vs = raw_t.copy(), raw_s.copy()
+    srt = port.sort_eigenmaps(mt.points, ms.points, gt.rand_idxs, gs.rand_idxs, gt.eig_vals, gs.eig_vals, vt, vs, n, True)
+    assert np.array_equal(f.Q, srt["Q"])
+    w = port.spectral_weights(srt["Q"], gs.eig_vals, gt.eig_vals, n_spec)
+    tc = port.features_as_coords(infos[0][0], [infos[0][1]], port.spectral_coords(vt, w, n_spec), 40)
+    sc = port.features_as_coords(infos[1][0], [infos[1][1]], port.spectral_coords(vs, w, n_spec), 40)
+    assert np.array_equal(tc, f.target_spectral_coords) and np.array_equal(sc, f.source_spectral_coords)
+    cs = port.correspondence_stage(dict(A=infos[0][0]), dict(A=infos[1][0]), mt.points, ms.points, tc, sc)
+    assert np.array_equal(cs["initial_idx"], idx0)
+    assert np.array_equal(cs["final_idx"], f.corresponding_target_idx_for_each_source_pt)
+    for name in ("Q", "target_matches", "source_matches", "flipped_pairs"):
+        out[f"{tag}_{name}"] = srt[name]
+    out[f"{tag}_spectral_weights"] = w
+    out[f"{tag}_target_coords_sha"] = np.array(sha(tc))
+    out[f"{tag}_source_coords_sha"] = np.array(sha(sc))
+    out[f"{tag}_initial_idx"] = idx0.astype(np.int32)
+    out[f"{tag}_final_idx"] = cs["final_idx"].astype(np.int32)
+    print(tag, "feature adjacency / features-as-coords / correspondences: port == reference (bitwise); eig",
+          np.sort(gt.eig_vals)[:3])
+    return out
+
+
 def main():
     if not os.path.isdir(REF):
         raise SystemExit("needs /root/reference (build container only)")
@@ -120,6 +191,7 @@ def main():
         os.path.join(GOLD, "meshes.npz"),
         **{n + "_points": m.points for n, m in meshes.items()},
         **{n + "_tris": m.tris for n, m in meshes.items()},
+        **{n + "_scalar": m.point_scalars[SCALAR] for n, m in meshes.items()},
     )
 
     out = {}
@@ -199,6 +271,7 @@ def main():
         out[f"{tag}_weighted_avg_sha"] = np.array(sha(cs["weighted_avg_transformed_points"]))
         out[f"{tag}_sorted_vecs_s_sha"] = np.array(sha(vs))
 
+    out.update(feature_case(ref, meshes["target_mesh"], meshes["source_mesh"]))
     np.savez_compressed(os.path.join(GOLD, "reference_outputs.npz"), **out)
     for fn in sorted(os.listdir(GOLD)):
         print(fn, os.path.getsize(os.path.join(GOLD, fn)) // 1024, "KiB")

@@ -65,8 +65,13 @@ def adjacency(points, tris):
     e = directed_edges(tris)
     n = p.shape[0]
     d = p[e[:, 0]] - p[e[:, 1]]
+    # points may carry range-scaled node features behind xyz (graph.py:166-175); np.sum over < 8
+    # squares is the plain left-to-right sum
+    s2 = d[:, 0] * d[:, 0]
+    for c in range(1, p.shape[1]):
+        s2 = s2 + d[:, c] * d[:, c]
     with np.errstate(divide="ignore"):
-        w = 1.0 / np.sqrt((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2])
+        w = 1.0 / np.sqrt(s2)
     key = e[:, 0] * n + e[:, 1]
     # last write wins; duplicates of one (p1,p2) carry the identical value, so any pick is exact
     uk, ui = np.unique(key, return_index=True)
@@ -376,3 +381,36 @@ def spectral_stage(pts_t, tris_t, pts_s, tris_s, n_spectral_features=3, n_extra_
     out.update(graph_target=gt, graph_source=gs, eigsort=srt, spectral_weights=w,
                target_spectral_coords=tc, source_spectral_coords=sc)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# optional node features (mesh scalars)                  graph.py:88-142,166-175; focusr.py:218-269
+# ---------------------------------------------------------------------------------------------------
+def normalized_node_feature(values, norm_using_std=True, cap_std=3, norm_range_0_to_1=True):
+    """graph.py:121-142."""
+    f = np.array(values, dtype=np.float64)
+    if norm_using_std:
+        f = (f - np.mean(f)) / np.std(f)
+        if cap_std is not False:
+            f[f > cap_std] = cap_std
+            f[f < -cap_std] = -cap_std
+    if norm_range_0_to_1:
+        f = (f - np.min(f)) / np.ptp(f)
+    return f
+
+
+def feature_augmented_points(points, node_features):
+    """graph.py:113-119,166-175: xyz followed by the features scaled to the mean xyz range."""
+    scale = np.mean(np.ptp(points, axis=0))
+    return np.concatenate([points] + [(f * scale)[:, None] for f in node_features], axis=1)
+
+
+def features_as_coords(a, node_features, coords, iterations=40):
+    """focusr.py:228-262 for one graph: smooth, rescale to [0, 1], scale to the spectral range."""
+    out = np.zeros((coords.shape[0], len(node_features)))
+    for k, f in enumerate(node_features):
+        g = mean_filter(a, f, iterations)
+        g = g - np.min(g)
+        g = g / np.max(g)
+        out[:, k] = np.ptp(coords) * g
+    return np.concatenate((coords, out), axis=1)

@@ -24,7 +24,9 @@ def _dev_i32(a):
 
 
 class DeviceGraph:
-    def __init__(self, points_list, tris_list):
+    def __init__(self, points_list, tris_list, edge_points_list=None):
+        """``edge_points_list`` (optional): per mesh [n][3+f] coordinates the edge weights are measured
+        in (xyz followed by range-scaled node features, reference graph.py:166-175); default = xyz."""
         torch = _torch()
         self.n_meshes = len(points_list)
         sizes = [int(np.asarray(p).shape[0]) for p in points_list]
@@ -36,7 +38,11 @@ class DeviceGraph:
         tris = np.concatenate(
             [np.asarray(t, dtype=np.int64).reshape(-1, 3) + int(o) for t, o in zip(tris_list, self.mesh_off_host[:-1])]
         ).astype(np.int32)
-        self._init_from_host(torch.from_numpy(pts), torch.from_numpy(np.ascontiguousarray(tris)))
+        edge_pts = None
+        if edge_points_list is not None:
+            edge_pts = torch.from_numpy(np.ascontiguousarray(np.concatenate(
+                [np.asarray(p, dtype=np.float64).reshape(len(p), -1) for p in edge_points_list])))
+        self._init_from_host(torch.from_numpy(pts), torch.from_numpy(np.ascontiguousarray(tris)), edge_pts)
 
     @classmethod
     def from_device(cls, points, tris, mesh_off_host):
@@ -49,7 +55,7 @@ class DeviceGraph:
         self._init_from_host(points, tris)
         return self
 
-    def _init_from_host(self, points, tris):
+    def _init_from_host(self, points, tris, edge_points=None):
         torch = _torch()
         dev = torch.device("cuda", torch.cuda.current_device())
         self.device = dev
@@ -67,7 +73,8 @@ class DeviceGraph:
         lib = _lib.load()
         ws_bytes = int(lib.focusr_laplacian_workspace_bytes(n, f))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        _lib.call("focusr_laplacian_build", _lib.ptr(self.points), _lib.ptr(self.tris), n, f, _lib.ptr(self.mesh_off), m,
+        ep = self.points if edge_points is None else edge_points.to(dev, non_blocking=True).contiguous()
+        _lib.call("focusr_laplacian_build", _lib.ptr(ep), int(ep.shape[1]), _lib.ptr(self.tris), n, f, _lib.ptr(self.mesh_off), m,
                   _lib.ptr(self.row_ptr), _lib.ptr(self.cols), _lib.ptr(self.weights), _lib.ptr(self.degree),
                   _lib.ptr(self.degree_inv), _lib.ptr(mesh_info), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
         # {nnz, one-way entries, zero-degree rows, non-finite weights} per mesh

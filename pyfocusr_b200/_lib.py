@@ -25,7 +25,7 @@ SIGNATURES = {
     "focusr_version": (_i, []),
     "focusr_launch_count": (C.c_ulonglong, []),
     "focusr_laplacian_workspace_bytes": (_sz, [_i, _i]),
-    "focusr_laplacian_build": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "focusr_laplacian_build": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "focusr_laplacian_csr": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "focusr_mean_filter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "focusr_gather_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),

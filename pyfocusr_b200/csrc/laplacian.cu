@@ -170,7 +170,7 @@ __global__ void k_edge_fill(const int* __restrict__ tris, int n_edges, int n_poi
 // sorted order is not), collapse duplicates (assignment semantics of graph.py:178: a repeated
 // directed edge carries the identical weight), and take the degree as the sequential
 // ascending-column sum of the weights (= scipy's A.sum(axis=1) bit for bit).
-__global__ void k_row_sort_unique(const double* __restrict__ points, int n_points,
+__global__ void k_row_sort_unique(const double* __restrict__ points, int pd, int n_points,
                                   const int* __restrict__ start, int* __restrict__ raw_cols,
                                   int* __restrict__ ucnt, double* __restrict__ degree,
                                   double* __restrict__ degree_inv) {
@@ -190,32 +190,30 @@ __global__ void k_row_sort_unique(const double* __restrict__ points, int n_point
   }
   int u = 0;
   double d = 0.0;
-  const double pi[3] = {points[3 * i], points[3 * i + 1], points[3 * i + 2]};
+  const double* pi = points + (size_t)pd * i;
   for (int a = 0; a < len; ++a) {
     const int v = c[a];
     if (a > 0 && v == c[u - 1]) continue;
     c[u++] = v;
-    const double pj[3] = {points[3 * v], points[3 * v + 1], points[3 * v + 2]};
-    d = FB_ADD(d, edge_weight(pi, pj));
+    d = FB_ADD(d, edge_weight(pi, points + (size_t)pd * v, pd));
   }
   ucnt[i] = u;
   degree[i] = d;
   degree_inv[i] = degree_inverse(d);
 }
 
-__global__ void k_compact(const double* __restrict__ points, int n_points,
+__global__ void k_compact(const double* __restrict__ points, int pd, int n_points,
                           const int* __restrict__ start, const int* __restrict__ raw_cols,
                           const int* __restrict__ row_ptr, int* __restrict__ cols,
                           double* __restrict__ weights) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_points) return;
   const int s = start[i], o = row_ptr[i], u = row_ptr[i + 1] - o;
-  const double pi[3] = {points[3 * i], points[3 * i + 1], points[3 * i + 2]};
+  const double* pi = points + (size_t)pd * i;
   for (int a = 0; a < u; ++a) {
     const int v = raw_cols[s + a];
-    const double pj[3] = {points[3 * v], points[3 * v + 1], points[3 * v + 2]};
     cols[o + a] = v;
-    weights[o + a] = edge_weight(pi, pj);
+    weights[o + a] = edge_weight(pi, points + (size_t)pd * v, pd);
   }
 }
 
@@ -344,12 +342,13 @@ size_t focusr_laplacian_workspace_bytes(int n_points, int n_tris) {
   return b + 1024;
 }
 
-int focusr_laplacian_build(const double* points, const int* tris, int n_points, int n_tris,
+int focusr_laplacian_build(const double* points, int point_dim, const int* tris, int n_points, int n_tris,
                            const int* mesh_point_off, int n_meshes, int* row_ptr, int* cols,
                            double* weights, double* degree, double* degree_inv, int* mesh_info,
                            void* workspace, size_t workspace_bytes, focusr_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   FB_REQUIRE(n_points > 0 && n_tris >= 0 && n_meshes > 0, "laplacian_build: empty input");
+  FB_REQUIRE(point_dim >= 1 && point_dim <= 64, "laplacian_build: point_dim must be in [1, 64]");
   FB_REQUIRE((long long)3 * n_tris < 2147483647LL, "laplacian_build: too many triangles for int32 CSR");
   Carver cv(workspace, workspace_bytes);
   int* cnt = cv.take<int>((size_t)n_points + 1);
@@ -379,12 +378,12 @@ int focusr_laplacian_build(const double* points, const int* tris, int n_points, 
     k_edge_fill<<<div_up(n_edges, T), T, 0, stream>>>(tris, n_edges, n_points, start, cursor, raw_cols);
     FB_COUNT_LAUNCH(1);
   }
-  k_row_sort_unique<<<div_up(n_points, T), T, 0, stream>>>(points, n_points, start, raw_cols, ucnt,
+  k_row_sort_unique<<<div_up(n_points, T), T, 0, stream>>>(points, point_dim, n_points, start, raw_cols, ucnt,
                                                            degree, degree_inv);
   FB_COUNT_LAUNCH(1);
   rc = exclusive_scan_i32(ucnt, row_ptr, n_points, scan_tmp, stream);
   if (rc) return rc;
-  k_compact<<<div_up(n_points, T), T, 0, stream>>>(points, n_points, start, raw_cols, row_ptr, cols, weights);
+  k_compact<<<div_up(n_points, T), T, 0, stream>>>(points, point_dim, n_points, start, raw_cols, row_ptr, cols, weights);
   k_mesh_stats<<<div_up(n_points, T), T, 0, stream>>>(row_ptr, cols, weights, n_points, mesh_point_off,
                                                       n_meshes, mesh_info);
   FB_COUNT_LAUNCH(2);

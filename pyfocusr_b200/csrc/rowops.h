@@ -24,13 +24,16 @@
 
 namespace fb {
 
-// Reference graph.py:177-178:  1.0 / np.sqrt(np.sum(np.square(X_pt1 - X_pt2)))
-// np.sum over 3 squares is the sequential (d0^2 + d1^2) + d2^2.
-FB_HD double edge_weight(const double* p1, const double* p2) {
+// Reference graph.py:163-178:  1.0 / np.sqrt(np.sum(np.square(X_pt1 - X_pt2))) where X_pt is xyz, or
+// xyz followed by the range-scaled node features when include_features_in_adj_matrix is set
+// (graph.py:166-175).  np.sum over fewer than 8 squares is the sequential ((d0^2 + d1^2) + d2^2) + ...
+FB_HD double edge_weight(const double* p1, const double* p2, int dim = 3) {
   const double d0 = FB_SUB(p1[0], p2[0]);
-  const double d1 = FB_SUB(p1[1], p2[1]);
-  const double d2 = FB_SUB(p1[2], p2[2]);
-  const double s = FB_ADD(FB_ADD(FB_MUL(d0, d0), FB_MUL(d1, d1)), FB_MUL(d2, d2));
+  double s = FB_MUL(d0, d0);
+  for (int c = 1; c < dim; ++c) {
+    const double d = FB_SUB(p1[c], p2[c]);
+    s = FB_ADD(s, FB_MUL(d, d));
+  }
   return FB_DIV(1.0, FB_SQRT(s));
 }
 

@@ -217,8 +217,26 @@ class Focusr(object):
             self.target_spectral_coords = np.concatenate(
                 (self.target_spectral_coords * self.graph_target.mean_pts_scale_range, self.graph_target.points), axis=1)
 
+    # ------------------------------------------------------------------ focusr.py:218-269
     def append_features_to_spectral_coords(self):
-        raise NotImplementedError("extra node features as coordinates (focusr.py:218-269) are outside the hot path")
+        if self.graph_source.n_extra_features != self.graph_target.n_extra_features:
+            raise Exception(
+                "Number of extra features between"
+                " target ({}) and source ({}) dont match!".format(
+                    self.graph_target.n_extra_features, self.graph_source.n_extra_features))
+        out = []
+        for graph, coords in ((self.graph_source, self.source_spectral_coords),
+                              (self.graph_target, self.target_spectral_coords)):
+            feats = np.zeros((graph.n_points, graph.n_extra_features))
+            for k in range(graph.n_extra_features):
+                f = graph.mean_filter_graph(graph.node_features[k], iterations=self.feature_smoothing_iterations)  # K5
+                f = f - np.min(f)
+                f = f / np.max(f)
+                feats[:, k] = np.ptp(coords) * f
+            out.append(feats)
+        self.source_extra_features, self.target_extra_features = out
+        self.source_spectral_coords = np.concatenate((self.source_spectral_coords, self.source_extra_features), axis=1)
+        self.target_spectral_coords = np.concatenate((self.target_spectral_coords, self.target_extra_features), axis=1)
 
     # ------------------------------------------------------------------ focusr.py:297-334 (CPD: cycpd)
     def register_target_to_source(self, reg_type="deformable"):

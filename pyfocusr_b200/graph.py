@@ -8,8 +8,9 @@ numpy / scipy objects exactly as in the reference (eigsort mutates ``eig_vecs`` 
 
 Deliberate differences, all documented in DESIGN.md:
   * ``feature_weights=None`` is accepted (the reference raises AttributeError, graph.py:41-42);
-  * curvature features need VTK and the features-in-adjacency / features-in-G options are outside
-    the hot path: they raise NotImplementedError instead of silently doing something else;
+  * curvature features need VTK and the features-in-G option does not terminate in the reference
+    itself: they raise NotImplementedError instead of silently doing something else (mesh-scalar
+    features, features in the adjacency and features as coordinates ARE supported);
   * eigenpairs come back in ascending order with a fixed sign convention (ARPACK's order is
     ascending up to near-ties and its sign is random).
 """
@@ -98,9 +99,10 @@ class Graph(object):
         self.n_extra_features = len(self.node_features)
         self.feature_weights = np.eye(self.n_extra_features) if feature_weights is None else feature_weights
         self.mean_xyz_range_scaled_features = [f * self.mean_pts_scale_range for f in self.node_features]
-        if self.n_extra_features > 0 and (include_features_in_adj_matrix or include_features_in_G_matrix):
+        if self.n_extra_features > 0 and include_features_in_G_matrix:
             raise NotImplementedError(
-                "features in the adjacency / G matrix (graph.py:166-175,191-210) are outside the B200 hot path"
+                "features in the G matrix (graph.py:191-210) are not supported: the reference's own branch does not "
+                "terminate with current numpy/scipy (np.ptp of a sparse matrix), so there is nothing to match"
             )
         self._dev = None
 
@@ -122,7 +124,11 @@ class Graph(object):
     # --- device graph ---------------------------------------------------------------------------
     def _device_graph(self):
         if self._dev is None:
-            self._dev = DeviceGraph([self.points], [self._tris])
+            edge_pts = None
+            if (self.n_extra_features > 0) & (self.include_features_in_adj_matrix is True):
+                # graph.py:166-175: the features, scaled to the mean xyz range, extend the position
+                edge_pts = [np.concatenate([self.points] + [f[:, None] for f in self.mean_xyz_range_scaled_features], axis=1)]
+            self._dev = DeviceGraph([self.points], [self._tris], edge_pts)
         return self._dev
 
     # graph.py:148-178  (K1)

@@ -26,7 +26,7 @@ def shipped_meshes():
 
     z = np.load(os.path.join(GOLDEN, "meshes.npz"))
     names = ["target_mesh", "source_mesh", "target_mesh_15k", "source_mesh_15k"]
-    return {n: PolyData(z[n + "_points"], z[n + "_tris"]) for n in names}
+    return {n: PolyData(z[n + "_points"], z[n + "_tris"], {"thickness_change_(mm)": z[n + "_scalar"]}) for n in names}
 
 
 @pytest.fixture(scope="session")
@@ -50,6 +50,6 @@ def hostsim():
                                  dp, dp, ip, dp]
     lib.hostsim_rr_sym.argtypes = [dp, dp, dp, dp, C.c_int]
     lib.hostsim_eig_general.argtypes = [dp, C.c_int, dp, dp]
-    lib.hostsim_edge_weight.argtypes = [dp, dp]
+    lib.hostsim_edge_weight.argtypes = [dp, dp, C.c_int]
     lib.hostsim_edge_weight.restype = C.c_double
     return lib

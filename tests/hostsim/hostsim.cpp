@@ -239,5 +239,5 @@ int hostsim_eig_general(const double* a, int n, double* evals_ri, double* evecs_
   return rc;
 }
 
-double hostsim_edge_weight(const double* p1, const double* p2) { return fb::edge_weight(p1, p2); }
+double hostsim_edge_weight(const double* p1, const double* p2, int dim) { return fb::edge_weight(p1, p2, dim); }
 }

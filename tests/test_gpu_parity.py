@@ -560,3 +560,42 @@ def test_focusr_dropin_variants_5k(torch, shipped_meshes):
         assert np.array_equal(f.weighted_avg_transformed_points, cs["weighted_avg_transformed_points"]), kw
         if "n_coords_spectral_ordering" in kw:
             assert np.array_equal(f.graph_target.rand_idxs, np.arange(5000))
+
+
+def test_mesh_scalar_features_in_adjacency_and_as_coordinates(torch, shipped_meshes, golden):
+    """a mesh point scalar as extra node feature -- inside the edge weights
+    (graph.py:166-175; K1 with point_dim = 4) and smoothed + appended to the spectral coordinates
+    (focusr.py:218-269; K5 with one column)."""
+    from oracle import port
+    import pyfocusr_b200 as pyfocusr
+
+    name = "thickness_change_(mm)"
+    mt, ms = shipped_meshes["target_mesh"], shipped_meshes["source_mesh"]
+    for side, m in (("t", mt), ("s", ms)):
+        g = pyfocusr.Graph(m, n_spectral_features=6, n_rand_samples=100, list_features_to_get_from_mesh=[name],
+                           include_features_in_adj_matrix=True)
+        g.get_graph_spectrum()
+        a = g.adjacency_matrix
+        assert sha(a.data) + sha(a.indices) + sha(a.indptr) == str(golden["5k_feat_%s_A_sha" % side])
+        gold = np.sort(golden["5k_feat_%s_eig_vals" % side])
+        assert g.eig_vals.shape == gold.shape and np.max(np.abs(g.eig_vals - gold) / gold) <= 1e-6
+    np.random.seed(11)
+    f = pyfocusr.Focusr(mt, ms, icp_register_first=False, list_features_to_calc=[], list_features_to_get_from_mesh=[name],
+                        include_features_in_adj_matrix=True, use_features_as_coords=True, registration="identity")
+    vt0, vs0 = f.graph_target.eig_vecs.copy(), f.graph_source.eig_vecs.copy()
+    f.align_maps()
+    feats = [port.normalized_node_feature(m.point_scalars[name]) for m in (mt, ms)]
+    at = port.adjacency(port.feature_augmented_points(mt.points, [feats[0]]), mt.tris)
+    as_ = port.adjacency(port.feature_augmented_points(ms.points, [feats[1]]), ms.tris)
+    srt = port.sort_eigenmaps(mt.points, ms.points, f.graph_target.rand_idxs, f.graph_source.rand_idxs,
+                              f.graph_target.eig_vals, f.graph_source.eig_vals, vt0, vs0, 6, True)
+    assert np.max(np.abs(f.Q - srt["Q"]) / srt["Q"]) <= 1e-9
+    w = f.spectral_weights
+    tc = port.features_as_coords(at, [feats[0]], port.spectral_coords(vt0, w, 3), 40)
+    sc = port.features_as_coords(as_, [feats[1]], port.spectral_coords(vs0, w, 3), 40)
+    assert f.target_spectral_coords.shape == (5000, 4)
+    assert np.array_equal(f.target_spectral_coords, tc) and np.array_equal(f.source_spectral_coords, sc)
+    cs = port.correspondence_stage(dict(A=at), dict(A=as_), mt.points, ms.points, tc, sc)
+    assert np.array_equal(f.corresponding_target_idx_for_each_source_pt, cs["final_idx"])
+    with pytest.raises(NotImplementedError):
+        pyfocusr.Graph(mt, list_features_to_get_from_mesh=[name], include_features_in_G_matrix=True)

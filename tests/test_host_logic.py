@@ -48,8 +48,9 @@ def test_eig_general_matches_numpy(hostsim, n):
 def test_edge_weight_matches_numpy(hostsim):
     rng = np.random.RandomState(0)
     for _ in range(200):
-        p1, p2 = rng.standard_normal(3) * 50, rng.standard_normal(3) * 50
-        assert hostsim.hostsim_edge_weight(p1, p2) == 1.0 / np.sqrt(np.sum(np.square(p1 - p2)))
+        for dim in (3, 4, 5):
+            p1, p2 = rng.standard_normal(dim) * 50, rng.standard_normal(dim) * 50
+            assert hostsim.hostsim_edge_weight(p1, p2, dim) == 1.0 / np.sqrt(np.sum(np.square(p1 - p2)))
 
 
 # ------------------------------------------------------------------------------------------------ solver driver
