@@ -154,6 +154,26 @@ class SpectralBatch:
                     eig_vecs_presort=presort)
 
     # ------------------------------------------------------------------------------------------
+    def fetch(self, out, keys=("final_idx", "weighted_avg_transformed_points")):
+        """Device -> host read-back of the per-vertex results into reusable pinned buffers (one
+        asynchronous copy each, then a single synchronisation).  Returns numpy views that stay valid
+        until the next ``fetch``."""
+        torch = _lib.require_cuda()
+        if not hasattr(self, "_pinned"):
+            self._pinned = {}
+        res = {}
+        for k in keys:
+            t = out[k]
+            buf = self._pinned.get(k)
+            if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+                buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                self._pinned[k] = buf
+            buf.copy_(t, non_blocking=True)
+            res[k] = buf
+        torch.cuda.current_stream().synchronize()
+        return {k: v.numpy() for k, v in res.items()}
+
+    # ------------------------------------------------------------------------------------------
     def run_meshes(self, targets, sources, **kw):
         """Convenience: lists of PolyData-like meshes (``.points``, ``.tris``)."""
         torch = _lib.require_cuda()

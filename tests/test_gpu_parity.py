@@ -596,3 +596,33 @@ def test_mesh_scalar_features_in_adjacency_and_as_coordinates(torch, shipped_mes
     assert np.array_equal(f.corresponding_target_idx_for_each_source_pt, cs["final_idx"])
     with pytest.raises(NotImplementedError):
         pyfocusr.Graph(mt, list_features_to_get_from_mesh=[name], include_features_in_G_matrix=True)
+
+
+def test_error_behaviour_and_degenerate_inputs(torch):
+    """Degenerate geometry the reference does not check is reported, not propagated."""
+    from pyfocusr_b200 import _device
+    from pyfocusr_b200._device import DeviceGraph
+    from pyfocusr_b200._lib import FocusrB200Error
+    from pyfocusr_b200.mesh import icosphere
+
+    m = icosphere(6)
+    pts = m.points.copy()
+    pts[m.tris[0, 1]] = pts[m.tris[0, 0]]                      # zero-length edge -> 1/0 weight (graph.py:177-178)
+    g = DeviceGraph([pts], [m.tris])
+    assert g.mesh_info_host[0, 3] > 0
+    with pytest.raises(FocusrB200Error, match="non-finite"):
+        g.eigs_smallest(k=7, n_k_needed=6)
+    tiny = icosphere(1)                                         # 12 vertices < block size
+    with pytest.raises(FocusrB200Error, match="fewer vertices"):
+        DeviceGraph([tiny.points], [tiny.tris]).eigs_smallest(k=7, n_k_needed=6)
+    # a mesh without any triangle: every row has zero degree, the Laplacian is empty
+    g0 = DeviceGraph([m.points], [np.zeros((0, 3), dtype=np.int32)])
+    assert g0.nnz == 0 and g0.mesh_info_host[0].tolist() == [0, 0, m.points.shape[0], 0]
+    assert g0.laplacian_host()[0][-1] == 0
+    # more neighbours requested than references exist: missing slots are -1 / inf
+    refs = torch.from_numpy(np.random.RandomState(0).rand(2, 3)).cuda()
+    qs = torch.from_numpy(np.random.RandomState(1).rand(5, 3)).cuda()
+    idx, dist = _device.knn(refs, qs, k=3)
+    assert torch.all(idx[:, 2] == -1) and torch.all(torch.isinf(dist[:, 2])) and torch.all(idx[:, :2] >= 0)
+    with pytest.raises(FocusrB200Error):
+        _device.knn(refs, qs, k=9)

@@ -247,3 +247,17 @@ def test_decide_batch_equals_per_pair_scipy():
                 d1, s1, sg1 = moves_from_matches(tm, sm, fl, ref_is_target)
                 assert np.array_equal(q[p], q1) and np.array_equal(d[p], d1) and np.array_equal(s[p], s1)
                 assert np.array_equal(sg[p], sg1)
+
+
+def test_non_triangle_cells_are_rejected():
+    class Quad:
+        def GetNumberOfPoints(self): return 4
+        def GetPoint(self, i): return (float(i), 0.0, 0.0)
+        def GetNumberOfCells(self): return 1
+        def GetCell(self, i):
+            class C:
+                def GetNumberOfEdges(self): return 4
+            return C()
+
+    with pytest.raises(ValueError, match="triangle"):
+        fmesh.mesh_arrays(Quad())
