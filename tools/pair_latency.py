@@ -1,0 +1,28 @@
+"""Wall-clock of the drop-in single-pair API on the shipped 15k pair (BASELINE.json configs[0]) and the 5k pair
+(configs[1], n_spectral_features=10), ICP off / CPD identity, next to the CPU oracle port on the same inputs."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import pyfocusr_b200 as pyfocusr
+from pyfocusr_b200.mesh import PolyData
+from oracle import port
+
+z = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "meshes.npz"))
+def mesh(n): return PolyData(z[n + "_points"], z[n + "_tris"])
+for tag, (tn, sn), kw in (("configs[0] 15k pair, defaults", ("target_mesh_15k", "source_mesh_15k"), {}),
+                          ("configs[1] 5k pair, n_spectral_features=10", ("target_mesh", "source_mesh"), dict(n_spectral_features=10))):
+    mt, ms = mesh(tn), mesh(sn)
+    for rep in range(3):
+        np.random.seed(0)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        f = pyfocusr.Focusr(mt, ms, icp_register_first=False, list_features_to_calc=[], registration="identity", **kw)
+        t1 = time.perf_counter()
+        f.align_maps()
+        torch.cuda.synchronize(); t2 = time.perf_counter()
+    ns = kw.get("n_spectral_features", 3)
+    np.random.seed(0)
+    t3 = time.perf_counter()
+    port.spectral_stage(mt.points, mt.tris, ms.points, ms.tris, ns, 3, 5000)
+    t4 = time.perf_counter()
+    print("%s: B200 drop-in Focusr() %.3f s + align_maps() %.3f s = %.3f s;  CPU oracle port %.2f s  (eigenpairs kept: %d / %d)" % (
+        tag, t1 - t0, t2 - t1, t2 - t0, t4 - t3, f.graph_target.eig_vals.size, f.graph_source.eig_vals.size), flush=True)
