@@ -133,8 +133,9 @@ int focusr_eigs_smallest_dist(const int* row_ptr, const int* cols_local, const d
 void focusr_profile_reset(void);
 void focusr_profile_get(double* out4_host);
 
-/* Tuning knobs (experiments and A/B profiling).  key 0: variant of the filter-step kernel for b = 16
- * (0 = default; see csrc/spmm.cu). */
+/* Tuning knobs (experiments and A/B profiling; see the tuning records in csrc/spmm.cu, csrc/eigs.cu).
+ * key 0: filter-step kernel (0 = register-capped gather kernel, 1 = TMA bulk-staged y window in
+ * shared memory, b <= 32);  key 1: L2 budget in MB for blocking the filter over mesh groups (0 = off). */
 int focusr_set_tuning(int key, int value);
 
 /* y = L x for a dense block of n_cols vectors (n_cols a multiple of 8, <= 96), used by tests and

@@ -28,7 +28,9 @@ constexpr int SPMM_ROWS_PER_BLOCK = 256;
 // registers at 32 (8 CTAs = 64 warps per SM) took the filter step from 4151 to 4288 GB/s.  What
 // does not help on B200: staging the CSR entries in shared memory (occupancy drops to 16 warps,
 // 1.8 TB/s), fetching 8 entries then issuing 8 gathers back to back (2.9 TB/s), or loading the
-// warp's entry range with one coalesced load and distributing it by shuffles (3.1 TB/s).
+// warp's entry range with one coalesced load and distributing it by shuffles (3.1 TB/s), bringing the
+// CTA's window of y rows into shared memory with one TMA bulk copy (k_spmm_staged below: 3.7 TB/s in the
+// filter, 4 CTAs/SM), or blocking the filter over groups of meshes that fit the 126 MB L2 (eigs.cu).
 template <int B, int TPR, int MODE>
 __global__ void __launch_bounds__(SPMM_THREADS, (B / (2 * TPR) == 1) ? 8 : ((B / (2 * TPR) == 2) ? 6 : 3))
 k_spmm(const int* __restrict__ row_ptr, const int* __restrict__ cols, const double* __restrict__ weights,
@@ -97,11 +99,153 @@ k_spmm(const int* __restrict__ row_ptr, const int* __restrict__ cols, const doub
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// TMA-staged variant: the window of y rows the CTA's rows gather from -- its own 256 rows plus
+// SPMM_HALO rows either side, which is where mesh neighbours live for locality-ordered vertices --
+// is brought into shared memory by ONE bulk asynchronous copy (cp.async.bulk, SASS UBLKCP) signalled
+// through an mbarrier; gathers hit shared memory, columns outside the window fall back to global.
+// Selected with focusr_set_tuning(0, 1).  Measured on B200 (256 meshes x 15 212 vertices, b = 16): bit-identical
+// output, 3712 GB/s in the filter against 4355 GB/s for k_spmm -- the hardware L1 already serves 59% of the
+// gathers and the 48 KB window costs half the resident warps -- so it is kept as an A/B variant, not the default.
+// ---------------------------------------------------------------------------------------------
+constexpr int SPMM_HALO = 64;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <int B, int TPR, int MODE>
+__global__ void __launch_bounds__(SPMM_THREADS, 4)
+k_spmm_staged(const int* __restrict__ row_ptr, const int* __restrict__ cols, const double* __restrict__ weights,
+              const double* __restrict__ degree, const double* __restrict__ degree_inv,
+              const int* __restrict__ mesh_off, const double* __restrict__ y, const double* __restrict__ x_prev,
+              double* __restrict__ out, const double* __restrict__ alpha, const double* __restrict__ gamma,
+              const double* __restrict__ center, int step, int n_steps) {
+  constexpr int VPT = B / (2 * TPR);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* s_y = reinterpret_cast<double*>(smem_raw);  // [(ROWS + 2 HALO)][B]
+  __shared__ __align__(8) unsigned long long s_bar;
+  const int mesh = blockIdx.y;
+  const int m_lo = mesh_off[mesh], m_hi = mesh_off[mesh + 1];
+  const int r0 = m_lo + blockIdx.x * SPMM_ROWS_PER_BLOCK;
+  const int r1 = min(m_hi, r0 + SPMM_ROWS_PER_BLOCK);
+  if (r0 >= r1) return;
+  const int w0 = max(m_lo, r0 - SPMM_HALO), w1 = min(m_hi, r1 + SPMM_HALO);
+  const unsigned bar = smem_u32(&s_bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned bytes = (unsigned)(w1 - w0) * B * 8u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(s_y)),
+                 "l"(y + (size_t)w0 * B), "r"(bytes), "r"(bar)
+                 : "memory");
+  }
+  double al = 1.0, ga = 0.0, cc = 0.0;
+  if (MODE == 0) {
+    al = alpha[(size_t)mesh * n_steps + step];
+    ga = gamma[(size_t)mesh * n_steps + step];
+    cc = center[mesh];
+  }
+  const int g = threadIdx.x / TPR, t = threadIdx.x % TPR;
+  // first row's pointers are fetched while the bulk copy is in flight
+  int row = r0 + g;
+  int p0 = row < r1 ? row_ptr[row] : 0, p1 = row < r1 ? row_ptr[row + 1] : 0;
+  {
+    unsigned done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(bar)
+          : "memory");
+    }
+  }
+  for (; row < r1; row += SPMM_THREADS / TPR) {
+    double2 acc[VPT];
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) acc[v] = make_double2(0.0, 0.0);
+#pragma unroll 4
+    for (int p = p0; p < p1; ++p) {
+      const int c = cols[p];
+      const double w = weights[p];
+      const bool in_win = c >= w0 && c < w1;
+      const double2* src = in_win ? reinterpret_cast<const double2*>(s_y + (size_t)(c - w0) * B)
+                                  : reinterpret_cast<const double2*>(y + (size_t)c * B);
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) {
+        const double2 a = src[t + v * TPR];
+        acc[v].x = fma(w, a.x, acc[v].x);
+        acc[v].y = fma(w, a.y, acc[v].y);
+      }
+    }
+    const double d = degree[row];
+    const double di = degree_inv[row];
+    const double2* yr = reinterpret_cast<const double2*>(s_y + (size_t)(row - w0) * B);
+    const double2* xr = reinterpret_cast<const double2*>(x_prev + (size_t)row * B);
+    double2* o = reinterpret_cast<double2*>(out + (size_t)row * B);
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      const double2 yv = yr[t + v * TPR];
+      double2 r;
+      if (MODE == 1) {
+        r.x = d * yv.x - acc[v].x;
+        r.y = d * yv.y - acc[v].y;
+      } else if (MODE == 2) {
+        r.x = di * (d * yv.x - acc[v].x);
+        r.y = di * (d * yv.y - acc[v].y);
+      } else {
+        const double lx = di * (d * yv.x - acc[v].x);
+        const double ly = di * (d * yv.y - acc[v].y);
+        r.x = al * (lx - cc * yv.x);
+        r.y = al * (ly - cc * yv.y);
+        if (ga != 0.0) {
+          const double2 xv = __ldg(xr + t + v * TPR);
+          r.x -= ga * xv.x;
+          r.y -= ga * xv.y;
+        }
+      }
+      o[t + v * TPR] = r;
+    }
+    const int nrow = row + SPMM_THREADS / TPR;
+    if (nrow < r1) {
+      p0 = row_ptr[nrow];
+      p1 = row_ptr[nrow + 1];
+    }
+  }
+}
+
+int g_spmm_variant = 0;  // focusr_set_tuning(0, v): 0 = register-capped gather kernel, 1 = TMA-staged window
+
 template <int B, int TPR>
 static int launch_spmm_b(int mode, const SpmmGraph& g, const double* y, const double* x_prev, double* out,
                          const double* alpha, const double* gamma, const double* center, int step,
                          int n_steps, cudaStream_t stream) {
   dim3 grid(div_up(g.max_mesh_rows, SPMM_ROWS_PER_BLOCK), g.n_meshes);
+  if (g_spmm_variant == 1 && B <= 32) {
+    const size_t smem = sizeof(double) * (size_t)(SPMM_ROWS_PER_BLOCK + 2 * SPMM_HALO) * B;
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(k_spmm_staged<B, TPR, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k_spmm_staged<B, TPR, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(k_spmm_staged<B, TPR, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      attr_done = true;
+    }
+    if (mode == 0)
+      k_spmm_staged<B, TPR, 0><<<grid, SPMM_THREADS, smem, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv,
+                                                                     g.mesh_off, y, x_prev, out, alpha, gamma, center, step, n_steps);
+    else if (mode == 1)
+      k_spmm_staged<B, TPR, 1><<<grid, SPMM_THREADS, smem, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv,
+                                                                     g.mesh_off, y, x_prev, out, alpha, gamma, center, step, n_steps);
+    else
+      k_spmm_staged<B, TPR, 2><<<grid, SPMM_THREADS, smem, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv,
+                                                                     g.mesh_off, y, x_prev, out, alpha, gamma, center, step, n_steps);
+    FB_COUNT_LAUNCH(1);
+    return FB_OK;
+  }
   if (mode == 0)
     k_spmm<B, TPR, 0><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv,
                                                          g.mesh_off, y, x_prev, out, alpha, gamma, center, step, n_steps);
@@ -226,6 +370,10 @@ using namespace fb;
 extern "C" {
 
 int focusr_set_tuning(int key, int value) {
+  if (key == 0) {
+    fb::g_spmm_variant = value;
+    return 0;
+  }
   if (key == 1) {
     fb::g_l2_budget_mb = value;
     return 0;

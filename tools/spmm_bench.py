@@ -16,7 +16,8 @@ x = torch.randn((g.n_points, b), dtype=torch.float64, device="cuda")
 lib = _lib.load()
 nbytes = 12.0 * g.nnz + 20.0 * g.n_points + 16.0 * b * g.n_points
 ref = None
-for var in (0,):
+for var in (0, 1):
+    lib.focusr_set_tuning(0, var)
     y = g.laplacian_apply(x)
     if ref is None:
         ref = y.clone()
