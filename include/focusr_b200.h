@@ -111,7 +111,18 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
  * (rank 0: focusr_dist_unique_id, broadcast by the caller, then focusr_dist_init on every rank).
  * Every rank runs the same driver and sees identical Ritz values, so all control decisions agree.
  * Outputs: eig_vals [ldv] (identical on all ranks), eig_vecs [n_local][ldv] (this rank's rows).
+ *
+ * P2P mode (use_p2p = 1): the halo is FUSED into the SpMM.  Every rank keeps its three vector blocks
+ * in a region shared through CUDA IPC (focusr_dist_shared_alloc -> 64-byte handle, exchanged by the
+ * caller, focusr_dist_shared_open) and the kernel gathers a remote column straight from the owning
+ * rank's HBM over NVLink (ghost g lives at row ghost_row[g] of rank ghost_peer[g]); no pack / send /
+ * receive, no ghost copies, and the steps are ordered by a flag barrier in peer memory instead of a
+ * collective.  `rows_cap` = the largest n_local of any rank (identical layout on every rank).
  * ------------------------------------------------------------------------------------------- */
+size_t focusr_dist_shared_bytes(int rows_cap, int block_size, int world);
+int focusr_dist_shared_alloc(size_t bytes, char* handle64_host);
+int focusr_dist_shared_open(const char* handles_host, int rank, int world);
+int focusr_dist_shared_free(void);
 int focusr_dist_unique_id(char* out128_host);
 int focusr_dist_init(const char* id128_host, int rank, int world);
 int focusr_dist_finalize(void);
@@ -120,7 +131,8 @@ int focusr_eigs_smallest_dist(const int* row_ptr, const int* cols_local, const d
                               const double* degree, const double* degree_inv, const double* points,
                               int n_local, int n_ghost, long long row_begin_global, long long nnz_local,
                               const int* send_idx, int n_send, const int* send_counts_host,
-                              const int* recv_counts_host, int n_zero_rows_global, int k,
+                              const int* recv_counts_host, const int* ghost_peer, const int* ghost_row,
+                              int use_p2p, int rows_cap, int n_zero_rows_global, int k,
                               int n_k_needed, int k_buffer, double min_eig_val, double tol,
                               int max_outer, int block_size, double spectrum_upper_bound,
                               double* eig_vals, double* eig_vecs, int ldv, int* result_i_host,

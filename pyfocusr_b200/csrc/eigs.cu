@@ -464,6 +464,17 @@ struct DistCtx {
   double* sendbuf = nullptr;       // device [n_send][B]
   double* small = nullptr;         // device scratch for all-reduced small blocks
   int* fake_off = nullptr;         // device {0, 1}: lets the chunk-summing kernels read one chunk
+  // --- P2P mode: halo fused into the SpMM, vector blocks live in an IPC-shared region ---
+  bool p2p = false;
+  double* blocks = nullptr;              // this rank's three [rows_cap][B] blocks inside the shared region
+  size_t block_stride = 0;               // doubles between consecutive blocks
+  const double* const* peer_blocks = nullptr;  // device [3][world]: block k of rank p
+  unsigned long long* flags = nullptr;   // this rank's flag slots (one 128-byte line per peer)
+  unsigned long long* const* peer_flags = nullptr;  // device [world]: flag array of rank p
+  const int* ghost_peer = nullptr;       // device [n_ghost]
+  const int* ghost_row = nullptr;        // device [n_ghost]
+  int* dev_err = nullptr;                // device flag raised by a barrier time-out
+  unsigned long long epoch = 0;
 };
 static ncclComm_t g_dist_comm = nullptr;
 static int g_dist_rank = 0, g_dist_world = 1;
@@ -554,6 +565,40 @@ k_write_scaled(const double* __restrict__ x, const double* __restrict__ theta, i
   if (threadIdx.x == 0) eig_vals[j] = theta[c];
 }
 
+
+// Inter-GPU barrier through flags in peer memory: lane p publishes `epoch` into slot `rank` of rank
+// p's flag array (st.release.sys over NVLink) and waits until rank p has published the same epoch
+// here.  Kernels of different ranks run on different GPUs, so the spin always makes progress; a
+// generous cycle budget turns a lost peer into an error instead of a hang.
+__global__ void k_peer_barrier(unsigned long long* my_flags, unsigned long long* const* peer_flags, int rank,
+                               int world, unsigned long long epoch, int* err) {
+  const int p = threadIdx.x;
+  if (p >= world || p == rank) return;
+  __threadfence_system();
+  unsigned long long* dst = peer_flags[p] + (size_t)rank * 16;  // 16 x 8 B = one 128-byte line per slot
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(epoch) : "memory");
+  const unsigned long long* src = my_flags + (size_t)p * 16;
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+    if (v >= epoch) break;
+    if (clock64() - t0 > 20000000000LL) {  // ~10 s at 1.9 GHz
+      atomicExch(err, 1);
+      break;
+    }
+  }
+}
+
+struct PeerShared {
+  void* base = nullptr;
+  size_t bytes = 0;
+  int world = 0, rank = 0;
+  std::vector<void*> peer;
+};
+static PeerShared g_shared;
+constexpr size_t PEER_FLAG_BYTES = 128;
+
 struct CudaBackend {
   // graph of this run (rows are the run's meshes; pointers are global, offsets select the run)
   SpmmGraph g;
@@ -596,6 +641,12 @@ struct CudaBackend {
   // refresh the ghost rows of a [n_loc + n_ghost][B] block from their owners
   void halo_exchange(double* x) {
     if (!dist || dist->world == 1) return;
+    if (dist->p2p) {  // nothing moves: peers read the rows in place; only order the steps
+      ++dist->epoch;
+      k_peer_barrier<<<1, 32, 0, stream>>>(dist->flags, dist->peer_flags, dist->rank, dist->world, dist->epoch, dist->dev_err);
+      FB_COUNT_LAUNCH(1);
+      return;
+    }
     NcclApi& api = nccl_api();
     if (dist->n_send > 0) {
       k_pack_rows<<<div_up((long long)dist->n_send * B, 256), 256, 0, stream>>>(x, dist->send_idx, dist->n_send, B, dist->sendbuf);
@@ -614,6 +665,15 @@ struct CudaBackend {
       ro += rcnt;
     }
     nccl_check(api.GroupEnd(), "group end");
+  }
+  int block_index(const double* ptr) const { return (int)((ptr - dist->blocks) / (ptrdiff_t)dist->block_stride); }
+  void spmm(int mode, const SpmmGraph& gg, const double* y, const double* x_prev, double* out, const double* al,
+            const double* ga, const double* ce, int step, int n_steps) {
+    if (dist && dist->p2p && dist->world > 1)
+      launch_spmm_p2p(mode, B, gg, dist->n_loc, y, dist->peer_blocks + (size_t)block_index(y) * dist->world,
+                      dist->ghost_peer, dist->ghost_row, x_prev, out, al, ga, ce, step, n_steps, stream);
+    else
+      launch_spmm(mode, B, gg, y, x_prev, out, al, ga, ce, step, n_steps, stream);
   }
   void all_reduce(void* buf, size_t count, int dtype, int op, const char* what) {
     if (!dist || dist->world == 1) return;
@@ -673,7 +733,7 @@ struct CudaBackend {
   }
   void apply_DmA() {  // Z (stored in Xn) = (D - A) X
     halo_exchange(X);
-    launch_spmm(1, B, g, X, X, Xn, nullptr, nullptr, nullptr, 0, 0, stream);
+    spmm(1, g, X, X, Xn, nullptr, nullptr, nullptr, 0, 0);
     check("apply_DmA");
   }
   void gram() {
@@ -806,7 +866,7 @@ struct CudaBackend {
         double *c2 = cur, *p2 = prev, *n2 = next;
         for (int s = 0; s < len; ++s) {
           halo_exchange(c2);
-          launch_spmm(0, B, gg, c2, p2, n2, alpha + (size_t)m0 * len, gamma + (size_t)m0 * len, center + m0, s, len, stream);
+          spmm(0, gg, c2, p2, n2, alpha + (size_t)m0 * len, gamma + (size_t)m0 * len, center + m0, s, len);
           double* t = p2;
           p2 = c2;
           c2 = n2;
@@ -1072,15 +1132,75 @@ int focusr_dist_finalize(void) {
   return FB_OK;
 }
 
+
+// ---- IPC-shared region for the P2P-fused halo: [flags: world x 128 B][3 x rows_cap x B doubles] ----
+static size_t shared_flag_bytes(int world) { return align_up((size_t)world * PEER_FLAG_BYTES); }
+
+size_t focusr_dist_shared_bytes(int rows_cap, int block_size, int world) {
+  return shared_flag_bytes(world) + 3 * align_up(sizeof(double) * (size_t)rows_cap * block_size);
+}
+
+int focusr_dist_shared_alloc(size_t bytes, char* handle64_host) {
+  if (g_shared.base) {
+    for (int p = 0; p < (int)g_shared.peer.size(); ++p)
+      if (g_shared.peer[p] && p != g_shared.rank) cudaIpcCloseMemHandle(g_shared.peer[p]);
+    cudaFree(g_shared.base);
+    g_shared = PeerShared();
+  }
+  FB_CUDA(cudaMalloc(&g_shared.base, bytes));
+  FB_CUDA(cudaMemset(g_shared.base, 0, bytes));
+  g_shared.bytes = bytes;
+  cudaIpcMemHandle_t h;
+  FB_CUDA(cudaIpcGetMemHandle(&h, g_shared.base));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64_host, &h, 64);
+  FB_CUDA(cudaDeviceSynchronize());
+  return FB_OK;
+}
+
+int focusr_dist_shared_open(const char* handles_host, int rank, int world) {
+  FB_REQUIRE(g_shared.base != nullptr, "dist_shared_open: allocate first");
+  g_shared.peer.assign(world, nullptr);
+  g_shared.world = world;
+  g_shared.rank = rank;
+  for (int p = 0; p < world; ++p) {
+    if (p == rank) {
+      g_shared.peer[p] = g_shared.base;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles_host + (size_t)p * 64, 64);
+    FB_CUDA(cudaIpcOpenMemHandle(&g_shared.peer[p], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  return FB_OK;
+}
+
+int focusr_dist_shared_free(void) {
+  if (g_shared.base) {
+    for (int p = 0; p < (int)g_shared.peer.size(); ++p)
+      if (g_shared.peer[p] && p != g_shared.rank) cudaIpcCloseMemHandle(g_shared.peer[p]);
+    cudaFree(g_shared.base);
+  }
+  g_shared = PeerShared();
+  return FB_OK;
+}
+static unsigned long long g_peer_epoch = 0;
+
 static size_t dist_extra_layout(int n_send, int B, int world, DistCtx* d, Carver& cv) {
   double* sendbuf = cv.take<double>((size_t)std::max(n_send, 1) * B);
   const size_t small_n = std::max((size_t)2 * B * B, (size_t)4 * B * (world + 1));
   double* small = cv.take<double>(small_n);
   int* fake_off = cv.take<int>(2);
+  const double** peer_blocks = cv.take<const double*>((size_t)3 * world);
+  unsigned long long** peer_flags = cv.take<unsigned long long*>((size_t)world);
+  int* dev_err = cv.take<int>(2);
   if (d) {
     d->sendbuf = sendbuf;
     d->small = small;
     d->fake_off = fake_off;
+    d->peer_blocks = peer_blocks;
+    d->peer_flags = peer_flags;
+    d->dev_err = dev_err;
   }
   return cv.used + 256;
 }
@@ -1095,7 +1215,8 @@ int focusr_eigs_smallest_dist(const int* row_ptr, const int* cols_local, const d
                               const double* degree, const double* degree_inv, const double* points,
                               int n_local, int n_ghost, long long row_begin_global, long long nnz_local,
                               const int* send_idx, int n_send, const int* send_counts_host,
-                              const int* recv_counts_host, int n_zero_rows_global, int k, int n_k_needed,
+                              const int* recv_counts_host, const int* ghost_peer, const int* ghost_row,
+                              int use_p2p, int rows_cap, int n_zero_rows_global, int k, int n_k_needed,
                               int k_buffer, double min_eig_val, double tol, int max_outer, int block_size,
                               double spectrum_upper_bound, double* eig_vals, double* eig_vecs, int ldv,
                               int* result_i_host, double* result_d_host, void* workspace,
@@ -1155,15 +1276,60 @@ int focusr_eigs_smallest_dist(const int* row_ptr, const int* cols_local, const d
   be.eig_vecs = eig_vecs;
   be.ldv = ldv;
   be.dist = &d;
+  std::vector<const double*> pb_host;
+  std::vector<unsigned long long*> pf_host;
+  if (use_p2p && world > 1) {
+    FB_REQUIRE(g_shared.base != nullptr && g_shared.world == world && (int)g_shared.peer.size() == world,
+               "eigs_dist: P2P mode needs focusr_dist_shared_alloc/open first");
+    FB_REQUIRE(rows_cap >= n_local && focusr_dist_shared_bytes(rows_cap, B, world) <= g_shared.bytes,
+               "eigs_dist: shared region too small for rows_cap=%d block=%d", rows_cap, B);
+    const size_t stride = align_up(sizeof(double) * (size_t)rows_cap * B) / sizeof(double);
+    d.p2p = true;
+    d.block_stride = stride;
+    d.blocks = reinterpret_cast<double*>((char*)g_shared.base + shared_flag_bytes(world));
+    d.flags = reinterpret_cast<unsigned long long*>(g_shared.base);
+    d.ghost_peer = ghost_peer;
+    d.ghost_row = ghost_row;
+    d.epoch = g_peer_epoch;
+    pb_host.resize((size_t)3 * world);
+    pf_host.resize(world);
+    for (int p = 0; p < world; ++p) {
+      pf_host[p] = reinterpret_cast<unsigned long long*>(g_shared.peer[p]);
+      for (int kb = 0; kb < 3; ++kb)
+        pb_host[(size_t)kb * world + p] =
+            reinterpret_cast<const double*>((char*)g_shared.peer[p] + shared_flag_bytes(world)) + (size_t)kb * stride;
+    }
+    FB_CUDA(cudaMemcpyAsync(const_cast<const double**>(d.peer_blocks), pb_host.data(), sizeof(double*) * 3 * world,
+                            cudaMemcpyHostToDevice, stream));
+    FB_CUDA(cudaMemcpyAsync(const_cast<unsigned long long**>(d.peer_flags), pf_host.data(), sizeof(void*) * world,
+                            cudaMemcpyHostToDevice, stream));
+    FB_CUDA(cudaMemsetAsync(d.dev_err, 0, sizeof(int) * 2, stream));
+    be.X = d.blocks;
+    be.Y = d.blocks + stride;
+    be.Xn = d.blocks + 2 * stride;
+  }
   FB_CUDA(cudaMemcpyAsync(const_cast<int*>(be.g.mesh_off), off_host, sizeof(off_host), cudaMemcpyHostToDevice, stream));
   FB_CUDA(cudaMemcpyAsync(d.fake_off, fake, sizeof(fake), cudaMemcpyHostToDevice, stream));
   // ghost rows of all three blocks start defined (the first exchange overwrites them)
-  FB_CUDA(cudaMemsetAsync(be.X, 0, sizeof(double) * (size_t)(n_local + n_ghost) * B, stream));
-  FB_CUDA(cudaMemsetAsync(be.Y, 0, sizeof(double) * (size_t)(n_local + n_ghost) * B, stream));
-  FB_CUDA(cudaMemsetAsync(be.Xn, 0, sizeof(double) * (size_t)(n_local + n_ghost) * B, stream));
+  const size_t ext_rows = d.p2p ? (size_t)n_local : (size_t)(n_local + n_ghost);
+  FB_CUDA(cudaMemsetAsync(be.X, 0, sizeof(double) * ext_rows * B, stream));
+  FB_CUDA(cudaMemsetAsync(be.Y, 0, sizeof(double) * ext_rows * B, stream));
+  FB_CUDA(cudaMemsetAsync(be.Xn, 0, sizeof(double) * ext_rows * B, stream));
   FB_CUDA(cudaStreamSynchronize(stream));  // off_host / fake live on this stack frame
   MeshResult r;
   const int rc = chfsi_solve(be, p, &r);
+  if (d.p2p) {
+    // peers may still be reading this rank's blocks in their last step: leave together
+    be.halo_exchange(be.X);
+    g_peer_epoch = d.epoch;
+    int herr[2] = {0, 0};
+    cudaMemcpyAsync(herr, d.dev_err, sizeof(herr), cudaMemcpyDeviceToHost, stream);
+    cudaStreamSynchronize(stream);
+    if (herr[0] != 0) {
+      set_error("eigs_dist: a peer did not reach the inter-GPU barrier (time-out)");
+      return FB_ERR_CUDA;
+    }
+  }
   if (be.err != FB_OK) return be.err;
   FB_CUDA(cudaStreamSynchronize(stream));
   g_filter_profile.collect();

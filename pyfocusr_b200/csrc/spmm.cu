@@ -294,6 +294,126 @@ int launch_spmm(int mode, int b, const SpmmGraph& g, const double* y, const doub
 #undef FB_CASE
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Row-partitioned multi-GPU variant with the halo FUSED into the SpMM: a column that belongs to
+// another rank is read straight from that rank's memory over NVLink (peer pointer obtained through
+// CUDA IPC), so there is no pack / send / receive and no ghost copy -- the transfer of the ~1% of
+// boundary rows overlaps the gathers of the local 99%.  peer_y[p] is rank p's copy of the block being
+// read; ghost g = col - n_loc lives at row ghost_row[g] of rank ghost_peer[g].  Ordering between
+// ranks is a flag barrier (k_peer_barrier in eigs.cu) before the launch.
+// ---------------------------------------------------------------------------------------------
+template <int B, int TPR, int MODE>
+__global__ void __launch_bounds__(SPMM_THREADS, (B / (2 * TPR) == 1) ? 8 : ((B / (2 * TPR) == 2) ? 6 : 3))
+k_spmm_p2p(const int* __restrict__ row_ptr, const int* __restrict__ cols, const double* __restrict__ weights,
+           const double* __restrict__ degree, const double* __restrict__ degree_inv, int n_loc,
+           const double* __restrict__ y, const double* const* __restrict__ peer_y,
+           const int* __restrict__ ghost_peer, const int* __restrict__ ghost_row,
+           const double* __restrict__ x_prev, double* __restrict__ out, const double* __restrict__ alpha,
+           const double* __restrict__ gamma, const double* __restrict__ center, int step, int n_steps) {
+  constexpr int VPT = B / (2 * TPR);
+  const int r0 = blockIdx.x * SPMM_ROWS_PER_BLOCK;
+  const int r1 = min(n_loc, r0 + SPMM_ROWS_PER_BLOCK);
+  double al = 1.0, ga = 0.0, cc = 0.0;
+  if (MODE == 0) {
+    al = alpha[step];
+    ga = gamma[step];
+    cc = center[0];
+  }
+  const int g = threadIdx.x / TPR, t = threadIdx.x % TPR;
+  for (int row = r0 + g; row < r1; row += SPMM_THREADS / TPR) {
+    double2 acc[VPT];
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) acc[v] = make_double2(0.0, 0.0);
+    const int p0 = row_ptr[row], p1 = row_ptr[row + 1];
+#pragma unroll 4
+    for (int p = p0; p < p1; ++p) {
+      const int c = cols[p];
+      const double w = weights[p];
+      const double2* src;
+      if (c < n_loc) {
+        src = reinterpret_cast<const double2*>(y + (size_t)c * B);
+      } else {
+        const int gi = c - n_loc;
+        src = reinterpret_cast<const double2*>(peer_y[ghost_peer[gi]] + (size_t)ghost_row[gi] * B);
+      }
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) {
+        const double2 a = __ldg(src + t + v * TPR);
+        acc[v].x = fma(w, a.x, acc[v].x);
+        acc[v].y = fma(w, a.y, acc[v].y);
+      }
+    }
+    const double d = degree[row];
+    const double di = degree_inv[row];
+    const double2* yr = reinterpret_cast<const double2*>(y + (size_t)row * B);
+    const double2* xr = reinterpret_cast<const double2*>(x_prev + (size_t)row * B);
+    double2* o = reinterpret_cast<double2*>(out + (size_t)row * B);
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      const double2 yv = __ldg(yr + t + v * TPR);
+      double2 r;
+      if (MODE == 1) {
+        r.x = d * yv.x - acc[v].x;
+        r.y = d * yv.y - acc[v].y;
+      } else {
+        const double lx = di * (d * yv.x - acc[v].x);
+        const double ly = di * (d * yv.y - acc[v].y);
+        r.x = al * (lx - cc * yv.x);
+        r.y = al * (ly - cc * yv.y);
+        if (ga != 0.0) {
+          const double2 xv = __ldg(xr + t + v * TPR);
+          r.x -= ga * xv.x;
+          r.y -= ga * xv.y;
+        }
+      }
+      o[t + v * TPR] = r;
+    }
+  }
+}
+
+template <int B, int TPR>
+static int launch_spmm_p2p_b(int mode, const SpmmGraph& g, int n_loc, const double* y, const double* const* peer_y,
+                             const int* ghost_peer, const int* ghost_row, const double* x_prev, double* out,
+                             const double* alpha, const double* gamma, const double* center, int step, int n_steps,
+                             cudaStream_t stream) {
+  dim3 grid(div_up(n_loc, SPMM_ROWS_PER_BLOCK));
+  if (mode == 0)
+    k_spmm_p2p<B, TPR, 0><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv, n_loc, y,
+                                                             peer_y, ghost_peer, ghost_row, x_prev, out, alpha, gamma, center, step, n_steps);
+  else
+    k_spmm_p2p<B, TPR, 1><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv, n_loc, y,
+                                                             peer_y, ghost_peer, ghost_row, x_prev, out, alpha, gamma, center, step, n_steps);
+  FB_COUNT_LAUNCH(1);
+  return FB_OK;
+}
+
+int launch_spmm_p2p(int mode, int b, const SpmmGraph& g, int n_loc, const double* y, const double* const* peer_y,
+                    const int* ghost_peer, const int* ghost_row, const double* x_prev, double* out, const double* alpha,
+                    const double* gamma, const double* center, int step, int n_steps, cudaStream_t stream) {
+#define FB_CASE(BB, TT) \
+  case BB:              \
+    return launch_spmm_p2p_b<BB, TT>(mode, g, n_loc, y, peer_y, ghost_peer, ghost_row, x_prev, out, alpha, gamma, center, step, n_steps, stream);
+  switch (b) {
+    FB_CASE(8, 4)
+    FB_CASE(16, 8)
+    FB_CASE(24, 4)
+    FB_CASE(32, 8)
+    FB_CASE(40, 4)
+    FB_CASE(48, 8)
+    FB_CASE(56, 4)
+    FB_CASE(64, 16)
+    FB_CASE(72, 4)
+    FB_CASE(80, 8)
+    FB_CASE(88, 4)
+    FB_CASE(96, 16)
+    default:
+      set_error("spmm (p2p): unsupported block size %d", b);
+      return FB_ERR_UNSUPPORTED;
+  }
+#undef FB_CASE
+}
+
 // ---------------------------------------------------------------------------------------------
 // Graph.mean_filter_graph (graph.py:349-354).  scipy stores each row of
 // average_mat = diag(1/(1+d)) @ (A + I) in DESCENDING column order and `average_mat @ x`

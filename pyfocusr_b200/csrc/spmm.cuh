@@ -26,4 +26,9 @@ int launch_spmm(int mode, int b, const SpmmGraph& g, const double* y, const doub
                 const double* alpha, const double* gamma, const double* center, int step, int n_steps,
                 cudaStream_t stream);
 
+// row-partitioned multi-GPU: remote columns are gathered from the owning rank's memory (NVLink P2P)
+int launch_spmm_p2p(int mode, int b, const SpmmGraph& g, int n_loc, const double* y, const double* const* peer_y,
+                    const int* ghost_peer, const int* ghost_row, const double* x_prev, double* out, const double* alpha,
+                    const double* gamma, const double* center, int step, int n_steps, cudaStream_t stream);
+
 }  // namespace fb

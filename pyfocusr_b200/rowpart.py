@@ -107,13 +107,41 @@ class RowPartitionedSolver:
         self.n_send = int(send_idx.size)
         self.send_counts = np.ascontiguousarray(send_counts, dtype=np.int32)
         self.recv_counts = np.ascontiguousarray(part["recv_counts"], dtype=np.int32)
+        # P2P mode: where every ghost row lives (owner rank, row inside the owner's block)
+        ghosts = part["ghosts"]
+        owner = np.searchsorted(self.bounds[1:], ghosts, side="right").astype(np.int32)
+        g_row = (ghosts - self.bounds[owner]).astype(np.int32)
+        self.ghost_peer = torch.from_numpy(owner if owner.size else np.zeros(1, np.int32)).to(dev)
+        self.ghost_row = torch.from_numpy(g_row if g_row.size else np.zeros(1, np.int32)).to(dev)
+        self.rows_cap = int(np.max(np.diff(self.bounds)))
+        self._shared_for_block = None
         del full
         self._lib = lib
 
-    def eigs_smallest(self, k, n_k_needed, k_buffer=1, min_eig_val=1e-10, tol=1e-10, max_outer=60, block_size=0):
+    def _ensure_shared(self, block):
+        """IPC-shared region holding this rank's three vector blocks + barrier flags (P2P mode)."""
+        if self._shared_for_block == block or self.world == 1:
+            return
+        lib = self._lib
+        nbytes = int(lib.focusr_dist_shared_bytes(self.rows_cap, block, self.world))
+        handle = (C.c_char * 64)()
+        _lib.call("focusr_dist_shared_alloc", nbytes, C.cast(handle, C.c_void_p))
+        handles = b"".join(fdist.gather_objects(bytes(handle.raw)))
+        buf = (C.c_char * (64 * self.world)).from_buffer_copy(handles)
+        _lib.call("focusr_dist_shared_open", C.cast(buf, C.c_void_p), self.rank, self.world)
+        fdist.barrier()  # every rank has zeroed its flags and mapped its peers before anyone signals
+        self._shared_for_block = block
+
+    def eigs_smallest(self, k, n_k_needed, k_buffer=1, min_eig_val=1e-10, tol=1e-10, max_outer=60, block_size=0,
+                      p2p=True):
+        """``p2p=True`` (default when world > 1): halo fused into the SpMM over NVLink peer memory;
+        ``p2p=False``: packed boundary rows exchanged with grouped ncclSend/ncclRecv."""
         torch = _lib.require_cuda()
         lib = self._lib
         b = int(block_size) if block_size else int(lib.focusr_eigs_block_size(k, n_k_needed, k_buffer, 0, self.n_zero_rows))
+        use_p2p = bool(p2p) and self.world > 1
+        if use_p2p:
+            self._ensure_shared(b)
         ldv = b
         vals = torch.zeros(ldv, dtype=torch.float64, device=self.device)
         vecs = torch.zeros((self.n_local, ldv), dtype=torch.float64, device=self.device)
@@ -123,15 +151,18 @@ class RowPartitionedSolver:
         _lib.call("focusr_eigs_smallest_dist", _lib.ptr(self.row_ptr), _lib.ptr(self.cols_local), _lib.ptr(self.weights),
                   _lib.ptr(self.degree), _lib.ptr(self.degree_inv), _lib.ptr(self.points), self.n_local, self.n_ghost,
                   self.row_begin, self.nnz_local, _lib.ptr(self.send_idx), self.n_send, _lib.ptr(self.send_counts),
-                  _lib.ptr(self.recv_counts), self.n_zero_rows, int(k), int(n_k_needed), int(k_buffer),
+                  _lib.ptr(self.recv_counts), _lib.ptr(self.ghost_peer), _lib.ptr(self.ghost_row), int(use_p2p),
+                  self.rows_cap, self.n_zero_rows, int(k), int(n_k_needed), int(k_buffer),
                   float(min_eig_val), float(tol), int(max_outer), b, 0.0, _lib.ptr(vals), _lib.ptr(vecs), ldv,
                   _lib.ptr(res_i), _lib.ptr(res_d), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
         m = int(res_i[1])
         info = dict(status=int(res_i[0]), n_found=m, k_final=int(res_i[2]), outer_iterations=int(res_i[3]),
                     filter_degree=int(res_i[4]), block_size=b, world=int(res_i[7]), max_residual=float(res_d[0]),
-                    n_local=self.n_local, n_ghost=self.n_ghost, n_send=self.n_send)
+                    n_local=self.n_local, n_ghost=self.n_ghost, n_send=self.n_send, p2p=use_p2p)
         return vals[:m], vecs[:, :m], info
 
     def close(self):
         if self.world > 1:
+            fdist.barrier()
+            _lib.call("focusr_dist_shared_free")
             _lib.call("focusr_dist_finalize")

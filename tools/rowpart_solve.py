@@ -15,16 +15,17 @@ from pyfocusr_b200.rowpart import RowPartitionedSolver
 
 nu = int(sys.argv[1]) if len(sys.argv) > 1 else 316
 k = int(sys.argv[2]) if len(sys.argv) > 2 else 11
+p2p = (sys.argv[3] != "nccl") if len(sys.argv) > 3 else True   # halo: fused P2P loads (default) or ncclSend/Recv
 rank, local, world = fdist.world()
 torch.cuda.set_device(local)
 fdist.init("nccl")
 m = icosphere(nu)
 solver = RowPartitionedSolver(m.points, m.tris)
-solver.eigs_smallest(k=k, n_k_needed=k - 1)          # warm-up (NCCL channels, kernels)
+solver.eigs_smallest(k=k, n_k_needed=k - 1, p2p=p2p)          # warm-up (NCCL channels, kernels)
 fdist.barrier()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-vals, vecs, info = solver.eigs_smallest(k=k, n_k_needed=k - 1)
+vals, vecs, info = solver.eigs_smallest(k=k, n_k_needed=k - 1, p2p=p2p)
 e1.record()
 fdist.barrier()
 ms = fdist.all_reduce_max(e0.elapsed_time(e1))
@@ -56,7 +57,7 @@ if rank == 0:
     res = float(torch.linalg.vector_norm(r, dim=0).max())
     norms = torch.linalg.vector_norm(allv, dim=0).cpu().numpy()
     print(json.dumps({"config": "configs[3]: icosphere nu=%d (%d vertices), k=%d smallest, row-partitioned over %d GPU(s)" % (nu, g.n_points, k, world),
-                      "n_gpus": world, "seconds": ms / 1e3, "status": info["status"], "n_found": info["n_found"],
+                      "n_gpus": world, "halo": ("p2p-fused" if info["p2p"] else ("nccl send/recv" if world > 1 else "none")), "seconds": ms / 1e3, "status": info["status"], "n_found": info["n_found"],
                       "outer_iterations": info["outer_iterations"], "filter_degree": info["filter_degree"], "block": info["block_size"],
                       "n_local": info["n_local"], "n_ghost": info["n_ghost"], "max_residual_global": res,
                       "max_rel_err_vs_scipy": rel, "within_1e-6": ok_ref, "unit_norm_err": float(np.max(np.abs(norms - 1.0))),
