@@ -247,12 +247,18 @@ int chfsi_solve(BE& be, const SolveParams& p, MeshResult* out) {
       be.rr_sym();
     } else {
       be.get_GH(gh.data(), gh.data() + (size_t)M * B * B);
+      // the meshes' small eigenproblems are independent: one host thread each (OpenMP when compiled in)
+      std::vector<int> rr_rc(M, 0);
+#if defined(_OPENMP)
+#pragma omp parallel for schedule(dynamic)
+#endif
       for (int m = 0; m < M; ++m) {
         const double cut = a_prev[m] < 0.0 ? 0.5 * p.beta : 2.0 * a_prev[m];
-        const int r = rr_nonsym_host(gh.data() + (size_t)m * B * B,
-                                     gh.data() + (size_t)(M + m) * B * B, B, cut,
-                                     wbuf.data() + (size_t)m * B * B, thbuf.data() + (size_t)m * B,
-                                     &n_low[m]);
+        rr_rc[m] = rr_nonsym_host(gh.data() + (size_t)m * B * B, gh.data() + (size_t)(M + m) * B * B, B, cut,
+                                  wbuf.data() + (size_t)m * B * B, thbuf.data() + (size_t)m * B, &n_low[m]);
+      }
+      for (int m = 0; m < M; ++m) {
+        const int r = rr_rc[m];
         if (r < 0 && !done[m]) {
           out[m].status = SOLVE_BREAKDOWN;
           done[m] = 1;

@@ -234,6 +234,34 @@ def test_eigs_icosphere_multiplets(torch, synth):
     assert np.max(np.linalg.norm(lap @ vecs - vecs * vals[None], axis=0)) <= 1e-9
 
 
+def test_eigs_damaged_meshes_nonsymmetric_batch(torch, synth):
+    """Holes and flipped triangles (one-way adjacency entries -> complex eigenvalue pairs of L) in a batch that
+    also holds a clean mesh: every mesh must still return the reference's pairs."""
+    import pyfocusr_b200.mesh as fmesh
+    from pyfocusr_b200._device import DeviceGraph
+
+    rng = np.random.RandomState(1)
+    ms = [synth["ell20a"]]
+    for nu, holes, flips in ((16, 12, 0), (20, 4, 25), (24, 30, 30)):
+        base = fmesh.perturbed_ellipsoid(nu, 5)
+        t = base.tris.copy()
+        keep = np.ones(len(t), bool)
+        keep[rng.choice(len(t), holes, replace=False)] = False
+        t = t[keep]
+        fl = rng.choice(len(t), flips, replace=False)
+        t[fl] = t[fl][:, [0, 2, 1]]
+        ms.append(fmesh.PolyData(base.points, t))
+    g = DeviceGraph([m.points for m in ms], [m.tris for m in ms])
+    vals, vecs, info = g.eigs_smallest(k=7, n_k_needed=6)
+    assert info["status"].tolist() == [0] * 4
+    assert info["symmetric"].tolist() == [1, 0, 0, 0]
+    vals, vecs = vals.cpu().numpy(), vecs.cpu().numpy()
+    for k, m in enumerate(ms):
+        nf = int(info["n_found"][k])
+        o0, o1 = g.mesh_off_host[k], g.mesh_off_host[k + 1]
+        check_eigs(vals[k, :nf], vecs[o0:o1, :nf], m, 6)
+
+
 def test_recursive_eig_function(torch, shipped_meshes, golden):
     from oracle import port
     from pyfocusr_b200 import recursive_eig

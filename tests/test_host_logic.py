@@ -261,3 +261,33 @@ def test_non_triangle_cells_are_rejected():
 
     with pytest.raises(ValueError, match="triangle"):
         fmesh.mesh_arrays(Quad())
+
+
+def test_driver_nonsymmetric_on_damaged_meshes(hostsim):
+    """Open / badly oriented meshes: removed triangles and flipped triangles give one-way adjacency entries, hence
+    complex eigenvalue pairs that the Chebyshev filter amplifies; the Euclidean Rayleigh-Ritz path must still
+    return the reference's eigenpairs."""
+    import ctypes
+
+    from pyfocusr_b200 import _lib
+
+    rng = np.random.RandomState(0)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    lib.focusr_eigs_block_size.argtypes = [ctypes.c_int] * 5
+    for nu, holes, flips in ((12, 5, 0), (16, 20, 10), (20, 3, 30)):
+        base = fmesh.perturbed_ellipsoid(nu, 3)
+        t = base.tris.copy()
+        keep = np.ones(len(t), bool)
+        keep[rng.choice(len(t), holes, replace=False)] = False
+        t = t[keep]
+        fl = rng.choice(len(t), flips, replace=False)
+        t[fl] = t[fl][:, [0, 2, 1]]
+        m = fmesh.PolyData(base.points, t)
+        a = port.adjacency(m.points, m.tris)
+        pat = (a != 0).astype(np.int8)
+        oneway = int((pat - pat.multiply(pat.T)).nnz)
+        assert oneway > 0
+        b = lib.focusr_eigs_block_size(7, 6, 1, oneway, 0)
+        rc, vals, vecs, ri, offs, sym = _solve(hostsim, [m], 7, 6, b, ldv=64)
+        assert rc == 0 and not sym and ri[0, 1] == 6
+        _check(m, vals[0, :6], vecs[:, :6], 6)
