@@ -83,8 +83,13 @@ int focusr_gather_rows(const double* in, const long long* idx, const int* idx_ba
  * with unit 2-norm and the largest-magnitude entry positive.  SYNCHRONISES the stream (once per
  * outer iteration).  `mesh_info_host` is focusr_laplacian_build's mesh_info copied to the host.
  * result_i_host [n_meshes][8]: {status, n_found, k_final, outer_iterations, total_filter_degree,
- * block_size, symmetric, restarts};  result_d_host [n_meshes][2]: {max_residual, 0}.
+ * block_size, symmetric, restarts};  result_d_host [n_meshes][2]: {max_residual, upper edge of the
+ * filter interval}.
  * status: 0 ok, 1 not converged, 2 block too small, 3 numerical breakdown, 4 ldv too small.
+ * `spectrum_upper_bound`: > 0 = filter up to this caller-guaranteed bound; 0 = start from the
+ * Gershgorin bound 2 and, for symmetric adjacencies, tighten it per mesh with a 10-step probe of the
+ * top of the spectrum (triangle meshes sit near 1.5; the degree scales with sqrt of the bound; an
+ * underestimate is detected and reverts to 2); < 0 = Gershgorin bound as is.
  * ------------------------------------------------------------------------------------------- */
 size_t focusr_eigs_workspace_bytes(int n_points, int n_meshes, int max_mesh_points, int block_size);
 int focusr_eigs_block_size(int k, int n_k_needed, int k_buffer, int max_one_way, int max_zero_rows);

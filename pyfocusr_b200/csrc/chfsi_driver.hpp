@@ -47,8 +47,11 @@ struct SolveParams {
   int max_outer;     // outer (Rayleigh-Ritz) iterations
   double amp_target; // filter amplification of the slowest wanted pair per outer iteration
   int max_degree;    // cap of the Chebyshev degree per outer iteration
-  double beta;       // upper bound of the spectrum
+  double beta;       // guaranteed upper bound of the spectrum (Gershgorin: 2)
   int ldv;           // capacity (columns) of the output arrays
+  int probe_degree;  // > 0: tighten beta per mesh with a top-of-spectrum probe of this many filter steps
+                     // (symmetric batches only); 0: filter up to `beta` as given
+  double land;       // the sized pass aims at land * tol
 };
 
 struct MeshResult {
@@ -59,6 +62,7 @@ struct MeshResult {
   int total_degree;
   int block;
   double max_residual;
+  double beta;     // upper edge of the filter interval that was used
 };
 
 inline void cheb_table(double a, double a_low, double beta, int m, double* alpha, double* gamma,
@@ -212,6 +216,38 @@ inline int retry_contract(const double* theta, int n_avail, int zr, const SolveP
   }
 }
 
+// Top-of-spectrum probe (symmetric adjacency).  The Gershgorin bound 2 is only attained by bipartite
+// graphs; triangle meshes sit near 1.5, and the filter degree scales with sqrt(beta).  The start block
+// is taken through `probe_degree` steps of the polynomial that damps [0, 1] (lambda_max > 1 always:
+// trace(L)/N ~ 1), then Rayleigh-Ritz gives the largest Ritz value theta_max <= lambda_max and the
+// residual r of its vector; some eigenvalue lies within r of theta_max, and with the dense top end of a
+// mesh spectrum theta_max + r has covered lambda_max on every mesh tried (the standard safeguarded bound
+// of Chebyshev-filtered iterations).  beta_m = min(beta, theta_max + 1.5 r + 0.01).  An underestimate is
+// not silent: what the filter then amplifies shows up as Ritz values near beta_m and the driver falls
+// back to `beta` for that mesh (see `leak` below).
+template <class BE>
+void probe_upper_bound(BE& be, const SolveParams& p, double* beta_m) {
+  const int M = be.n_meshes();
+  const int B = be.block();
+  const int deg = p.probe_degree;
+  std::vector<double> alpha((size_t)M * deg), gamma((size_t)M * deg), center(M);
+  be.init_block();
+  for (int m = 0; m < M; ++m)
+    cheb_table(0.0, p.beta, 1.0, deg, &alpha[(size_t)m * deg], &gamma[(size_t)m * deg], &center[m]);
+  be.filter(deg, alpha.data(), gamma.data(), center.data());
+  be.apply_DmA();
+  be.gram();
+  be.rr_sym();
+  be.rotate_and_residual();
+  std::vector<double> theta((size_t)M * B), res((size_t)M * B);
+  be.get_theta_res(theta.data(), res.data());
+  for (int m = 0; m < M; ++m) {
+    const double th = theta[(size_t)m * B + B - 1], r = res[(size_t)m * B + B - 1];
+    const double est = th + 1.5 * r + 0.01;
+    beta_m[m] = (th == th && r == r && th > 1.0 && est < p.beta) ? est : p.beta;
+  }
+}
+
 template <class BE>
 int chfsi_solve(BE& be, const SolveParams& p, MeshResult* out) {
   const int M = be.n_meshes();
@@ -236,7 +272,9 @@ int chfsi_solve(BE& be, const SolveParams& p, MeshResult* out) {
     out[m].block = B;
     out[m].max_residual = -1.0;
   }
-  std::vector<double> alpha, gamma, center(M);
+  std::vector<double> alpha, gamma, center(M), beta_m(M, p.beta);
+  if (sym && p.probe_degree > 0) probe_upper_bound(be, p, beta_m.data());
+  for (int m = 0; m < M; ++m) out[m].beta = beta_m[m];
   be.init_block();
   int n_done = 0;
   int rc = SOLVE_OK;
@@ -323,8 +361,14 @@ int chfsi_solve(BE& be, const SolveParams& p, MeshResult* out) {
       const double* th = &theta[(size_t)m * B];
       const int top = (sym ? B : n_low[m]) - 1;
       double a = th[top];
-      if (!(a < p.beta)) a = 0.5 * p.beta;
-      if (!(a > 0.0)) a = 1e-3 * p.beta;
+      if (outer >= 1 && beta_m[m] < p.beta && a > 0.8 * beta_m[m]) {
+        // leak: the filter amplified something above the probed bound; back to the guaranteed one
+        beta_m[m] = p.beta;
+        out[m].beta = p.beta;
+      }
+      const double beta = beta_m[m];
+      if (!(a < beta)) a = 0.5 * beta;
+      if (!(a > 0.0)) a = 1e-3 * beta;
       const int kp = last_kp[m];
       const double thk = th[std::max(0, std::min(kp, top) - 1)];
       if (outer >= 3 && (a - thk) <= 1e-3 * a) {
@@ -345,17 +389,17 @@ int chfsi_solve(BE& be, const SolveParams& p, MeshResult* out) {
       double amp = p.amp_target;
       const double worst = out[m].max_residual;
       if (outer >= 1 && worst > 0.0 && worst < 1e-2) {
-        const double need = worst / (0.05 * p.tol);
+        const double need = worst / (p.land * p.tol);
         const double cap = sym ? 1e7 : 1e4;
         if (need <= cap) amp = std::max(need, 30.0);
       }
-      deg = std::max(deg, cheb_degree(a, thk, p.beta, amp, p.max_degree));
+      deg = std::max(deg, cheb_degree(a, thk, beta, amp, p.max_degree));
     }
     if (n_done >= M) break;
     alpha.resize((size_t)M * deg);
     gamma.resize((size_t)M * deg);
     for (int m = 0; m < M; ++m)
-      cheb_table(last_a[m], last_alow[m], p.beta, deg, &alpha[(size_t)m * deg],
+      cheb_table(last_a[m], last_alow[m], beta_m[m], deg, &alpha[(size_t)m * deg],
                  &gamma[(size_t)m * deg], &center[m]);
     be.filter(deg, alpha.data(), gamma.data(), center.data());
     for (int m = 0; m < M; ++m)

@@ -1026,6 +1026,9 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
   // Gershgorin bound of the random-walk Laplacian: |L_ii| + sum_j |L_ij| = 2 d / (d + 1e-8) < 2
   p.beta = spectrum_upper_bound > 0.0 ? spectrum_upper_bound : 2.0;
   p.ldv = ldv;
+  // 0: probe the top of the spectrum and filter only up to it; > 0: trust the caller; < 0: Gershgorin as is
+  p.probe_degree = spectrum_upper_bound == 0.0 ? 10 : 0;
+  p.land = 0.2;
 
   // contiguous runs of meshes with the same symmetry class are solved as one batch
   int rc_all = FB_OK;
@@ -1081,7 +1084,7 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
       ri[6] = sym ? 1 : 0;
       ri[7] = 0;
       result_d_host[2 * m] = results[m].max_residual;
-      result_d_host[2 * m + 1] = 0.0;
+      result_d_host[2 * m + 1] = results[m].beta;
     }
     rc_all = std::max(rc_all, rc);
     m0 = m1;
@@ -1239,6 +1242,9 @@ int focusr_eigs_smallest_dist(const int* row_ptr, const int* cols_local, const d
   p.max_degree = 16384;
   p.beta = spectrum_upper_bound > 0.0 ? spectrum_upper_bound : 2.0;
   p.ldv = ldv;
+  // 0: probe the top of the spectrum and filter only up to it; > 0: trust the caller; < 0: Gershgorin as is
+  p.probe_degree = spectrum_upper_bound == 0.0 ? 10 : 0;
+  p.land = 0.2;
 
   DistCtx d;
   d.comm = g_dist_comm;
@@ -1342,7 +1348,7 @@ int focusr_eigs_smallest_dist(const int* row_ptr, const int* cols_local, const d
   result_i_host[6] = 1;
   result_i_host[7] = world;
   result_d_host[0] = r.max_residual;
-  result_d_host[1] = 0.0;
+  result_d_host[1] = r.beta;
   if (rc != FB_OK) set_error("eigs_dist: solver status %d", rc);
   return rc;
 }

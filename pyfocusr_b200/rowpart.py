@@ -157,7 +157,7 @@ class RowPartitionedSolver:
                   _lib.ptr(res_i), _lib.ptr(res_d), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
         m = int(res_i[1])
         info = dict(status=int(res_i[0]), n_found=m, k_final=int(res_i[2]), outer_iterations=int(res_i[3]),
-                    filter_degree=int(res_i[4]), block_size=b, world=int(res_i[7]), max_residual=float(res_d[0]),
+                    filter_degree=int(res_i[4]), block_size=b, world=int(res_i[7]), max_residual=float(res_d[0]), spectrum_bound=float(res_d[1]),
                     n_local=self.n_local, n_ghost=self.n_ghost, n_send=self.n_send, p2p=use_p2p)
         return vals[:m], vecs[:, :m], info
 

@@ -194,7 +194,7 @@ struct HostBackend {
 
 extern "C" {
 
-// result_i: per mesh [status, n_out, k_final, outer_iters, total_degree, block]; result_d: [max_residual]
+// result_i: per mesh [status, n_out, k_final, outer_iters, total_degree, block]; result_d: per mesh [max_residual, filter upper edge]
 int hostsim_eigs(const int* rp, const int* cols, const double* w, const double* deg, const double* dinv,
                  const double* pts, int n_rows, const int* off, int n_meshes, int symmetric,
                  const int* zero_rows, int block, int k0, int n_needed, int k_buffer, double min_eig,
@@ -206,14 +206,16 @@ int hostsim_eigs(const int* rp, const int* cols, const double* w, const double* 
   be.out_vals = eig_vals; be.out_vecs = eig_vecs; be.ldv = ldv;
   fb::SolveParams p;
   p.k0 = k0; p.n_needed = n_needed; p.k_buffer = k_buffer; p.min_eig = min_eig; p.tol = tol;
-  p.max_outer = max_outer; p.amp_target = amp_target; p.max_degree = max_degree; p.beta = beta; p.ldv = ldv;
+  p.max_outer = max_outer; p.amp_target = amp_target; p.max_degree = max_degree; p.beta = beta > 0.0 ? beta : 2.0; p.ldv = ldv;
+  p.probe_degree = beta == 0.0 ? 10 : 0; p.land = 0.2;
   std::vector<fb::MeshResult> r(n_meshes);
   const int rc = fb::chfsi_solve(be, p, r.data());
   for (int m = 0; m < n_meshes; ++m) {
     int* ri = result_i + 6 * m;
     ri[0] = r[m].status; ri[1] = r[m].n_out; ri[2] = r[m].k_final; ri[3] = r[m].outer_iters;
     ri[4] = r[m].total_degree; ri[5] = r[m].block;
-    result_d[m] = r[m].max_residual;
+    result_d[2 * m] = r[m].max_residual;
+    result_d[2 * m + 1] = r[m].beta;
   }
   return rc;
 }

@@ -54,7 +54,7 @@ def test_edge_weight_matches_numpy(hostsim):
 
 
 # ------------------------------------------------------------------------------------------------ solver driver
-def _solve(hostsim, meshes, k0, n_needed, block, ldv=32, tol=1e-10):
+def _solve(hostsim, meshes, k0, n_needed, block, ldv=32, tol=1e-10, beta=0.0, full=False):
     rps, cols, ws, degs, pts, offs, zrs = [], [], [], [], [], [0], []
     nnz = 0
     sym = True
@@ -75,11 +75,13 @@ def _solve(hostsim, meshes, k0, n_needed, block, ldv=32, tol=1e-10):
     deg = np.concatenate(degs)
     M, N = len(meshes), offs[-1]
     vals, vecs = np.zeros((M, ldv)), np.zeros((N, ldv))
-    ri, rd = np.zeros(6 * M, np.int32), np.zeros(M)
+    ri, rd = np.zeros(6 * M, np.int32), np.zeros(2 * M)
     rc = hostsim.hostsim_eigs(rp, np.concatenate(cols).astype(np.int32), np.concatenate(ws), deg, port.degree_inv(deg),
                               np.ascontiguousarray(np.concatenate(pts)), N, np.array(offs, np.int32), M, int(sym),
-                              np.array(zrs, np.int32), block, k0, n_needed, 1, 1e-10, tol, 60, 1e3, 4096, 2.0, ldv,
+                              np.array(zrs, np.int32), block, k0, n_needed, 1, 1e-10, tol, 60, 1e3, 4096, beta, ldv,
                               vals, vecs, ri, rd)
+    if full:
+        return rc, vals, vecs, ri.reshape(M, 6), offs, sym, rd.reshape(M, 2)
     return rc, vals, vecs, ri.reshape(M, 6), offs, sym
 
 
