@@ -225,6 +225,41 @@ int focusr_weighted_positions(const long long* idx3, const double* dist3,
                               const double* target_points, const int* point_base, int n_queries,
                               double* out, focusr_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * K8  Coherent Point Drift (focusr.py:297-334: cycpd.affine_registration, then
+ * cycpd.deformable_registration(num_eig, alpha, beta) on subsets X (source) / Y (target) of the
+ * spectral coordinates, then reg.transform_point_cloud on ALL target coordinates).  cycpd is an
+ * unpinned, absent dependency: the algorithm is Myronenko & Song, TPAMI 2010, with the conventions
+ * written down in oracle/cpd_port.py (the only thing these entry points are checked against).
+ * x [n_x][dim], y [n_y][dim] row-major fp64 on the device, 1 <= dim <= 16.  The EM loop runs on the
+ * device; the call SYNCHRONISES the stream once per 8 iterations to read the convergence state.
+ *   affine:      b_out [dim][dim], t_out [dim] (TY = Y b + t), ty_out [n_y][dim] (all nullable);
+ *                result_host[4] = {iterations, sigma2, objective q, |q - q_prev|}; the loop ends when
+ *                |q - q_prev| <= tolerance or at max_iterations.
+ *   deformable:  low-rank kernel with the num_eig (<= 152) leading eigenpairs of
+ *                G = exp(-|y_i - y_j|^2 / (2 beta^2)); w_out [n_y][dim]; result_host[6] = {iterations,
+ *                sigma2, |sigma2 - sigma2_prev|, eigen-iterations, eigen-residual / |lambda_1|,
+ *                smallest kept |eigenvalue|}; ends when |sigma2 - sigma2_prev| <= tolerance.
+ *   *_apply:     transform_point_cloud on any point set: pts b + t, or pts + G(pts, y) w.
+ * `w` is the outlier weight of the E-step (0 in the reference's calls).
+ * ------------------------------------------------------------------------------------------- */
+size_t focusr_cpd_workspace_bytes(int n_x, int n_y, int dim, int num_eig /* 0 = affine only */);
+int focusr_cpd_affine(const double* x, int n_x, const double* y, int n_y, int dim, int max_iterations,
+                      double tolerance, double w, double* b_out, double* t_out, double* ty_out,
+                      double* result_host, void* workspace, size_t workspace_bytes,
+                      focusr_stream_t stream);
+int focusr_cpd_deformable(const double* x, int n_x, const double* y, int n_y, int dim,
+                          int max_iterations, double tolerance, double w, double alpha, double beta,
+                          int num_eig, double* w_out, double* ty_out, double* result_host,
+                          void* workspace, size_t workspace_bytes, focusr_stream_t stream);
+/* g_out [n_y][n_y] = exp(-|y_i - y_j|^2 / (2 beta^2)): the `G` of cycpd's (G, W) parameter tuple. */
+int focusr_cpd_kernel_matrix(const double* y, int n_y, int dim, double beta, double* g_out,
+                             focusr_stream_t stream);
+int focusr_cpd_affine_apply(const double* pts, int n, int dim, const double* b, const double* t,
+                            double* out, focusr_stream_t stream);
+int focusr_cpd_deformable_apply(const double* pts, int n, const double* y, int n_y, int dim,
+                                const double* w, double beta, double* out, focusr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

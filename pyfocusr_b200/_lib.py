@@ -57,6 +57,12 @@ SIGNATURES = {
     "focusr_knn_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "focusr_knn": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "focusr_weighted_positions": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "focusr_cpd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "focusr_cpd_affine": (_i, [_vp, _i, _vp, _i, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "focusr_cpd_deformable": (_i, [_vp, _i, _vp, _i, _i, _i, _d, _d, _d, _d, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "focusr_cpd_kernel_matrix": (_i, [_vp, _i, _i, _d, _vp, _vp]),
+    "focusr_cpd_affine_apply": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "focusr_cpd_deformable_apply": (_i, [_vp, _i, _vp, _i, _i, _vp, _d, _vp, _vp]),
 }
 
 _lib = None

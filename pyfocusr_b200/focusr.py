@@ -4,10 +4,11 @@ Constructor signature, attribute names and method names follow the reference.  O
  the work runs in libfocusr_b200.so: both graphs' Laplacians and spectra,
 eigsort, KNN correspondences (focusr.py:351-366), the 300 + 40 smoothing passes and the second
 KNN (focusr.py:368-396), the k=3 weighted positions (focusr.py:401-426) and the nearest-neighbour
-gather (focusr.py:428-431).  ICP (VTK) and CPD (cycpd) stay on the reference's own libraries:
-they are imported lazily and raise ImportError when absent.  The extra keyword ``registration``
-("cycpd" | "identity", after the reference's last argument) lets the spectral stage run where
-cycpd is not installed, with CPD replaced by the identity as in BASELINE.md section 3.
+gather (focusr.py:428-431).  ICP stays on VTK (imported lazily, ImportError when absent).  The extra
+keyword ``registration`` (after the reference's last argument) selects the CPD step of
+focusr.py:297-334: "b200" (default) runs affine + deformable Coherent Point Drift on the GPU
+(pyfocusr_b200.cpd, same call surface as cycpd); "cycpd" uses the reference's own dependency when it
+is installed; "identity" skips the step, as in the throughput configuration of BASELINE.md section 3.
 """
 from __future__ import annotations
 
@@ -118,7 +119,7 @@ class Focusr(object):
         norm_node_features_cap_std=3,
         norm_node_features_0_1=True,
         verbose=False,
-        registration="cycpd",
+        registration="b200",
     ):
         self.verbose = verbose
         self.registration = registration
@@ -242,13 +243,18 @@ class Focusr(object):
     def register_target_to_source(self, reg_type="deformable"):
         if self.registration == "identity":
             return
-        try:
-            import cycpd  # type: ignore
-        except ImportError as e:
-            raise ImportError(
-                "CPD stays on the reference's cycpd path (focusr.py:297-334) and cycpd is not installed; "
-                "construct Focusr(..., registration='identity') to run the spectral stage without it"
-            ) from e
+        if self.registration == "cycpd":
+            try:
+                import cycpd  # type: ignore
+            except ImportError as e:
+                raise ImportError(
+                    "registration='cycpd' asks for the reference's own CPD dependency (focusr.py:297-334) and cycpd "
+                    "is not installed; use registration='b200' (GPU CPD) or 'identity'"
+                ) from e
+        elif self.registration == "b200":
+            from . import cpd as cycpd
+        else:
+            raise ValueError("registration must be 'b200', 'cycpd' or 'identity'")
         x = self.source_spectral_coords[self.graph_source.get_list_rand_idxs(self.n_coords_spectral_registration), :]
         y = self.target_spectral_coords[self.graph_target.get_list_rand_idxs(self.n_coords_spectral_registration), :]
         if reg_type == "deformable":

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../pyfocusr_b200/csrc/cpd_host.hpp"
 #include "../../pyfocusr_b200/csrc/chfsi_driver.hpp"
 #include "../../pyfocusr_b200/csrc/rowops.h"
 
@@ -225,6 +226,13 @@ int hostsim_rr_sym(double* g, double* h, double* w, double* theta, int b) {
   std::vector<int> rank(b), pq(b + 2);
   fb::SeqPar par;
   return fb::rayleigh_ritz_sym(g, h, y.data(), w, theta, rank.data(), rot.data(), pq.data(), b, par);
+}
+
+// a (n x n, symmetric) is overwritten by the eigenvectors (columns); evals unsorted
+int hostsim_eig_sym(double* a, double* evals, int n) { return fb::eig_sym_host(a, evals, n); }
+
+int hostsim_rr_leading(double* g, double* h, int b, double* w, double* theta) {
+  return fb::rr_leading_host(g, h, b, w, theta);
 }
 
 int hostsim_eig_general(const double* a, int n, double* evals_ri, double* evecs_ri) {
