@@ -11,10 +11,10 @@ from .batch import SpectralBatch
 from .eigsort import eigsort
 from .focusr import Focusr
 from .graph import Graph, recursive_eig
-from .mesh import PolyData, ellipsoid_pair, icosphere, perturbed_ellipsoid, read_vtk_mesh
+from .mesh import PolyData, ellipsoid_pair, icosphere, perturbed_ellipsoid, read_vtk_mesh, write_vtk_mesh
 
 __all__ = [
-    "Focusr", "Graph", "recursive_eig", "eigsort", "SpectralBatch", "PolyData", "read_vtk_mesh",
+    "Focusr", "Graph", "recursive_eig", "eigsort", "SpectralBatch", "PolyData", "read_vtk_mesh", "write_vtk_mesh",
     "icosphere", "perturbed_ellipsoid", "ellipsoid_pair", "vtk_functions",
 ]
 __version__ = "0.1.0"

@@ -288,7 +288,7 @@ int chfsi_solve(BE& be, const SolveParams& p, MeshResult* out) {
       // the meshes' small eigenproblems are independent: one host thread each (OpenMP when compiled in)
       std::vector<int> rr_rc(M, 0);
 #if defined(_OPENMP)
-#pragma omp parallel for schedule(dynamic)
+#pragma omp parallel for schedule(dynamic) if (M >= 8) num_threads(M < 64 ? M : 64)
 #endif
       for (int m = 0; m < M; ++m) {
         const double cut = a_prev[m] < 0.0 ? 0.5 * p.beta : 2.0 * a_prev[m];

@@ -116,57 +116,181 @@ class PolyData:
         return PolyData(self.points.copy(), self.tris.copy(), dict(self.point_scalars))
 
 
-def read_vtk_mesh(path_to_file):
-    """Legacy-ASCII ``DATASET POLYDATA`` reader (replaces ``vtk_functions.py:5-9``).
+_VTK_TYPES = {
+    "float": ">f4", "double": ">f8", "int": ">i4", "unsigned_int": ">u4", "long": ">i8", "unsigned_long": ">u8",
+    "short": ">i2", "unsigned_short": ">u2", "char": ">i1", "unsigned_char": ">u1", "vtktypeint64": ">i8",
+    "vtktypeint32": ">i4", "vtkidtype": ">i8", "bit": ">u1",
+}
 
-    Handles the sections present in the shipped data files (``POINTS``, ``POLYGONS``,
-    ``POINT_DATA``/``SCALARS``); all polygons must be triangles.
+
+class _LegacyCursor:
+    """Walks a legacy .vtk file held in memory: header lines as text, data blocks as ASCII tokens or
+    big-endian binary (the legacy format's byte order)."""
+
+    def __init__(self, buf, binary):
+        self.buf, self.pos, self.binary = buf, 0, binary
+
+    def line(self):
+        """Next non-blank line as a list of words (None at the end of the file)."""
+        n = len(self.buf)
+        while self.pos < n:
+            end = self.buf.find(b"\n", self.pos)
+            end = n if end < 0 else end
+            raw = self.buf[self.pos:end]
+            self.pos = end + 1
+            words = raw.decode("ascii", "replace").split()
+            if words:
+                return words
+        return None
+
+    def values(self, count, vtk_type):
+        dt = _VTK_TYPES.get(vtk_type.lower())
+        if dt is None:
+            raise ValueError("unsupported VTK data type %r" % vtk_type)
+        if self.binary:
+            nbytes = count * np.dtype(dt).itemsize
+            if self.pos + nbytes > len(self.buf):
+                raise ValueError("truncated binary section")
+            out = np.frombuffer(self.buf, dtype=dt, count=count, offset=self.pos)
+            self.pos += nbytes
+            return out
+        parts = self.buf[self.pos:].split(None, count)
+        if len(parts) < count:
+            raise ValueError("truncated ASCII section")
+        rest = parts[count] if len(parts) > count else b""
+        self.pos = len(self.buf) - len(rest)
+        if np.dtype(dt).kind != "f":
+            return np.array(parts[:count], dtype=np.int64)
+        out = np.array(parts[:count], dtype=np.float64)
+        return out.astype(np.float32) if np.dtype(dt).itemsize == 4 else out   # a `float` array holds float32 values
+
+
+def read_vtk_mesh(path_to_file):
+    """Legacy ``DATASET POLYDATA`` reader, ASCII and BINARY (replaces ``vtk_functions.py:5-9``, which goes
+    through ``vtkPolyDataReader``).
+
+    Handles ``POINTS``, ``POLYGONS`` in the classic layout (``n size`` then ``3 i j k`` records) and in the
+    version 5.x layout (``OFFSETS`` / ``CONNECTIVITY`` arrays), and ``POINT_DATA`` with ``SCALARS`` and
+    ``FIELD`` arrays; other sections (``VERTICES``, ``LINES``, ``CELL_DATA``, ``NORMALS``, ...) are skipped.
+    All polygons must be triangles.
     """
-    with open(path_to_file, "r") as f:
-        tokens = f.read().split("\n")
-    header = tokens[:4]
-    if len(header) < 4 or "ASCII" not in header[2].upper():
-        raise ValueError("only legacy ASCII VTK files are supported: %s" % path_to_file)
-    words = " ".join(tokens[4:]).split()
-    pos = 0
+    with open(path_to_file, "rb") as f:
+        buf = f.read()
+    head = buf.split(b"\n", 3)
+    if len(head) < 4 or not head[0].startswith(b"# vtk DataFile"):
+        raise ValueError("not a legacy VTK file: %s" % path_to_file)
+    mode = head[2].strip().upper()
+    if mode not in (b"ASCII", b"BINARY"):
+        raise ValueError("legacy VTK file must be ASCII or BINARY: %s" % path_to_file)
+    cur = _LegacyCursor(buf, mode == b"BINARY")
+    cur.pos = len(head[0]) + len(head[1]) + len(head[2]) + 3
     points = tris = None
     scalars = {}
-    n_points = 0
-    while pos < len(words):
-        w = words[pos].upper()
-        if w == "DATASET":
-            if words[pos + 1].upper() != "POLYDATA":
+    n_points, in_point_data = 0, False
+    while True:
+        words = cur.line()
+        if words is None:
+            break
+        key = words[0].upper()
+        if key == "DATASET":
+            if words[1].upper() != "POLYDATA":
                 raise ValueError("DATASET must be POLYDATA")
-            pos += 2
-        elif w == "POINTS":
-            n_points = int(words[pos + 1])
-            pos += 3
-            points = np.array(words[pos : pos + 3 * n_points], dtype=np.float64).reshape(-1, 3)
-            pos += 3 * n_points
-        elif w == "POLYGONS":
-            n_cells, size = int(words[pos + 1]), int(words[pos + 2])
-            pos += 3
-            raw = np.array(words[pos : pos + size], dtype=np.int64)
-            pos += size
-            if size != 4 * n_cells or not np.all(raw[0::4] == 3):
-                raise ValueError("only triangle meshes are supported")
-            tris = raw.reshape(-1, 4)[:, 1:].astype(np.int32)
-        elif w == "POINT_DATA":
-            pos += 2
-        elif w == "SCALARS":
-            name = words[pos + 1]
-            pos += 3
-            # optional numComp
-            if words[pos].upper() != "LOOKUP_TABLE":
-                pos += 1
-            pos += 2  # LOOKUP_TABLE <name>
-            scalars[name] = np.array(words[pos : pos + n_points], dtype=np.float64)
-            pos += n_points
-        else:
-            pos += 1
+        elif key == "POINTS":
+            n_points = int(words[1])
+            points = np.ascontiguousarray(cur.values(3 * n_points, words[2]).reshape(-1, 3), dtype=np.float64)
+        elif key in ("POLYGONS", "VERTICES", "LINES", "TRIANGLE_STRIPS"):
+            a, b = int(words[1]), int(words[2])
+            nxt_pos = cur.pos
+            nxt = cur.line()
+            if nxt is not None and nxt[0].upper() == "OFFSETS":          # version 5.x: a = n_cells + 1, b = connectivity size
+                offs = cur.values(a, nxt[1])
+                cw = cur.line()
+                if cw is None or cw[0].upper() != "CONNECTIVITY":
+                    raise ValueError("OFFSETS without CONNECTIVITY")
+                conn = cur.values(b, cw[1])
+                if key == "POLYGONS":
+                    if not np.all(np.diff(offs) == 3):
+                        raise ValueError("only triangle meshes are supported")
+                    tris = np.ascontiguousarray(conn.reshape(-1, 3), dtype=np.int32)
+            else:                                                          # classic: a = n_cells, b = total ints
+                cur.pos = nxt_pos
+                raw = cur.values(b, "int")
+                if key == "POLYGONS":
+                    if b != 4 * a or not np.all(raw[0::4] == 3):
+                        raise ValueError("only triangle meshes are supported")
+                    tris = np.ascontiguousarray(raw.reshape(-1, 4)[:, 1:], dtype=np.int32)
+        elif key == "POINT_DATA":
+            in_point_data, n_tuples = True, int(words[1])
+        elif key == "CELL_DATA":
+            in_point_data, n_tuples = False, int(words[1])
+        elif key == "SCALARS":
+            ncomp = int(words[3]) if len(words) > 3 else 1
+            lt_pos = cur.pos
+            lt = cur.line()
+            if lt is None or lt[0].upper() != "LOOKUP_TABLE":
+                cur.pos = lt_pos
+            vals = cur.values(n_tuples * ncomp, words[2])
+            if in_point_data and ncomp == 1:
+                scalars[words[1]] = np.asarray(vals, dtype=np.float64)
+        elif key in ("VECTORS", "NORMALS"):
+            cur.values(3 * n_tuples, words[2])
+        elif key == "TEXTURE_COORDINATES":
+            cur.values(int(words[2]) * n_tuples, words[3])
+        elif key == "COLOR_SCALARS":
+            cur.values(int(words[2]) * n_tuples, "unsigned_char" if cur.binary else "float")
+        elif key == "LOOKUP_TABLE":
+            cur.values(4 * int(words[2]), "unsigned_char" if cur.binary else "float")
+        elif key == "FIELD":
+            for _ in range(int(words[2])):
+                fw = cur.line()
+                if fw is None:
+                    break
+                if fw[0].upper() == "METADATA":      # 5.x information block: skip to the blank-line-terminated end
+                    fw = cur.line()
+                    while fw is not None and fw[0].upper() in ("INFORMATION", "NAME", "DATA"):
+                        fw = cur.line()
+                    if fw is None:
+                        break
+                ncomp, ntup = int(fw[1]), int(fw[2])
+                vals = cur.values(ncomp * ntup, fw[3])
+                if in_point_data and ncomp == 1 and ntup == n_points:
+                    scalars[fw[0]] = np.asarray(vals, dtype=np.float64)
+        # anything else (METADATA, INFORMATION, blank keywords): ignored
     if points is None or tris is None:
         raise ValueError("file has no POINTS/POLYGONS section: %s" % path_to_file)
+    if tris.size and (tris.min() < 0 or tris.max() >= n_points):
+        raise ValueError("polygon index out of range in %s" % path_to_file)
     return PolyData(points, tris, scalars)
+
+
+def write_vtk_mesh(mesh, path_to_file, binary=False):
+    """Write a legacy (version 3.0, classic POLYGONS layout) ``DATASET POLYDATA`` file: points as double,
+    triangles, and the point scalars.  ASCII output uses 17 significant digits, so both encodings round-trip
+    bit-exactly through :func:`read_vtk_mesh`."""
+    pts, tris = mesh_arrays(mesh)
+    scalars = getattr(mesh, "point_scalars", {}) or {}
+    n, f = pts.shape[0], tris.shape[0]
+    with open(path_to_file, "wb") as out:
+        out.write(b"# vtk DataFile Version 3.0\npyfocusr_b200 mesh\n" + (b"BINARY\n" if binary else b"ASCII\n"))
+        out.write(b"DATASET POLYDATA\nPOINTS %d double\n" % n)
+        if binary:
+            out.write(np.ascontiguousarray(pts, dtype=">f8").tobytes() + b"\n")
+        else:
+            out.write("\n".join(" ".join("%.17g" % v for v in row) for row in pts).encode() + b"\n")
+        out.write(b"POLYGONS %d %d\n" % (f, 4 * f))
+        cells = np.concatenate([np.full((f, 1), 3, dtype=np.int64), tris.astype(np.int64)], axis=1)
+        if binary:
+            out.write(np.ascontiguousarray(cells, dtype=">i4").tobytes() + b"\n")
+        else:
+            out.write("\n".join(" ".join(str(v) for v in row) for row in cells).encode() + b"\n")
+        if scalars:
+            out.write(b"POINT_DATA %d\n" % n)
+            for name, vals in scalars.items():
+                out.write(("SCALARS %s double 1\nLOOKUP_TABLE default\n" % name.replace(" ", "_")).encode())
+                if binary:
+                    out.write(np.ascontiguousarray(vals, dtype=">f8").tobytes() + b"\n")
+                else:
+                    out.write("\n".join("%.17g" % v for v in np.asarray(vals, dtype=np.float64)).encode() + b"\n")
 
 
 def mesh_arrays(vtk_mesh):

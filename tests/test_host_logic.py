@@ -293,3 +293,56 @@ def test_driver_nonsymmetric_on_damaged_meshes(hostsim):
         rc, vals, vecs, ri, offs, sym = _solve(hostsim, [m], 7, 6, b, ldv=64)
         assert rc == 0 and not sym and ri[0, 1] == 6
         _check(m, vals[0, :6], vecs[:, :6], 6)
+
+
+def test_legacy_vtk_reader_ascii_binary_and_v5_layout(tmp_path, shipped_meshes):
+    """mesh ingest without VTK.  ASCII and BINARY round trips are bit-exact, the
+    version 5.x OFFSETS/CONNECTIVITY layout is understood, other sections are skipped."""
+    m = shipped_meshes["source_mesh_15k"]
+    scal = dict(m.point_scalars)
+    assert scal                                                  # the shipped files carry thickness_change_(mm)
+    for binary in (False, True):
+        p = str(tmp_path / ("m%d.vtk" % binary))
+        fmesh.write_vtk_mesh(m, p, binary=binary)
+        r = fmesh.read_vtk_mesh(p)
+        assert np.array_equal(r.points, m.points) and np.array_equal(r.tris, m.tris)
+        for k, v in scal.items():
+            assert np.array_equal(r.point_scalars[k.replace(" ", "_")], v)
+    # version 5.1 layout written by hand, with a LINES section and CELL_DATA to skip, ASCII and BINARY
+    small = fmesh.icosphere(2)
+    n, f = small.points.shape[0], small.tris.shape[0]
+    offs, conn = np.arange(0, 3 * f + 1, 3), small.tris.reshape(-1)
+    for binary in (False, True):
+        p = str(tmp_path / ("v5_%d.vtk" % binary))
+        with open(p, "wb") as out:
+            out.write(b"# vtk DataFile Version 5.1\nv5\n" + (b"BINARY\n" if binary else b"ASCII\n") + b"DATASET POLYDATA\n")
+            out.write(b"POINTS %d float\n" % n)
+            p32 = small.points.astype(np.float32)
+            out.write(p32.astype(">f4").tobytes() + b"\n" if binary else (" ".join("%.9g" % v for v in p32.reshape(-1)) + "\n").encode())
+            out.write(b"LINES 2 2\nOFFSETS vtktypeint64\n")
+            out.write(np.array([0, 2], ">i8").tobytes() + b"\n" if binary else b"0 2\n")
+            out.write(b"CONNECTIVITY vtktypeint64\n")
+            out.write(np.array([0, 1], ">i8").tobytes() + b"\n" if binary else b"0 1\n")
+            out.write(b"POLYGONS %d %d\nOFFSETS vtktypeint64\n" % (f + 1, 3 * f))
+            out.write(offs.astype(">i8").tobytes() + b"\n" if binary else (" ".join(map(str, offs)) + "\n").encode())
+            out.write(b"CONNECTIVITY vtktypeint64\n")
+            out.write(conn.astype(">i8").tobytes() + b"\n" if binary else (" ".join(map(str, conn)) + "\n").encode())
+            out.write(b"CELL_DATA %d\nSCALARS cid int 1\nLOOKUP_TABLE default\n" % (f + 1))
+            cid = np.arange(f + 1)
+            out.write(cid.astype(">i4").tobytes() + b"\n" if binary else (" ".join(map(str, cid)) + "\n").encode())
+            out.write(b"POINT_DATA %d\nSCALARS height float\nLOOKUP_TABLE default\n" % n)
+            out.write(p32[:, 2].astype(">f4").tobytes() + b"\n" if binary else (" ".join("%.9g" % v for v in p32[:, 2]) + "\n").encode())
+        r = fmesh.read_vtk_mesh(p)
+        assert np.array_equal(r.points, p32.astype(np.float64)) and np.array_equal(r.tris, small.tris)
+        assert list(r.point_scalars) == ["height"] and np.array_equal(r.point_scalars["height"], p32[:, 2].astype(np.float64))
+    # error behaviour
+    bad = str(tmp_path / "bad.vtk")
+    open(bad, "wb").write(b"# vtk DataFile Version 3.0\nx\nASCII\nDATASET POLYDATA\nPOINTS 3 double\n0 0 0 1 0 0 0 1 0\nPOLYGONS 1 5\n4 0 1 2 0\n")
+    with pytest.raises(ValueError):
+        fmesh.read_vtk_mesh(bad)                                  # a quad
+    open(bad, "wb").write(b"# vtk DataFile Version 3.0\nx\nASCII\nDATASET POLYDATA\nPOINTS 3 double\n0 0 0 1 0 0 0 1 0\nPOLYGONS 1 4\n3 0 1 7\n")
+    with pytest.raises(ValueError):
+        fmesh.read_vtk_mesh(bad)                                  # index out of range
+    open(bad, "wb").write(b"not a vtk file\n\n\n\n")
+    with pytest.raises(ValueError):
+        fmesh.read_vtk_mesh(bad)
