@@ -33,7 +33,7 @@ namespace fb {
 
 constexpr int CPD_MAXD = 16;
 constexpr int CPD_T = 128;      // threads per CTA of the E-step kernels
-constexpr int CPD_CHUNK = 256;  // points of the other set staged in shared memory per CTA
+constexpr int CPD_CHUNK = 128;  // points of the other set staged in shared memory per CTA
 constexpr int CPD_ACH = 128;    // control points per stage of the deformable transform kernel
 constexpr int CPD_MCH = 128;    // rows per CTA of the moment kernels
 constexpr int CPD_TN_ROWS = 128;  // rows per warp of the tall-skinny Gram kernel
@@ -371,41 +371,53 @@ __global__ void k_cpd_finish(CpdState* st) {
 }
 
 // ------------------------------------------------------------------------------------------- dense helpers
-// partial[chunk][p][q] = sum_{r in chunk} A[r][p] scale[r] B[r][q]   (one warp per CTA; DMMA m8n8k4:
-// lane l holds A[l>>2][l&3], B[l&3][l>>2], D[l>>2][2(l&3)+{0,1}]).  grid (chunks, ra/8, ceil(rb/8/QT)).
+// partial[chunk][p][q] = sum_{r in chunk} A[r][p] scale[r] B[r][q]   (DMMA m8n8k4: lane l holds A[l>>2][l&3],
+// B[l&3][l>>2], D[l>>2][2(l&3)+{0,1}]).  CTA = 4 warps on one chunk of 128 rows: each warp takes 32 rows as 8
+// fully unrolled k-steps (all loads in flight at once -- the kernel is latency-bound, not flop-bound), then the
+// four accumulator tiles are added in warp order through shared memory.  grid (chunks, ra/8, ceil(rb/8/QT)).
 template <int QT>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(128)
 k_tn_gram(const double* __restrict__ A, int lda, const double* __restrict__ Bm, int ldb, const double* __restrict__ scale,
           int rows, int ra, int rb, double* __restrict__ partial, const CpdState* __restrict__ st) {
   if (st && !st->active) return;
-  const int lane = threadIdx.x, kq = lane & 3, cc = lane >> 2;
+  __shared__ double red[4][QT][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kq = lane & 3, cc = lane >> 2;
   const int chunk = blockIdx.x, p0 = blockIdx.y * 8, t0 = blockIdx.z * QT, nbt = rb >> 3;
-  const int r0 = chunk * CPD_TN_ROWS, r1 = min(rows, r0 + CPD_TN_ROWS);
+  const int r0 = chunk * CPD_TN_ROWS + warp * 32, r1 = min(rows, chunk * CPD_TN_ROWS + CPD_TN_ROWS);
   double acc[QT][2];
 #pragma unroll
   for (int t = 0; t < QT; ++t) acc[t][0] = acc[t][1] = 0.0;
-  for (int r = r0; r < r1; r += 4) {
-    const int row = r + kq;
+  double av[8], bv[8][QT];
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    const int row = r0 + 4 * s + kq;
     const bool ok = row < r1;
-    double a = 0.0;
-    if (ok) {
-      a = A[(size_t)row * lda + p0 + cc];
-      if (scale) a *= scale[row];
-    }
+    av[s] = ok ? A[(size_t)row * lda + p0 + cc] : 0.0;
+    if (ok && scale) av[s] *= scale[row];
+#pragma unroll
+    for (int t = 0; t < QT; ++t) bv[s][t] = (ok && t0 + t < nbt) ? Bm[(size_t)row * ldb + 8 * (t0 + t) + cc] : 0.0;
+  }
+#pragma unroll
+  for (int s = 0; s < 8; ++s)
+#pragma unroll
+    for (int t = 0; t < QT; ++t) dmma884c(acc[t][0], acc[t][1], av[s], bv[s][t]);
+#pragma unroll
+  for (int t = 0; t < QT; ++t) {
+    red[warp][t][2 * lane] = acc[t][0];
+    red[warp][t][2 * lane + 1] = acc[t][1];
+  }
+  __syncthreads();
+  if (warp == 0) {
 #pragma unroll
     for (int t = 0; t < QT; ++t)
       if (t0 + t < nbt) {
-        const double b = ok ? Bm[(size_t)row * ldb + 8 * (t0 + t) + cc] : 0.0;
-        dmma884c(acc[t][0], acc[t][1], a, b);
+        const double v0 = ((red[0][t][2 * lane] + red[1][t][2 * lane]) + red[2][t][2 * lane]) + red[3][t][2 * lane];
+        const double v1 = ((red[0][t][2 * lane + 1] + red[1][t][2 * lane + 1]) + red[2][t][2 * lane + 1]) + red[3][t][2 * lane + 1];
+        double* o = partial + ((size_t)chunk * ra + p0 + cc) * rb + 8 * (t0 + t) + 2 * kq;
+        o[0] = v0;
+        o[1] = v1;
       }
   }
-#pragma unroll
-  for (int t = 0; t < QT; ++t)
-    if (t0 + t < nbt) {
-      double* o = partial + ((size_t)chunk * ra + p0 + cc) * rb + 8 * (t0 + t) + 2 * kq;
-      o[0] = acc[t][0];
-      o[1] = acc[t][1];
-    }
 }
 
 __global__ void k_sum_partials(const double* __restrict__ partial, int chunks, int n, double* __restrict__ out,
@@ -556,42 +568,86 @@ k_cpd_def_solve(const double* __restrict__ t1, const double* __restrict__ t2, co
   for (int k0 = 0; k0 < rp; k0 += LU_PW) {
     const int k1 = min(k0 + LU_PW, rp);
     if (warp == 0) {
-      for (int k = k0; k < k1; ++k) {
-        double best = -1.0;
-        int bi = k;
-        for (int i = k + lane; i < rp; i += 32) {
-          const double v = fabs(a[i * ld + k]);
-          if (v > best) {
-            best = v;
-            bi = i;
-          }
-        }
+      // the panel lives in registers: lane l owns rows l, l+32, l+64, l+96 (rp <= 160 -> 5 slots)
+      constexpr int SL = 5;
+      double pr[SL][LU_PW];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-          if (ov > best || (ov == best && oi < bi)) {
-            best = ov;
-            bi = oi;
+      for (int sl = 0; sl < SL; ++sl) {
+        const int i = lane + 32 * sl;
+#pragma unroll
+        for (int c = 0; c < LU_PW; ++c) pr[sl][c] = (i < rp && k0 + c < k1) ? a[i * ld + k0 + c] : 0.0;
+      }
+#pragma unroll
+      for (int kk = 0; kk < LU_PW; ++kk) {
+        const int k = k0 + kk;
+        if (k < k1) {
+          double best = -1.0;
+          int bi = k;
+#pragma unroll
+          for (int sl = 0; sl < SL; ++sl) {
+            const int i = lane + 32 * sl;
+            const double v = fabs(pr[sl][kk]);
+            if (i >= k && i < rp && v > best) {
+              best = v;
+              bi = i;
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) {
+              best = ov;
+              bi = oi;
+            }
+          }
+          if (lane == 0) {
+            piv[kk] = bi;
+            if (!(best > 0.0)) bad = 1;
+          }
+          // pivot row and row k, broadcast from their owners; then the swap
+          double rowp[LU_PW], rowk[LU_PW];
+          const int slp = bi >> 5, slk = k >> 5;
+#pragma unroll
+          for (int c = 0; c < LU_PW; ++c) {
+            double mp = 0.0, mk = 0.0;
+#pragma unroll
+            for (int sl = 0; sl < SL; ++sl) {
+              if (sl == slp) mp = pr[sl][c];
+              if (sl == slk) mk = pr[sl][c];
+            }
+            rowp[c] = __shfl_sync(0xffffffffu, mp, bi & 31);
+            rowk[c] = __shfl_sync(0xffffffffu, mk, k & 31);
+          }
+          if (bi != k) {
+#pragma unroll
+            for (int sl = 0; sl < SL; ++sl)
+#pragma unroll
+              for (int c = 0; c < LU_PW; ++c) {
+                if (sl == slk && lane == (k & 31)) pr[sl][c] = rowp[c];
+                if (sl == slp && lane == (bi & 31)) pr[sl][c] = rowk[c];
+              }
+          }
+          const double inv = 1.0 / rowp[kk];
+#pragma unroll
+          for (int sl = 0; sl < SL; ++sl) {
+            const int i = lane + 32 * sl;
+            if (i > k && i < rp) {
+              const double f = pr[sl][kk] * inv;
+              pr[sl][kk] = f;
+#pragma unroll
+              for (int c = kk + 1; c < LU_PW; ++c) pr[sl][c] -= f * rowp[c];
+            }
           }
         }
-        if (lane == 0) {
-          piv[k - k0] = bi;
-          if (!(best > 0.0)) bad = 1;
-        }
-        if (bi != k && lane < k1 - k0) {  // swap inside the panel
-          const double tmp = a[k * ld + k0 + lane];
-          a[k * ld + k0 + lane] = a[bi * ld + k0 + lane];
-          a[bi * ld + k0 + lane] = tmp;
-        }
-        __syncwarp();
-        const double inv = 1.0 / a[k * ld + k];
-        for (int i = k + 1 + lane; i < rp; i += 32) {
-          const double f = a[i * ld + k] * inv;
-          a[i * ld + k] = f;
-          for (int c = k + 1; c < k1; ++c) a[i * ld + c] -= f * a[k * ld + c];
-        }
-        __syncwarp();
+      }
+#pragma unroll
+      for (int sl = 0; sl < SL; ++sl) {
+        const int i = lane + 32 * sl;
+        if (i >= k0 && i < rp)
+#pragma unroll
+          for (int c = 0; c < LU_PW; ++c)
+            if (k0 + c < k1) a[i * ld + k0 + c] = pr[sl][c];
       }
     }
     __syncthreads();
@@ -647,6 +703,135 @@ k_cpd_def_solve(const double* __restrict__ t1, const double* __restrict__ t2, co
     const int k = i / dp, d = i % dp;
     z[i] = d < d_real ? a[k * ld + rp + d] : 0.0;
   }
+}
+
+// The same system for the common ranks (a thread's share of the matrix fits 28 registers): Gaussian
+// elimination WITHOUT pivoting with the matrix held in registers.  lambda S^-1 + Q^T dP Q is symmetric positive
+// definite on the eigenpairs with S > 0, and the rows of (rounding-noise) eigenvalues S < 0 have diagonals
+// ~ -lambda / |S| that dominate their row by >= 1e8, so no pivot can be small against its column.  Thread t owns
+// column c = t % CW and the rows rg, rg + RG, ... of it; step k publishes row k and column k through
+// double-buffered shared memory (one barrier per column instead of a serial panel factorisation), then every
+// thread updates its own elements.  Back substitution: one warp per right-hand side, the running right-hand
+// side in registers, the solved component broadcast by shuffle, reciprocal diagonal precomputed.
+template <int MAXJ>
+__global__ void __launch_bounds__(512)
+k_cpd_def_solve_reg(const double* __restrict__ t1, const double* __restrict__ t2, const double* __restrict__ S, int rp, int dp,
+                    int d_real, double alpha, CpdState* st, double* __restrict__ z) {
+  if (!st->active) return;
+  extern __shared__ double sm[];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int CW = rp + d_real, RG = 512 / CW, ld = CW + 1;
+  const int c = t % CW, rg = t / CW;
+  const bool on = rg < RG;
+  double* a = sm;                        // [rp][ld]   (written after the elimination)
+  double* rowbuf = a + (size_t)rp * ld;  // [2][CW]
+  double* colbuf = rowbuf + 2 * CW;      // [2][rp]
+  double* dinv = colbuf + 2 * rp;        // [rp]
+  __shared__ int bad;
+  const double lam = alpha * st->sigma2;
+  double v[MAXJ];
+#pragma unroll
+  for (int j = 0; j < MAXJ; ++j) {
+    const int r = rg + RG * j;
+    double x = 0.0;
+    if (on && r < rp) {
+      if (c < rp) {
+        x = t1[(size_t)r * rp + c];
+        if (r == c) {
+          double sv = S[r];
+          if (fabs(sv) < 1e-300) sv = sv < 0.0 ? -1e-300 : 1e-300;
+          x += lam / sv;
+        }
+      } else {
+        x = t2[(size_t)r * dp + (c - rp)];
+      }
+    }
+    v[j] = x;
+  }
+  if (t == 0) {
+    st->lam = lam;
+    bad = 0;
+  }
+  for (int k = 0; k < rp; ++k) {
+    double* rb = rowbuf + (k & 1) * CW;
+    double* cb = colbuf + (k & 1) * rp;
+    const int jk = k / RG, rgk = k - jk * RG;
+    if (on && rg == rgk) {
+      double x = 0.0;
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j)
+        if (j == jk) x = v[j];
+      rb[c] = x;
+    }
+    if (on && c == k) {
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j) {
+        const int r = rg + RG * j;
+        if (r < rp) cb[r] = v[j];
+      }
+    }
+    __syncthreads();
+    if (on && c > k) {
+      const double piv = rb[k];
+      if (!(fabs(piv) > 0.0)) bad = 1;
+      const double s = rb[c] / piv;
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j) {
+        const int r = rg + RG * j;
+        if (r > k && r < rp) v[j] -= cb[r] * s;
+      }
+    }
+  }
+  if (on) {
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+      const int r = rg + RG * j;
+      if (r < rp) a[r * ld + c] = v[j];
+    }
+  }
+  __syncthreads();
+  if (bad) {
+    if (t == 0) {
+      st->singular = 1;
+      st->diff = 0.0;
+    }
+    return;
+  }
+  for (int r = t; r < rp; r += 512) dinv[r] = 1.0 / a[r * ld + r];
+  __syncthreads();
+  if (warp < d_real) {
+    constexpr int SL = 5;  // rp <= 160
+    const int cr = rp + warp;
+    double b[SL];
+#pragma unroll
+    for (int sl = 0; sl < SL; ++sl) {
+      const int i = lane + 32 * sl;
+      b[sl] = i < rp ? a[i * ld + cr] : 0.0;
+    }
+    for (int k = rp - 1; k >= 0; --k) {
+      const int slk = k >> 5;
+      double mine = 0.0;
+#pragma unroll
+      for (int sl = 0; sl < SL; ++sl)
+        if (sl == slk) mine = b[sl];
+      const double zk = __shfl_sync(0xffffffffu, mine, k & 31) * dinv[k];
+#pragma unroll
+      for (int sl = 0; sl < SL; ++sl) {
+        const int i = lane + 32 * sl;
+        if (i < k)
+          b[sl] -= a[i * ld + k] * zk;
+        else if (i == k)
+          b[sl] = zk;
+      }
+    }
+#pragma unroll
+    for (int sl = 0; sl < SL; ++sl) {
+      const int i = lane + 32 * sl;
+      if (i < rp) z[(size_t)i * dp + warp] = b[sl];
+    }
+  }
+  for (int i = t; i < rp * dp; i += 512)
+    if (i % dp >= d_real) z[i] = 0.0;
 }
 
 // W = (F - P1 (Q Z)) / lambda  (padded [M][DP]); one warp per control point, lanes over the rank
@@ -880,10 +1065,10 @@ static int tn_gram(const double* A, int lda, const double* Bm, int ldb, const do
   const int chunks = div_up(rows, CPD_TN_ROWS), nbt = rb / 8;
   if (nbt > 2) {  // wide right operand: 8 column tiles per warp, so each A fragment feeds 8 MMAs
     dim3 grid(chunks, ra / 8, div_up(nbt, 8));
-    k_tn_gram<8><<<grid, 32, 0, stream>>>(A, lda, Bm, ldb, scale, rows, ra, rb, partial, st);
+    k_tn_gram<8><<<grid, 128, 0, stream>>>(A, lda, Bm, ldb, scale, rows, ra, rb, partial, st);
   } else {
     dim3 grid(chunks, ra / 8, 1);
-    k_tn_gram<2><<<grid, 32, 0, stream>>>(A, lda, Bm, ldb, scale, rows, ra, rb, partial, st);
+    k_tn_gram<2><<<grid, 128, 0, stream>>>(A, lda, Bm, ldb, scale, rows, ra, rb, partial, st);
   }
   k_sum_partials<<<div_up(ra * rb, 256), 256, 0, stream>>>(partial, chunks, ra * rb, out, st);
   FB_COUNT_LAUNCH(2);
@@ -1122,6 +1307,12 @@ int focusr_cpd_deformable(const double* x, int n_x, const double* y, int n_y, in
   FB_CUDA(cudaMemsetAsync(w.W, 0, sizeof(double) * (size_t)M * dp, stream));
   const size_t smem = sizeof(double) * (size_t)rp * (rp + dp + 1);
   FB_CUDA(cudaFuncSetAttribute(k_cpd_def_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // register-resident elimination when every thread's share of the matrix fits 28 registers
+  const int cw = rp + D, rgroups = 512 / cw;
+  const bool reg_lu = rgroups >= 1 && (rp + rgroups - 1) / rgroups <= 28;
+  const size_t smem_reg = sizeof(double) * ((size_t)rp * (cw + 1) + 2 * cw + 3 * rp);
+  if (reg_lu)
+    FB_CUDA(cudaFuncSetAttribute(k_cpd_def_solve_reg<28>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_reg));
   CpdState h;
   if ((rc = cpd_read_state(w, &h, stream))) return rc;
   while (h.active) {
@@ -1131,7 +1322,10 @@ int focusr_cpd_deformable(const double* x, int n_x, const double* y, int n_y, in
       k_cpd_def_prep<<<div_up(M * dp, 256), 256, 0, stream>>>(w.p1, w.px, y, M, D, dp, w.F, w.st);
       if ((rc = tn_gram(w.Q, rp, w.Q, rp, w.p1, M, rp, rp, w.tn_part, w.T1, w.st, stream))) return rc;
       if ((rc = tn_gram(w.Q, rp, w.F, dp, nullptr, M, rp, dp, w.tn_part, w.T2, w.st, stream))) return rc;
-      k_cpd_def_solve<<<1, 512, smem, stream>>>(w.T1, w.T2, w.S, rp, dp, D, alpha, w.st, w.Zs);
+      if (reg_lu)
+        k_cpd_def_solve_reg<28><<<1, 512, smem_reg, stream>>>(w.T1, w.T2, w.S, rp, dp, D, alpha, w.st, w.Zs);
+      else
+        k_cpd_def_solve<<<1, 512, smem, stream>>>(w.T1, w.T2, w.S, rp, dp, D, alpha, w.st, w.Zs);
 #define FB_L(DD) k_cpd_def_w<DD><<<div_up(M, 8), 256, 0, stream>>>(w.F, w.p1, w.Q, rp, w.Zs, M, dp, w.st, w.W)
       FB_CPD_DISPATCH(D, FB_L)
 #undef FB_L
