@@ -260,6 +260,18 @@ int focusr_cpd_affine_apply(const double* pts, int n, int dim, const double* b, 
 int focusr_cpd_deformable_apply(const double* pts, int n, const double* y, int n_y, int dim,
                                 const double* w, double beta, double* out, focusr_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * K9  vtkCurvatures (vtk_functions.py:40-74; the node features of the reference's default
+ * list_features_to_calc=["curvature"], graph.py:11-15,86-87): discrete Gauss, mean, minimum and
+ * maximum curvature per vertex of a triangle mesh (or of a batch of meshes with global vertex ids).
+ * VTK is an unpinned, absent dependency: the algorithm is vtkCurvatures.cxx as restated in
+ * oracle/curvature_port.py.  Outputs [n_points] each, nullable.  SYNCHRONISES the stream (index check).
+ * ------------------------------------------------------------------------------------------- */
+size_t focusr_curvature_workspace_bytes(int n_points, int n_tris);
+int focusr_curvatures(const double* points, const int* tris, int n_points, int n_tris, double* gauss,
+                      double* mean, double* k_min, double* k_max, void* workspace,
+                      size_t workspace_bytes, focusr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

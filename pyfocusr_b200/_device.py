@@ -269,6 +269,24 @@ def weighted_positions(idx3, dist3, target_points, point_base=None):
     return out
 
 
+def curvatures(points, tris):
+    """vtkCurvatures on the device (vtk_functions.py:40-74).  ``points`` (N, 3) f64, ``tris`` (F, 3) i32, host or
+    device.  Returns a dict of device tensors ``gauss``, ``mean``, ``minimum``, ``maximum``, each (N,)."""
+    torch = _torch()
+    lib = _lib.load()
+    pts = points if isinstance(points, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(points, dtype=np.float64))
+    tr = tris if isinstance(tris, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(tris, dtype=np.int32))
+    pts = pts.to(device="cuda", dtype=torch.float64).contiguous()
+    tr = tr.to(device="cuda", dtype=torch.int32).contiguous()
+    n, f = int(pts.shape[0]), int(tr.shape[0])
+    out = torch.empty((4, n), dtype=torch.float64, device=pts.device)
+    nbytes = int(lib.focusr_curvature_workspace_bytes(n, f))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=pts.device)
+    _lib.call("focusr_curvatures", _lib.ptr(pts), _lib.ptr(tr), n, f, _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]),
+              _lib.ptr(out[3]), _lib.ptr(ws), nbytes, _lib.stream_ptr())
+    return dict(gauss=out[0], mean=out[1], minimum=out[2], maximum=out[3])
+
+
 def eigsort_costs(graph, vecs, t_mesh, s_mesh, idx_t, idx_s, n_features):
     """Cost matrices of eigsort for pairs (t_mesh[p], s_mesh[p]) of ``graph``.
     idx_t / idx_s: host int arrays [n_pairs][n_samples] (Graph.rand_idxs).  Returns device tensors

@@ -8,9 +8,10 @@ numpy / scipy objects exactly as in the reference (eigsort mutates ``eig_vecs`` 
 
 Deliberate differences, all documented in DESIGN.md:
   * ``feature_weights=None`` is accepted (the reference raises AttributeError, graph.py:41-42);
-  * curvature features need VTK and the features-in-G option does not terminate in the reference
-    itself: they raise NotImplementedError instead of silently doing something else (mesh-scalar
-    features, features in the adjacency and features as coordinates ARE supported);
+  * curvature features (graph.py:11-15: vtkCurvatures min / max) are computed by the library's own
+    kernel (csrc/curvature.cu) instead of VTK; the features-in-G option does not terminate in the
+    reference itself and raises NotImplementedError (mesh-scalar and curvature features, features in
+    the adjacency and features as coordinates ARE supported);
   * eigenpairs come back in ascending order with a fixed sign convention (ARPACK's order is
     ascending up to near-ties and its sign is random).
 """
@@ -24,6 +25,38 @@ from ._device import DeviceGraph
 from .mesh import mesh_arrays
 
 __all__ = ["Graph", "recursive_eig"]
+
+
+def _curvature_arrays(vtk_mesh, names):
+    from . import _device
+
+    _lib.require_cuda()
+    pts, tris = mesh_arrays(vtk_mesh)
+    out = _device.curvatures(pts, tris)
+    return [out[n].cpu().numpy() for n in names]
+
+
+def get_min_max_curvature_values(vtk_mesh):
+    """vtk_functions.py:67-74 on the GPU: (minimum, maximum) principal curvature per vertex."""
+    return tuple(_curvature_arrays(vtk_mesh, ("minimum", "maximum")))
+
+
+def get_min_curvature(vtk_mesh):
+    """vtk_functions.py:59-64."""
+    return _curvature_arrays(vtk_mesh, ("minimum",))
+
+
+def get_max_curvature(vtk_mesh):
+    """vtk_functions.py:51-56."""
+    return _curvature_arrays(vtk_mesh, ("maximum",))
+
+
+# graph.py:11-15
+features_dictionary = {
+    "curvature": get_min_max_curvature_values,
+    "min_curvature": get_min_curvature,
+    "max_curvature": get_max_curvature,
+}
 
 
 class Graph(object):
@@ -76,11 +109,8 @@ class Graph(object):
 
         # graph.py:84-119: extra node features (outside the hot path; host-side only)
         self.node_features = []
-        if len(list_features_to_calc) > 0:
-            raise NotImplementedError(
-                "list_features_to_calc=%r needs vtkCurvatures (reference vtk_functions.py:40-74), which is "
-                "outside the B200 hot path; pass list_features_to_calc=[]" % (list_features_to_calc,)
-            )
+        for feature in list_features_to_calc:
+            self.node_features += list(features_dictionary[feature](self.vtk_mesh))
         for feature in list_features_to_get_from_mesh:
             pd = vtk_mesh.GetPointData()
             found = None
