@@ -272,6 +272,23 @@ int focusr_curvatures(const double* points, const int* tris, int n_points, int n
                       double* mean, double* k_min, double* k_max, void* workspace,
                       size_t workspace_bytes, focusr_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * K10  ICP pre-alignment (focusr.py:106-131 -> vtk_functions.py:12-37: vtkIterativeClosestPointTransform
+ * with a rigid-body (similarity = 0) or similarity landmark transform, closest points ON the target
+ * surface, StartByMatchingCentroids, exactly max_iterations landmark fits; landmarks = every
+ * (n_source / max_landmarks)-th source point).  VTK is an unpinned, absent dependency: the algorithm is
+ * VTK 9's as restated in oracle/icp_port.py.  matrix_out: device [16], row-major 4x4 acting on column
+ * vectors (vtkMatrix4x4 layout); transformed_out: device [n_source_points][3] = matrix * source (the
+ * `apply_transform` of vtk_functions.py:32-37); both nullable.  Target triangle ids must be in range
+ * (checked by focusr_laplacian_build on the same mesh).  Does not synchronise.
+ * ------------------------------------------------------------------------------------------- */
+size_t focusr_icp_workspace_bytes(int n_source_points, int max_landmarks);
+int focusr_icp(const double* target_points, int n_target_points, const int* target_tris,
+               int n_target_tris, const double* source_points, int n_source_points, int max_landmarks,
+               int max_iterations, int similarity, int start_by_matching_centroids,
+               double* matrix_out, double* transformed_out, void* workspace, size_t workspace_bytes,
+               focusr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -269,6 +269,30 @@ def weighted_positions(idx3, dist3, target_points, point_base=None):
     return out
 
 
+def icp(target_points, target_tris, source_points, max_iterations=100, max_landmarks=1000, similarity=False,
+        start_by_matching_centroids=True):
+    """vtkIterativeClosestPointTransform on the device (vtk_functions.py:12-37).  Returns ``(matrix, moved)``:
+    the accumulated 4x4 matrix (host numpy, acting on column vectors) and the transformed source points
+    (device tensor)."""
+    torch = _torch()
+    lib = _lib.load()
+
+    def dev(a, dt):
+        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+        return t.to(device="cuda", dtype=dt).contiguous()
+
+    tp, sp, tt = dev(target_points, torch.float64), dev(source_points, torch.float64), dev(target_tris, torch.int32)
+    ns = int(sp.shape[0])
+    mat = torch.empty(16, dtype=torch.float64, device=sp.device)
+    moved = torch.empty_like(sp)
+    nbytes = int(lib.focusr_icp_workspace_bytes(ns, int(max_landmarks)))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=sp.device)
+    _lib.call("focusr_icp", _lib.ptr(tp), int(tp.shape[0]), _lib.ptr(tt), int(tt.shape[0]), _lib.ptr(sp), ns,
+              int(max_landmarks), int(max_iterations), int(bool(similarity)), int(bool(start_by_matching_centroids)),
+              _lib.ptr(mat), _lib.ptr(moved), _lib.ptr(ws), nbytes, _lib.stream_ptr())
+    return mat.cpu().numpy().reshape(4, 4), moved
+
+
 def curvatures(points, tris):
     """vtkCurvatures on the device (vtk_functions.py:40-74).  ``points`` (N, 3) f64, ``tris`` (F, 3) i32, host or
     device.  Returns a dict of device tensors ``gauss``, ``mean``, ``minimum``, ``maximum``, each (N,)."""

@@ -4,7 +4,7 @@ Constructor signature, attribute names and method names follow the reference.  O
  the work runs in libfocusr_b200.so: both graphs' Laplacians and spectra,
 eigsort, KNN correspondences (focusr.py:351-366), the 300 + 40 smoothing passes and the second
 KNN (focusr.py:368-396), the k=3 weighted positions (focusr.py:401-426) and the nearest-neighbour
-gather (focusr.py:428-431).  ICP stays on VTK (imported lazily, ImportError when absent).  The extra
+gather (focusr.py:428-431), and the ICP pre-alignment of focusr.py:106-131 (csrc/icp.cu).  The extra
 keyword ``registration`` (after the reference's last argument) selects the CPD step of
 focusr.py:297-334: "b200" (default) runs affine + deformable Coherent Point Drift on the GPU
 (pyfocusr_b200.cpd, same call surface as cycpd); "cycpd" uses the reference's own dependency when it
@@ -30,33 +30,34 @@ def print_header(message, banner_length=72):
     print("=" * banner_length)
 
 
-def _icp_transform_vtk(target, source, transform_mode):
-    try:
-        import vtk  # type: ignore
-    except ImportError as e:  # pragma: no cover - VTK is not in this image
-        raise ImportError(
-            "icp_register_first=True needs VTK (reference vtk_functions.py:12-37); pass "
-            "icp_register_first=False for pre-aligned meshes"
-        ) from e
-    icp = vtk.vtkIterativeClosestPointTransform()
-    if transform_mode == "rigid":
-        icp.GetLandmarkTransform().SetModeToRigidBody()
-    elif transform_mode == "similarity":
-        icp.GetLandmarkTransform().SetModeToSimilarity()
-    else:
-        raise TypeError("Error invalid transform mode")
-    icp.SetTarget(target)
-    icp.SetSource(source)
-    icp.SetMaximumNumberOfIterations(100)
-    icp.StartByMatchingCentroidsOn()
-    icp.Modified()
-    icp.Update()
-    icp.SetMaximumNumberOfLandmarks(1000)
-    tf = vtk.vtkTransformPolyDataFilter()
-    tf.SetInputData(source)
-    tf.SetTransform(icp)
-    tf.Update()
-    return icp, tf.GetOutput()
+class IcpTransform(object):
+    """What ``vtk_functions.icp_transform`` returns, reduced to what the drop-in needs: the accumulated 4x4
+    matrix (``.matrix``; ``GetMatrix().GetElement(i, j)`` for code written against vtkTransform)."""
+
+    def __init__(self, matrix):
+        self.matrix = np.asarray(matrix, dtype=np.float64).reshape(4, 4)
+
+    def GetMatrix(self):
+        return self
+
+    def GetElement(self, i, j):
+        return float(self.matrix[i, j])
+
+
+def _icp_transform(target, source, transform_mode):
+    """vtk_functions.py:12-37 on the GPU (csrc/icp.cu): register ``source`` onto ``target``; returns the transform
+    and a copy of ``source`` moved by it.  100 iterations; 1000 landmarks -- the reference sets the landmark count
+    after its first Update(), and the re-run triggered by ``apply_transform`` is the one that counts."""
+    from .mesh import mesh_arrays
+
+    if transform_mode not in ("rigid", "similarity"):
+        raise TypeError("Error invalid transform mode")                       # vtk_functions.py:20-21 raises a str
+    _lib.require_cuda()
+    tp, tt = mesh_arrays(target)
+    sp, st = mesh_arrays(source)
+    mat, moved = _device.icp(tp, tt, sp, max_iterations=100, max_landmarks=1000, similarity=transform_mode == "similarity")
+    scalars = dict(getattr(source, "point_scalars", {}) or {})
+    return IcpTransform(mat), PolyData(moved.cpu().numpy(), np.array(st, copy=True), scalars)
 
 
 def _mesh_with_points(mesh, points):
@@ -156,12 +157,12 @@ class Focusr(object):
             if ctype != "kd":
                 raise ValueError("correspondence type must be 'kd' or 'hungarian'")
 
-        # focusr.py:110-131 (ICP stays on VTK)
+        # focusr.py:110-131 (vtkIterativeClosestPointTransform restated on the GPU: csrc/icp.cu)
         if icp_register_first is True:
             if icp_reg_target_to_source is True:
-                icp, vtk_mesh_target = _icp_transform_vtk(vtk_mesh_source, vtk_mesh_target, icp_registration_mode)
+                icp, vtk_mesh_target = _icp_transform(vtk_mesh_source, vtk_mesh_target, icp_registration_mode)
             else:
-                icp, vtk_mesh_source = _icp_transform_vtk(vtk_mesh_target, vtk_mesh_source, icp_registration_mode)
+                icp, vtk_mesh_source = _icp_transform(vtk_mesh_target, vtk_mesh_source, icp_registration_mode)
             self._icp_transform = icp
 
         graph_kwargs = dict(
