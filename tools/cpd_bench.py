@@ -68,6 +68,23 @@ def main():
         t2 = time.perf_counter()
         print("drop-in 15k pair with GPU CPD: ctor %.1f ms, align_maps %.1f ms, unique correspondences %d" %
               ((t1 - t0) * 1e3, (t2 - t1) * 1e3, len(np.unique(f.corresponding_target_idx_for_each_source_pt))))
+    # every default of the reference, ICP included (100 iterations, 1000 landmarks, closest points on 30k triangles)
+    from pyfocusr_b200 import _device
+
+    for rep in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _device.icp(mt.points, mt.tris, ms.points)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        np.random.seed(0)
+        f = pyfocusr.Focusr(mt, ms)
+        t2 = time.perf_counter()
+        f.align_maps()
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        print("ICP alone %.1f ms; Focusr(target, source) with all defaults: ctor %.1f ms + align_maps %.1f ms = %.1f ms" %
+              ((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (t3 - t1) * 1e3))
 
 
 if __name__ == "__main__":
