@@ -25,7 +25,10 @@ class SpectralBatch:
     def __init__(self, n_spectral_features=3, n_extra_spectral=3, n_coords_spectral_ordering=5000,
                  graph_smoothing_iterations=300, projection_smooth_iterations=40,
                  target_eigenmap_as_reference=True, get_weighted_spectral_coords=True, tol=1e-10,
-                 block_size=0, seed=0):
+                 block_size=0, seed=0, registration="identity", n_coords_spectral_registration=5000,
+                 rigid_before_non_rigid_reg=True, rigid_reg_max_iterations=100, rigid_tolerance=1e-8,
+                 non_rigid_max_iterations=1000, non_rigid_tolerance=1e-8, non_rigid_alpha=0.5, non_rigid_beta=3.0,
+                 non_rigid_n_eigens=100):
         self.ns = int(n_spectral_features)
         self.n = int(n_spectral_features + n_extra_spectral)
         self.n_samples = int(n_coords_spectral_ordering)
@@ -36,6 +39,17 @@ class SpectralBatch:
         self.tol = float(tol)
         self.block_size = int(block_size)
         self.seed = int(seed)
+        # focusr.py:297-334, 537-543: "identity" (BASELINE.json's throughput configuration) or "b200" = affine +
+        # deformable CPD on the GPU, one pair after the other (pyfocusr_b200.cpd; Focusr's keyword names)
+        if registration not in ("identity", "b200"):
+            raise ValueError("registration must be 'identity' or 'b200'")
+        self.registration = registration
+        self.n_coords_spectral_registration = int(n_coords_spectral_registration)
+        self.rigid_before_non_rigid_reg = bool(rigid_before_non_rigid_reg)
+        self.cpd_kwargs = dict(rigid_reg_max_iterations=rigid_reg_max_iterations, rigid_tolerance=rigid_tolerance,
+                               non_rigid_max_iterations=non_rigid_max_iterations, non_rigid_tolerance=non_rigid_tolerance,
+                               non_rigid_alpha=non_rigid_alpha, non_rigid_beta=non_rigid_beta,
+                               non_rigid_n_eigens=non_rigid_n_eigens)
         self.smooth_l2_bytes = 0  # > 0: smoothing runs group by group of meshes that fit L2 (see DeviceGraph.mean_filter)
         self.timings = {}
 
@@ -124,7 +138,11 @@ class SpectralBatch:
         ref_off = g.mesh_off[: P + 1].contiguous()
         qry_off = (g.mesh_off[P:] - nt_total).contiguous()
         max_q, max_r = int(sizes[P:].max()), int(sizes[:P].max())
-        # CPD would transform target coords here (out of scope; identity)
+        cpd_idx, coords_b4_reg = None, None
+        if self.registration == "b200":  # register every pair's target coordinates onto its source's
+            coords_b4_reg = coords.clone()
+            cpd_idx = self._register_pairs(coords, off, P, sizes)
+            mark("cpd")
         idx0, _ = _device.knn(coords[:nt_total], coords[nt_total:], k=1, ref_off=ref_off, query_off=qry_off,
                               max_queries=max_q, max_refs=max_r, want_dist=False)
         mark("knn_initial")
@@ -151,9 +169,46 @@ class SpectralBatch:
                     source_projected_on_target=src_proj[nt_total:], final_idx=idx1[:, 0], knn3_idx=idx3,
                     knn3_dist=dist3, weighted_avg_transformed_points=weighted,
                     nearest_neighbor_transformed_points=nearest, idx_t=idx_t, idx_s=idx_s, costs=costs,
-                    eig_vecs_presort=presort)
+                    eig_vecs_presort=presort, cpd_idx=cpd_idx, coords_b4_reg=coords_b4_reg)
 
     # ------------------------------------------------------------------------------------------
+    def _register_pairs(self, coords, off, P, sizes):
+        """focusr.py:537-543 per pair: affine on fresh random subsets, transform all target coordinates, then
+        deformable on fresh subsets, transform again.  Returns the index draws [(s_aff, t_aff, s_def, t_def)]."""
+        from .cpd import affine_registration, deformable_registration
+
+        torch = _lib.require_cuda()
+        rng = np.random.RandomState(self.seed + 7919)
+        kw, draws = self.cpd_kwargs, []
+
+        def draw(n):  # Graph.get_list_rand_idxs (graph.py:274-290)
+            if self.n_coords_spectral_registration > n:
+                return np.arange(n, dtype=np.int64)
+            return rng.choice(n, size=self.n_coords_spectral_registration, replace=False).astype(np.int64)
+
+        for p in range(P):
+            t0, t1, s0, s1 = int(off[p]), int(off[p + 1]), int(off[P + p]), int(off[P + p + 1])
+            tgt, src = coords[t0:t1], coords[s0:s1]
+            rec = []
+            stages = (["affine"] if self.rigid_before_non_rigid_reg else []) + ["deformable"]
+            for stage in stages:
+                i_s, i_t = draw(s1 - s0), draw(t1 - t0)   # source first, as the reference's dict literal evaluates
+                rec += [i_s, i_t]
+                x = src[torch.from_numpy(i_s).to(src.device)]
+                y = tgt[torch.from_numpy(i_t).to(tgt.device)]
+                if stage == "affine":
+                    reg = affine_registration(X=x, Y=y, max_iterations=kw["rigid_reg_max_iterations"],
+                                              tolerance=kw["rigid_tolerance"])
+                else:
+                    reg = deformable_registration(X=x, Y=y, num_eig=kw["non_rigid_n_eigens"],
+                                                  max_iterations=kw["non_rigid_max_iterations"],
+                                                  tolerance=kw["non_rigid_tolerance"], alpha=kw["non_rigid_alpha"],
+                                                  beta=kw["non_rigid_beta"])
+                reg.register()
+                tgt.copy_(reg.transform_point_cloud(tgt.contiguous()))
+            draws.append(tuple(rec))
+        return draws
+
     def fetch(self, out, keys=("final_idx", "weighted_avg_transformed_points")):
         """Device -> host read-back of the per-vertex results into reusable pinned buffers (one
         asynchronous copy each, then a single synchronisation).  Returns numpy views that stay valid

@@ -6,6 +6,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
+import pyfocusr_b200.mesh as fmesh
 from oracle import cpd_port as cp
 
 
@@ -220,3 +221,37 @@ def test_focusr_dropin_with_gpu_cpd(torch, shipped_meshes):
                                    mt.points, ms.points, f.target_spectral_coords, f.source_spectral_coords)
     assert np.array_equal(f.corresponding_target_idx_for_each_source_pt, cs["final_idx"])
     assert np.array_equal(f.weighted_avg_transformed_points, cs["weighted_avg_transformed_points"])
+
+
+@pytest.mark.gpu
+def test_batch_pipeline_with_gpu_cpd(torch):
+    """SpectralBatch(registration="b200"): every pair's target coordinates are registered (affine, then deformable,
+    fresh subsets each) before the correspondences; checked against the oracle CPD fed the batch's own draws."""
+    from oracle import port
+    from pyfocusr_b200 import SpectralBatch
+
+    t = [fmesh.perturbed_ellipsoid(9, 0), fmesh.perturbed_ellipsoid(9, 2)]
+    s = [fmesh.perturbed_ellipsoid(9, 1), fmesh.perturbed_ellipsoid(9, 3)]
+    sb = SpectralBatch(n_coords_spectral_ordering=500, graph_smoothing_iterations=20, projection_smooth_iterations=5,
+                       registration="b200", n_coords_spectral_registration=400, rigid_reg_max_iterations=10,
+                       rigid_tolerance=0.0, non_rigid_max_iterations=6, non_rigid_tolerance=0.0)
+    out = sb.run_meshes(t, s)
+    off = out["graph"].mesh_off_host
+    before, after = out["coords_b4_reg"].cpu().numpy(), out["coords"].cpu().numpy()
+    fin = out["final_idx"].cpu().numpy()
+    q0 = 0
+    for p in range(2):
+        tr, sr = slice(off[p], off[p + 1]), slice(off[2 + p], off[2 + p + 1])
+        i_s, i_t, i_s2, i_t2 = out["cpd_idx"][p]
+        ref_tc, _ = cp.register_target_to_source(before[tr], before[sr], i_t, i_s, rigid_max_iterations=10, rigid_tolerance=0.0,
+                                                 max_iterations=6, tolerance=0.0, alpha=0.5, beta=3.0, num_eig=100,
+                                                 idx_t2=i_t2, idx_s2=i_s2)
+        assert np.max(np.abs(after[tr] - ref_tc)) <= 1e-7
+        assert np.array_equal(after[sr], before[sr])                     # the source is never moved
+        cs = port.correspondence_stage(dict(A=port.adjacency(t[p].points, t[p].tris)), dict(A=port.adjacency(s[p].points, s[p].tris)),
+                                       t[p].points, s[p].points, after[tr], after[sr], 20, 5)
+        n_s = s[p].points.shape[0]
+        assert np.array_equal(fin[q0:q0 + n_s], cs["final_idx"])
+        q0 += n_s
+    with pytest.raises(ValueError):
+        SpectralBatch(registration="cycpd")
