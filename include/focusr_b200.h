@@ -282,7 +282,7 @@ int focusr_curvatures(const double* points, const int* tris, int n_points, int n
  * `apply_transform` of vtk_functions.py:32-37); both nullable.  Target triangle ids must be in range
  * (checked by focusr_laplacian_build on the same mesh).  Does not synchronise.
  * ------------------------------------------------------------------------------------------- */
-size_t focusr_icp_workspace_bytes(int n_source_points, int max_landmarks);
+size_t focusr_icp_workspace_bytes(int n_source_points, int n_target_tris);
 int focusr_icp(const double* target_points, int n_target_points, const int* target_tris,
                int n_target_tris, const double* source_points, int n_source_points, int max_landmarks,
                int max_iterations, int similarity, int start_by_matching_centroids,

@@ -285,7 +285,7 @@ def icp(target_points, target_tris, source_points, max_iterations=100, max_landm
     ns = int(sp.shape[0])
     mat = torch.empty(16, dtype=torch.float64, device=sp.device)
     moved = torch.empty_like(sp)
-    nbytes = int(lib.focusr_icp_workspace_bytes(ns, int(max_landmarks)))
+    nbytes = int(lib.focusr_icp_workspace_bytes(ns, int(tt.shape[0])))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=sp.device)
     _lib.call("focusr_icp", _lib.ptr(tp), int(tp.shape[0]), _lib.ptr(tt), int(tt.shape[0]), _lib.ptr(sp), ns,
               int(max_landmarks), int(max_iterations), int(bool(similarity)), int(bool(start_by_matching_centroids)),

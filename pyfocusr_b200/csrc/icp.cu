@@ -5,9 +5,10 @@
 //
 // Everything runs on the device with no synchronisation inside the loop: the accumulated 4x4 matrix, the
 // per-iteration landmark transform and the landmark positions live in HBM.
-//   k_icp_closest   closest point ON THE TARGET SURFACE for every landmark: brute force over all triangles
-//                   (Ericson's region test), 8 landmarks per CTA so that every triangle read is used 8 times;
-//                   ties between triangles go to the lower index; fixed-order argmin.
+//   k_icp_closest   closest point ON THE TARGET SURFACE for every landmark: exact scan over all triangles
+//                   (Ericson's region test) with bounding-sphere pruning seeded by the previous iteration's
+//                   winner, 8 landmarks per CTA so that every triangle read is used 8 times; ties between
+//                   triangles go to the lower index; fixed-order argmin.
 //   k_icp_fit       one CTA: centroids, M = sum a b^T, Horn's 4x4 matrix, its dominant eigenvector by cyclic
 //                   Jacobi in one thread, rotation (+ scale), translation; accumulated <- L * accumulated.
 //   k_icp_move      landmarks <- L landmarks.
@@ -100,14 +101,31 @@ __global__ void k_icp_init_landmarks(const double* __restrict__ src, int step, i
   a[3 * i + 2] = q.z;
 }
 
+// bounding sphere of every target triangle: centre = centroid, radius = largest vertex distance (+ 1 ulp-ish slack)
+__global__ void k_icp_spheres(const double* __restrict__ tp, const int* __restrict__ tris, int nf, double* __restrict__ sph) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nf) return;
+  const P3 a = p3(tp, tris[3 * (size_t)f]), b = p3(tp, tris[3 * (size_t)f + 1]), c = p3(tp, tris[3 * (size_t)f + 2]);
+  const P3 m = (a + b + c) * (1.0 / 3.0);
+  const P3 da = a - m, db = b - m, dc = c - m;
+  const double r2 = fmax(dot3(da, da), fmax(dot3(db, db), dot3(dc, dc)));
+  sph[4 * (size_t)f] = m.x;
+  sph[4 * (size_t)f + 1] = m.y;
+  sph[4 * (size_t)f + 2] = m.z;
+  sph[4 * (size_t)f + 3] = sqrt(r2) * (1.0 + 1e-12);
+}
+
+// Exact closest point with pruning: a triangle is skipped only when the distance to its bounding sphere is
+// STRICTLY larger than the best distance known (seeded, from the second iteration on, with the winner of the
+// previous iteration), so every triangle that attains the minimum is still evaluated and the lowest index wins.
 __global__ void __launch_bounds__(ICP_T)
 k_icp_closest(const double* __restrict__ a, int nb, const double* __restrict__ tp, const int* __restrict__ tris, int nf,
-              double* __restrict__ closest) {
+              const double* __restrict__ sph, int* __restrict__ winner, int have_prev, double* __restrict__ closest) {
   __shared__ double sd[ICP_LM][ICP_T];
   __shared__ int si[ICP_LM][ICP_T];
   const int l0 = blockIdx.x * ICP_LM, t = threadIdx.x;
   P3 lm[ICP_LM];
-  double best[ICP_LM];
+  double best[ICP_LM], bound[ICP_LM];
   int bi[ICP_LM];
 #pragma unroll
   for (int l = 0; l < ICP_LM; ++l) {
@@ -115,16 +133,35 @@ k_icp_closest(const double* __restrict__ a, int nb, const double* __restrict__ t
     lm[l] = p3(a, i);
     best[l] = INFINITY;
     bi[l] = 0x7fffffff;
+    bound[l] = INFINITY;
+    if (have_prev) {
+      const int f = winner[i];
+      const P3 d = lm[l] - closest_on_triangle(lm[l], p3(tp, tris[3 * (size_t)f]), p3(tp, tris[3 * (size_t)f + 1]), p3(tp, tris[3 * (size_t)f + 2]));
+      bound[l] = sqrt(dot3(d, d)) * (1.0 + 1e-12);  // the previous winner will be met again in the scan below
+    }
   }
   for (int f = t; f < nf; f += ICP_T) {
+    const P3 c = P3{sph[4 * (size_t)f], sph[4 * (size_t)f + 1], sph[4 * (size_t)f + 2]};
+    const double r = sph[4 * (size_t)f + 3];
+    bool any = false;
+    double gap[ICP_LM];
+#pragma unroll
+    for (int l = 0; l < ICP_LM; ++l) {
+      const P3 d = lm[l] - c;
+      gap[l] = sqrt(dot3(d, d)) - r;  // lower bound of the distance to the triangle
+      any = any || !(gap[l] > bound[l]);
+    }
+    if (!any) continue;
     const P3 va = p3(tp, tris[3 * (size_t)f]), vb = p3(tp, tris[3 * (size_t)f + 1]), vc = p3(tp, tris[3 * (size_t)f + 2]);
 #pragma unroll
     for (int l = 0; l < ICP_LM; ++l) {
+      if (gap[l] > bound[l]) continue;
       const P3 d = lm[l] - closest_on_triangle(lm[l], va, vb, vc);
       const double d2 = dot3(d, d);
       if (d2 < best[l]) {  // f ascends within a thread: the first minimum is the lowest index
         best[l] = d2;
         bi[l] = f;
+        bound[l] = fmin(bound[l], sqrt(d2) * (1.0 + 1e-12));
       }
     }
   }
@@ -155,6 +192,7 @@ k_icp_closest(const double* __restrict__ a, int nb, const double* __restrict__ t
     closest[3 * (l0 + t)] = c.x;
     closest[3 * (l0 + t) + 1] = c.y;
     closest[3 * (l0 + t) + 2] = c.z;
+    winner[l0 + t] = f;
   }
 }
 
@@ -291,12 +329,14 @@ using namespace fb;
 
 extern "C" {
 
-size_t focusr_icp_workspace_bytes(int n_source_points, int max_landmarks) {
-  if (n_source_points <= 0 || max_landmarks <= 0) return 0;
+size_t focusr_icp_workspace_bytes(int n_source_points, int n_target_tris) {
+  if (n_source_points <= 0 || n_target_tris <= 0) return 0;
   Carver cv(nullptr, 0);
   cv.take<double>(32);
   cv.take<double>((size_t)3 * n_source_points);
   cv.take<double>((size_t)3 * n_source_points);
+  cv.take<double>((size_t)4 * n_target_tris);
+  cv.take<int>((size_t)n_source_points);
   return cv.used + 256;
 }
 
@@ -307,7 +347,7 @@ int focusr_icp(const double* target_points, int n_target_points, const int* targ
   cudaStream_t stream = (cudaStream_t)stream_;
   FB_REQUIRE(n_target_points > 0 && n_target_tris > 0 && n_source_points > 0, "icp: empty mesh");
   FB_REQUIRE(max_landmarks > 0 && max_iterations >= 0, "icp: bad iteration or landmark count");
-  const size_t need = focusr_icp_workspace_bytes(n_source_points, max_landmarks);
+  const size_t need = focusr_icp_workspace_bytes(n_source_points, n_target_tris);
   if (need > workspace_bytes) {
     set_error("icp: workspace too small (%zu < %zu)", workspace_bytes, need);
     return FB_ERR_WORKSPACE;
@@ -316,6 +356,8 @@ int focusr_icp(const double* target_points, int n_target_points, const int* targ
   double* mats = cv.take<double>(32);  // acc[16], L[16]
   double* a = cv.take<double>((size_t)3 * n_source_points);
   double* cl = cv.take<double>((size_t)3 * n_source_points);
+  double* sph = cv.take<double>((size_t)4 * n_target_tris);
+  int* winner = cv.take<int>((size_t)n_source_points);
   double *acc = mats, *L = mats + 16;
   // vtkIterativeClosestPointTransform::InternalUpdate: every step-th source point is a landmark
   const int step = n_source_points > max_landmarks ? n_source_points / max_landmarks : 1;
@@ -323,9 +365,11 @@ int focusr_icp(const double* target_points, int n_target_points, const int* targ
   k_icp_start<<<1, 1024, 0, stream>>>(source_points, n_source_points, target_points, n_target_points,
                                       start_by_matching_centroids ? 1 : 0, acc);
   k_icp_init_landmarks<<<div_up(nb, 256), 256, 0, stream>>>(source_points, step, nb, acc, a);
-  FB_COUNT_LAUNCH(2);
+  k_icp_spheres<<<div_up(n_target_tris, 256), 256, 0, stream>>>(target_points, target_tris, n_target_tris, sph);
+  FB_COUNT_LAUNCH(3);
   for (int it = 0; it < max_iterations; ++it) {
-    k_icp_closest<<<div_up(nb, ICP_LM), ICP_T, 0, stream>>>(a, nb, target_points, target_tris, n_target_tris, cl);
+    k_icp_closest<<<div_up(nb, ICP_LM), ICP_T, 0, stream>>>(a, nb, target_points, target_tris, n_target_tris, sph, winner,
+                                                            it > 0 ? 1 : 0, cl);
     k_icp_fit<<<1, 256, 0, stream>>>(a, cl, nb, similarity ? 1 : 0, L, acc);
     FB_COUNT_LAUNCH(2);
     if (it + 1 >= max_iterations) break;
