@@ -217,6 +217,12 @@ int focusr_knn(const double* refs, int ld_refs, const int* ref_off, int n_refs_t
                long long* idx, double* dist, void* workspace, size_t workspace_bytes,
                focusr_stream_t stream);
 
+/* The distance matrix of the 'hungarian' correspondence (focusr.py:340-349: scipy cdist(spectral_pts,
+ * target_pts), euclidean): out [n_a][n_b] = |a_i - b_j|_2.  The assignment itself stays on the host in scipy's
+ * linear_sum_assignment, exactly as the reference calls it. */
+int focusr_cdist(const double* a, int n_a, const double* b, int n_b, int dim, double* out,
+                 focusr_stream_t stream);
+
 /* E3  get_weighted_final_node_locations (focusr.py:401-426) from the k=3 neighbours:
  * coincident neighbour -> its target point, else inverse-distance weighted mean of the three
  * target points.  idx3 is local to the segment of `target_points` starting at point_base[i]

@@ -56,6 +56,7 @@ SIGNATURES = {
                                   _vp, _sz, _vp]),
     "focusr_knn_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "focusr_knn": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "focusr_cdist": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp]),
     "focusr_weighted_positions": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "focusr_curvature_workspace_bytes": (_sz, [_i, _i]),
     "focusr_curvatures": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

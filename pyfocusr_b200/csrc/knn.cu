@@ -158,9 +158,36 @@ __global__ void k_weighted_positions(const long long* __restrict__ idx3, const d
 
 }  // namespace fb
 
+namespace fb {
+// out[q][r] = sqrt(sum_d (a_q[d] - b_r[d])^2), sequential sum without FMA (scipy cdist's arithmetic)
+__global__ void k_cdist(const double* __restrict__ a, int na, const double* __restrict__ b, int nb, int dim, double* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x, q = blockIdx.y;
+  if (r >= nb) return;
+  const double* pa = a + (size_t)q * dim;
+  const double* pb = b + (size_t)r * dim;
+  const double d0 = FB_SUB(pa[0], pb[0]);
+  double s = FB_MUL(d0, d0);
+  for (int c = 1; c < dim; ++c) {
+    const double d = FB_SUB(pa[c], pb[c]);
+    s = FB_ADD(s, FB_MUL(d, d));
+  }
+  out[(size_t)q * nb + r] = sqrt(s);
+}
+}  // namespace fb
+
 using namespace fb;
 
 extern "C" {
+
+int focusr_cdist(const double* a, int n_a, const double* b, int n_b, int dim, double* out, focusr_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  FB_REQUIRE(n_a > 0 && n_b > 0 && dim > 0 && n_a <= 65535, "cdist: bad sizes (at most 65535 rows)");
+  dim3 grid(div_up(n_b, 256), n_a);
+  k_cdist<<<grid, 256, 0, stream>>>(a, n_a, b, n_b, dim, out);
+  FB_COUNT_LAUNCH(1);
+  FB_LAUNCH_CHECK();
+  return FB_OK;
+}
 
 size_t focusr_knn_workspace_bytes(int n_refs_total, int n_queries_total, int n_segments, int dim) {
   return knn_pruned_workspace_bytes(n_refs_total, n_queries_total, n_segments, dim);

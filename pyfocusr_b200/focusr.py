@@ -150,11 +150,7 @@ class Focusr(object):
         self.final_correspondence_type = final_correspondence_type
         self.return_transformed_mesh = return_transformed_mesh
         for ctype in (initial_correspondence_type, final_correspondence_type):
-            if ctype == "hungarian":
-                raise NotImplementedError(
-                    "the O(N^3) 'hungarian' correspondence (focusr.py:340-349) is outside the B200 hot path; use 'kd'"
-                )
-            if ctype != "kd":
+            if ctype not in ("kd", "hungarian"):
                 raise ValueError("correspondence type must be 'kd' or 'hungarian'")
 
         # focusr.py:110-131 (vtkIterativeClosestPointTransform restated on the GPU: csrc/icp.cu)
@@ -272,7 +268,18 @@ class Focusr(object):
 
     # ------------------------------------------------------------------ focusr.py:340-366
     def get_hungarian_correspondence(self, target_pts, spectral_pts):
-        raise NotImplementedError("'hungarian' correspondence is outside the B200 hot path")
+        """focusr.py:340-349: the N x N distance matrix on the GPU, then scipy's linear_sum_assignment on the host
+        exactly as the reference calls it (an O(N^3) third-party solve; minutes at 15k vertices there too)."""
+        from scipy.optimize import linear_sum_assignment
+
+        torch = _lib.require_cuda()
+        a = torch.from_numpy(np.ascontiguousarray(spectral_pts, dtype=np.float64)).cuda()
+        b = torch.from_numpy(np.ascontiguousarray(target_pts, dtype=np.float64)).cuda()
+        dist = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float64, device=a.device)
+        _lib.call("focusr_cdist", _lib.ptr(a), int(a.shape[0]), _lib.ptr(b), int(b.shape[0]), int(a.shape[1]),
+                  _lib.ptr(dist), _lib.stream_ptr())
+        _, target_idx = linear_sum_assignment(dist.cpu().numpy())
+        self.corresponding_target_idx_for_each_source_pt = target_idx
 
     def get_kd_correspondence(self, target_pts, spectral_pts):
         torch = _lib.require_cuda()
@@ -282,7 +289,10 @@ class Focusr(object):
         self.corresponding_target_idx_for_each_source_pt = idx[:, 0].cpu().numpy()
 
     def get_initial_correspondences(self):
-        self.get_kd_correspondence(self.target_spectral_coords, self.source_spectral_coords)
+        if self.initial_correspondence_type == "kd":
+            self.get_kd_correspondence(self.target_spectral_coords, self.source_spectral_coords)
+        elif self.initial_correspondence_type == "hungarian":
+            self.get_hungarian_correspondence(self.target_spectral_coords, self.source_spectral_coords)
 
     # ------------------------------------------------------------------ focusr.py:368-396
     def get_smoothed_correspondences(self):
@@ -291,7 +301,10 @@ class Focusr(object):
         self.source_projected_on_target = self.graph_source.mean_filter_graph(
             self.smoothed_target_coords[self.corresponding_target_idx_for_each_source_pt, :],
             iterations=self.projection_smooth_iterations)
-        self.get_kd_correspondence(self.smoothed_target_coords, self.source_projected_on_target)
+        if self.final_correspondence_type == "kd":
+            self.get_kd_correspondence(self.smoothed_target_coords, self.source_projected_on_target)
+        elif self.final_correspondence_type == "hungarian":
+            self.get_hungarian_correspondence(self.smoothed_target_coords, self.source_projected_on_target)
 
     # ------------------------------------------------------------------ focusr.py:401-431
     def get_weighted_final_node_locations(self, n_closest_pts=3):

@@ -654,3 +654,35 @@ def test_error_behaviour_and_degenerate_inputs(torch):
     assert torch.all(idx[:, 2] == -1) and torch.all(torch.isinf(dist[:, 2])) and torch.all(idx[:, :2] >= 0)
     with pytest.raises(FocusrB200Error):
         _device.knn(refs, qs, k=9)
+
+
+def test_hungarian_correspondence(torch, synth):
+    """focusr.py:340-349: cdist on the GPU bit-equal to scipy's, assignment by the same scipy call as the reference."""
+    import pyfocusr_b200 as pyfocusr
+    from scipy.optimize import linear_sum_assignment
+    from scipy.spatial.distance import cdist
+
+    from pyfocusr_b200 import _lib
+
+    rng = np.random.RandomState(0)
+    for na, nb, d in ((300, 300, 3), (257, 400, 6), (50, 31, 13)):
+        a, b = rng.rand(na, d), rng.rand(nb, d)
+        ad, bd = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+        out = torch.empty((na, nb), dtype=torch.float64, device="cuda")
+        _lib.call("focusr_cdist", _lib.ptr(ad), na, _lib.ptr(bd), nb, d, _lib.ptr(out), _lib.stream_ptr())
+        ref = cdist(a, b)
+        got = out.cpu().numpy()
+        assert np.max(np.abs(got - ref)) <= 4e-16 * np.max(ref)          # same formula; scipy's build may contract an FMA
+        assert np.array_equal(linear_sum_assignment(got)[1], linear_sum_assignment(ref)[1])
+    t, s = synth["ell20a"], synth["ell20b"]
+    np.random.seed(0)
+    f = pyfocusr.Focusr(t, s, icp_register_first=False, list_features_to_calc=[], registration="identity",
+                        initial_correspondence_type="hungarian", final_correspondence_type="hungarian",
+                        n_coords_spectral_ordering=1000, graph_smoothing_iterations=20, projection_smooth_iterations=5)
+    f.align_maps()
+    idx = f.corresponding_target_idx_for_each_source_pt
+    assert idx.shape == (s.points.shape[0],) and len(np.unique(idx)) == idx.size      # a one-to-one assignment
+    _, ref_idx = linear_sum_assignment(cdist(f.source_projected_on_target, f.smoothed_target_coords))
+    assert np.array_equal(idx, ref_idx)
+    with pytest.raises(ValueError):
+        pyfocusr.Focusr(t, s, icp_register_first=False, initial_correspondence_type="nearest")
