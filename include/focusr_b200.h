@@ -71,6 +71,17 @@ int focusr_mean_filter(const int* row_ptr, const int* cols, const double* weight
                        double* values_out, double* scratch, int n_cols, int iterations,
                        focusr_stream_t stream);
 
+/* K5, persistent form: the same smoothing for whole meshes [mesh_begin, mesh_end) of the batch graph with
+ * every mesh owned by one 16-CTA thread-block cluster for ALL `iterations` passes (vector and matrix slices in
+ * distributed shared memory; one launch, no global traffic inside the loop).  Bit-identical to
+ * focusr_mean_filter; measured about as fast (csrc/smooth_cluster.cu has the numbers), so optional.  n_cols 1 or 3; values_in / values_out indexed by global row, values_in not modified.
+ * Returns 103 (unsupported) when the form does not apply (other n_cols, meshes too large for shared memory,
+ * cluster size unavailable): call focusr_mean_filter instead. */
+int focusr_mean_filter_meshes(const int* row_ptr, const int* cols, const double* weights,
+                              const double* degree, const int* mesh_point_off, int mesh_begin,
+                              int mesh_end, int max_mesh_points, const double* values_in,
+                              double* values_out, int n_cols, int iterations, focusr_stream_t stream);
+
 /* out[i][:] = in[idx[i]][:]  (focusr.py:387 `smoothed_target_coords[corresponding_idx, :]`;
  * focusr.py:429-431 nearest-neighbour positions).  `idx_base[i]` (nullable) is added to idx[i]. */
 int focusr_gather_rows(const double* in, const long long* idx, const int* idx_base, int n_rows,
@@ -151,6 +162,7 @@ void focusr_profile_reset(void);
 void focusr_profile_get(double* out4_host);
 
 /* Tuning knobs (experiments and A/B profiling; see the tuning records in csrc/spmm.cu, csrc/eigs.cu).
+ * key 2: variant of the persistent cluster smoothing kernel (0..3: threads x gather batch).
  * key 0: filter-step kernel (0 = register-capped gather kernel, 1 = TMA bulk-staged y window in
  * shared memory, b <= 32);  key 1: L2 budget in MB for blocking the filter over mesh groups (0 = off). */
 int focusr_set_tuning(int key, int value);

@@ -191,14 +191,29 @@ class DeviceGraph:
         return out
 
     # --- K5 -----------------------------------------------------------------------------------
-    def mean_filter(self, values, iterations, row_begin=0, row_end=None, l2_group_bytes=0):
+    def mean_filter(self, values, iterations, row_begin=0, row_end=None, l2_group_bytes=0, cluster=False):
         """values: device [n_points][c] (rows outside the range are ignored).  Returns a new tensor.
-        ``l2_group_bytes`` > 0 runs all iterations on one group of whole meshes after the other, each
-        group's matrix + vectors sized to stay resident in L2 (126 MB on B200)."""
+        One launch per pass by default.  ``cluster=True``: when the range covers whole meshes and c is 1 or 3, every
+        mesh runs all its passes inside one thread-block cluster (``focusr_mean_filter_meshes``: one launch,
+        distributed shared memory; bit-identical; measured no faster, see csrc/smooth_cluster.cu).  ``l2_group_bytes`` > 0 (per-pass form only) runs all iterations on one group of
+        whole meshes after the other, each group sized to stay resident in L2 (126 MB on B200)."""
         torch = _torch()
         row_end = self.n_points if row_end is None else row_end
         c = int(values.shape[1])
         out = torch.empty_like(values)
+        if cluster and c in (1, 3) and iterations >= 1 and not l2_group_bytes:
+            off = self.mesh_off_host
+            mb, me = int(np.searchsorted(off, row_begin)), int(np.searchsorted(off, row_end))
+            if mb < me <= self.n_meshes and off[mb] == row_begin and off[me] == row_end:
+                lib = _lib.load()
+                rc = lib.focusr_mean_filter_meshes(_lib.ptr(self.row_ptr), _lib.ptr(self.cols), _lib.ptr(self.weights),
+                                                   _lib.ptr(self.degree), _lib.ptr(self.mesh_off), mb, me,
+                                                   int(np.max(np.diff(off[mb:me + 1]))), _lib.ptr(values), _lib.ptr(out),
+                                                   c, int(iterations), _lib.stream_ptr())
+                if rc == 0:
+                    return out
+                if rc != 103:  # 103 = the cluster form does not apply here; anything else is an error
+                    raise _lib.FocusrB200Error("focusr_mean_filter_meshes", rc, lib.focusr_last_error().decode("utf-8", "replace"))
         scratch = torch.empty_like(values)
         ranges = [(int(row_begin), int(row_end))]
         if l2_group_bytes and iterations > 1:

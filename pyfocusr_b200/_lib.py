@@ -28,6 +28,7 @@ SIGNATURES = {
     "focusr_laplacian_build": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "focusr_laplacian_csr": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "focusr_mean_filter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
+    "focusr_mean_filter_meshes": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
     "focusr_gather_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "focusr_eigs_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "focusr_eigs_block_size": (_i, [_i, _i, _i, _i, _i]),

@@ -498,6 +498,10 @@ int focusr_set_tuning(int key, int value) {
     fb::g_l2_budget_mb = value;
     return 0;
   }
+  if (key == 2) {
+    fb::g_smooth_variant = value;
+    return 0;
+  }
   fb::set_error("set_tuning: unknown key %d", key);
   return fb::FB_ERR_ARG;
 }

@@ -19,6 +19,7 @@ bool spmm_block_supported(int b);
 
 // focusr_set_tuning(1, MB): L2 budget for blocking the filter over groups of meshes (0 = off)
 extern int g_l2_budget_mb;
+extern int g_smooth_variant;  // smooth_cluster.cu
 
 // mode 0: out = alpha[mesh][step] * (L y - center[mesh] y) - gamma[mesh][step] * x_prev
 // mode 1: out = (D - A) y          mode 2: out = L y

@@ -686,3 +686,29 @@ def test_hungarian_correspondence(torch, synth):
     assert np.array_equal(idx, ref_idx)
     with pytest.raises(ValueError):
         pyfocusr.Focusr(t, s, icp_register_first=False, initial_correspondence_type="nearest")
+
+
+def test_cluster_smoothing_is_bit_identical(torch, shipped_meshes, synth):
+    """focusr_mean_filter_meshes (all passes of a mesh inside one thread-block cluster, distributed shared memory)
+    against the one-launch-per-pass kernel: bit-identical, for 1 and 3 columns, mixed mesh sizes, sub-ranges of the
+    batch, an isolated vertex, and odd / even / single iteration counts."""
+    from pyfocusr_b200._device import DeviceGraph
+    from pyfocusr_b200.mesh import icosphere
+
+    small = icosphere(3)
+    pts = np.concatenate([small.points, [[9.0, 9.0, 9.0]]])                    # unreferenced vertex: empty row
+    ms = [shipped_meshes["source_mesh_15k"], synth["ell20a"], shipped_meshes["target_mesh"], synth["ell39"]]
+    g = DeviceGraph([m.points for m in ms] + [pts], [m.tris for m in ms] + [small.tris])
+    off = g.mesh_off_host
+    rng = np.random.RandomState(0)
+    for c in (3, 1):
+        x = torch.from_numpy(rng.standard_normal((g.n_points, c))).cuda()
+        for iters, (mb, me) in ((1, (0, 5)), (2, (1, 3)), (7, (0, 5)), (40, (2, 5)), (301, (3, 4))):
+            r0, r1 = int(off[mb]), int(off[me])
+            a = g.mean_filter(x, iters, r0, r1, cluster=True)
+            b = g.mean_filter(x, iters, r0, r1, cluster=False)
+            assert torch.equal(a[r0:r1], b[r0:r1]), (c, iters, mb, me)
+    # a range that is not made of whole meshes silently takes the per-pass path
+    a = g.mean_filter(x, 3, 10, 5000, cluster=True)
+    b = g.mean_filter(x, 3, 10, 5000, cluster=False)
+    assert torch.equal(a[10:5000], b[10:5000])
