@@ -244,6 +244,8 @@ def run_ours(a):
     secondary = {"spmv_filter_hbm_gbs": achieved,
                  "knn_queries_per_s": {"initial_k1_d3": knn_q / (stages["knn_initial"] / 1e3) if stages.get("knn_initial") else None,
                                        "final_k3_d3": knn_q / (stages["knn_final"] / 1e3) if stages.get("knn_final") else None}}
+    if world == 1 and not a.no_cpu_baseline:
+        secondary["widened_rows_ms"] = widened_rows_timing(a.nu)
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
         t0 = time.perf_counter()
@@ -261,6 +263,52 @@ def run_ours(a):
     print(json.dumps(line))
     fdist.finalize()
     return 0
+
+
+def widened_rows_timing(nu):
+    """SURVEY.md section 8f rows, outside the timed region (N = 1 only): one CPD registration at the reference's
+    default sizes on the spectral-coordinate-like synthetic problem of tools/cpd_bench.py, ICP and curvatures on one
+    synthetic pair.  Wall-clock with device synchronisation, second run of each (the first warms the allocator)."""
+    import torch
+
+    from pyfocusr_b200 import _device
+    from pyfocusr_b200.cpd import affine_registration, deformable_registration
+    from pyfocusr_b200.mesh import ellipsoid_pair
+    from tools.cpd_bench import problem
+
+    def timed(fn):
+        out = None
+        for _ in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = fn()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) * 1e3
+        return dt, out
+
+    x, y = problem(0, 5000, 5000, 3)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    res = {}
+
+    def run_affine():
+        reg = affine_registration(X=xd, Y=yd, max_iterations=100, tolerance=1e-8)
+        reg.register()
+        return reg
+
+    res["cpd_affine_5000x5000"], aff = timed(run_affine)
+    ty = aff.transform_point_cloud(yd)
+
+    def run_def():
+        reg = deformable_registration(X=xd, Y=ty, max_iterations=1000, tolerance=1e-8, alpha=0.5, beta=3.0, num_eig=100)
+        reg.register()
+        return reg
+
+    res["cpd_deformable_5000x5000_num_eig100"], dreg = timed(run_def)
+    res["cpd_iterations"] = [int(aff.iteration), int(dreg.iteration)]
+    t, s_ = ellipsoid_pair(0, nu)
+    res["icp_100it_1000_landmarks"], _ = timed(lambda: _device.icp(t.points, t.tris, s_.points))
+    res["curvatures_one_mesh"], _ = timed(lambda: _device.curvatures(t.points, t.tris))
+    return res
 
 
 def main():
