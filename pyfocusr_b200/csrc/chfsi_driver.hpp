@@ -285,7 +285,8 @@ int chfsi_solve(BE& be, const SolveParams& p, MeshResult* out) {
       be.rr_sym();
     } else {
       be.get_GH(gh.data(), gh.data() + (size_t)M * B * B);
-      // the meshes' small eigenproblems are independent: one host thread each (OpenMP when compiled in)
+      // the meshes' small eigenproblems are independent: one host thread each (OpenMP when compiled in) -- from 8
+      // meshes up only: for a single pair the team start-up costs more than it saves (Focusr() 38 -> 79 ms measured)
       std::vector<int> rr_rc(M, 0);
 #if defined(_OPENMP)
 #pragma omp parallel for schedule(dynamic) if (M >= 8) num_threads(M < 64 ? M : 64)
