@@ -28,7 +28,7 @@ class SpectralBatch:
                  block_size=0, seed=0, registration="identity", n_coords_spectral_registration=5000,
                  rigid_before_non_rigid_reg=True, rigid_reg_max_iterations=100, rigid_tolerance=1e-8,
                  non_rigid_max_iterations=1000, non_rigid_tolerance=1e-8, non_rigid_alpha=0.5, non_rigid_beta=3.0,
-                 non_rigid_n_eigens=100):
+                 non_rigid_n_eigens=100, cpd_streams=8):
         self.ns = int(n_spectral_features)
         self.n = int(n_spectral_features + n_extra_spectral)
         self.n_samples = int(n_coords_spectral_ordering)
@@ -46,6 +46,7 @@ class SpectralBatch:
         self.registration = registration
         self.n_coords_spectral_registration = int(n_coords_spectral_registration)
         self.rigid_before_non_rigid_reg = bool(rigid_before_non_rigid_reg)
+        self.cpd_streams = max(1, int(cpd_streams))
         self.cpd_kwargs = dict(rigid_reg_max_iterations=rigid_reg_max_iterations, rigid_tolerance=rigid_tolerance,
                                non_rigid_max_iterations=non_rigid_max_iterations, non_rigid_tolerance=non_rigid_tolerance,
                                non_rigid_alpha=non_rigid_alpha, non_rigid_beta=non_rigid_beta,
@@ -174,39 +175,69 @@ class SpectralBatch:
     # ------------------------------------------------------------------------------------------
     def _register_pairs(self, coords, off, P, sizes):
         """focusr.py:537-543 per pair: affine on fresh random subsets, transform all target coordinates, then
-        deformable on fresh subsets, transform again.  Returns the index draws [(s_aff, t_aff, s_def, t_def)]."""
+        deformable on fresh subsets, transform again.  Returns the index draws [(s_aff, t_aff, s_def, t_def)].
+
+        The pairs are independent, and one registration leaves most of the GPU idle during its latency-bound
+        steps (the r x r solve, the host Rayleigh-Ritz of the low-rank set-up), so ``cpd_streams`` host threads
+        run registrations concurrently, one CUDA stream each (ctypes releases the GIL inside the library).  All
+        random draws are made up front in pair order: the result does not depend on the thread schedule."""
+        from concurrent.futures import ThreadPoolExecutor
+
         from .cpd import affine_registration, deformable_registration
 
         torch = _lib.require_cuda()
         rng = np.random.RandomState(self.seed + 7919)
-        kw, draws = self.cpd_kwargs, []
+        kw = self.cpd_kwargs
+        stages = (["affine"] if self.rigid_before_non_rigid_reg else []) + ["deformable"]
 
         def draw(n):  # Graph.get_list_rand_idxs (graph.py:274-290)
             if self.n_coords_spectral_registration > n:
                 return np.arange(n, dtype=np.int64)
             return rng.choice(n, size=self.n_coords_spectral_registration, replace=False).astype(np.int64)
 
+        draws = []
         for p in range(P):
-            t0, t1, s0, s1 = int(off[p]), int(off[p + 1]), int(off[P + p]), int(off[P + p + 1])
-            tgt, src = coords[t0:t1], coords[s0:s1]
+            nt, ns = int(off[p + 1] - off[p]), int(off[P + p + 1] - off[P + p])
             rec = []
-            stages = (["affine"] if self.rigid_before_non_rigid_reg else []) + ["deformable"]
-            for stage in stages:
-                i_s, i_t = draw(s1 - s0), draw(t1 - t0)   # source first, as the reference's dict literal evaluates
-                rec += [i_s, i_t]
-                x = src[torch.from_numpy(i_s).to(src.device)]
-                y = tgt[torch.from_numpy(i_t).to(tgt.device)]
-                if stage == "affine":
-                    reg = affine_registration(X=x, Y=y, max_iterations=kw["rigid_reg_max_iterations"],
-                                              tolerance=kw["rigid_tolerance"])
-                else:
-                    reg = deformable_registration(X=x, Y=y, num_eig=kw["non_rigid_n_eigens"],
-                                                  max_iterations=kw["non_rigid_max_iterations"],
-                                                  tolerance=kw["non_rigid_tolerance"], alpha=kw["non_rigid_alpha"],
-                                                  beta=kw["non_rigid_beta"])
-                reg.register()
-                tgt.copy_(reg.transform_point_cloud(tgt.contiguous()))
+            for _ in stages:
+                rec += [draw(ns), draw(nt)]   # source first, as the reference's dict literal evaluates
             draws.append(tuple(rec))
+
+        main = torch.cuda.current_stream()
+        device = coords.device
+
+        def work(pairs):
+            st = torch.cuda.Stream(device=device)
+            st.wait_stream(main)
+            with torch.cuda.device(device), torch.cuda.stream(st):
+                for p in pairs:
+                    t0, t1, s0, s1 = int(off[p]), int(off[p + 1]), int(off[P + p]), int(off[P + p + 1])
+                    tgt, src = coords[t0:t1], coords[s0:s1]
+                    for k, stage in enumerate(stages):
+                        i_s, i_t = draws[p][2 * k], draws[p][2 * k + 1]
+                        x = src[torch.from_numpy(i_s).to(device)]
+                        y = tgt[torch.from_numpy(i_t).to(device)]
+                        if stage == "affine":
+                            reg = affine_registration(X=x, Y=y, max_iterations=kw["rigid_reg_max_iterations"],
+                                                      tolerance=kw["rigid_tolerance"])
+                        else:
+                            reg = deformable_registration(X=x, Y=y, num_eig=kw["non_rigid_n_eigens"],
+                                                          max_iterations=kw["non_rigid_max_iterations"],
+                                                          tolerance=kw["non_rigid_tolerance"], alpha=kw["non_rigid_alpha"],
+                                                          beta=kw["non_rigid_beta"])
+                        reg.register()
+                        tgt.copy_(reg.transform_point_cloud(tgt.contiguous()))
+            st.synchronize()
+            return st
+
+        n_workers = min(self.cpd_streams, P)
+        chunks = [list(range(w, P, n_workers)) for w in range(n_workers)]
+        if n_workers == 1:
+            work(chunks[0])
+        else:
+            with ThreadPoolExecutor(max_workers=n_workers) as pool:
+                for st in pool.map(work, chunks):
+                    main.wait_stream(st)
         return draws
 
     def fetch(self, out, keys=("final_idx", "weighted_avg_transformed_points")):

@@ -1,6 +1,8 @@
 // Shared plumbing of libfocusr_b200.so: error reporting, launch checks, small device helpers.
 #pragma once
 #include <cuda_runtime.h>
+
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -64,8 +66,9 @@ struct Carver {
 
 inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-// number of launches issued by this library since load (bench.py reports it as gpu_launches)
-extern unsigned long long g_launch_count;
+// number of launches issued by this library since load (bench.py reports it as gpu_launches); atomic because
+// independent calls may come from several host threads (one stream each), as the batched CPD does
+extern std::atomic<unsigned long long> g_launch_count;
 #define FB_COUNT_LAUNCH(n) (fb::g_launch_count += (unsigned long long)(n))
 
 // exclusive prefix sum of int32 (out[n] = total); tmp needs scan_tmp_ints(n) ints

@@ -8,13 +8,15 @@
 // in the edge weight, sequential ascending-column degree sums.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "rowops.h"
 
 namespace fb {
 
 static thread_local char g_err[512] = "";
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -331,7 +333,7 @@ extern "C" {
 
 const char* focusr_last_error(void) { return fb::g_err; }
 int focusr_version(void) { return 100; }
-unsigned long long focusr_launch_count(void) { return fb::g_launch_count; }
+unsigned long long focusr_launch_count(void) { return fb::g_launch_count.load(); }
 
 size_t focusr_laplacian_workspace_bytes(int n_points, int n_tris) {
   size_t b = 0;
