@@ -119,3 +119,71 @@ def test_row_partitioned_multi_gpu_under_torchrun():
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert line["status"] == 0 and line["n_found"] == 10 and line["max_residual_global"] <= 1e-9
+
+
+def test_batch_pipeline_full_size_properties():
+    """configs[2] at bench size per step (64 pairs = 128 meshes of 15 212 vertices in one batch): the oracle cannot
+    follow at this size, so the batch is checked through size-independent properties of every stage and against
+    the oracle / a stand-alone run on a few of its pairs."""
+    import torch
+
+    import bench
+    from oracle import port
+    from pyfocusr_b200 import SpectralBatch, _device
+
+    P = 64
+    pts, tris, off, n, f, base = bench.make_pairs(list(range(P)))
+    sb = SpectralBatch()
+    out = sb.run(torch.from_numpy(pts).cuda(), torch.from_numpy(tris).cuda(), off, P, keep_presort=True)
+    g, info = out["graph"], out["eigs_info"]
+    # K2: every mesh converged, eigenvalues ascending and positive, residuals below the solver's tolerance
+    assert np.all(info["status"] == 0) and np.all(info["n_found"] == 6) and np.all(info["symmetric"] == 1)
+    assert info["max_residual"].max() <= 1e-10
+    vals = out["eig_vals"].cpu().numpy()[:, :6]
+    assert np.all(vals > 1e-10) and np.all(np.diff(vals, axis=1) >= 0)
+    assert np.all(info["spectrum_bound"] < 1.7) and np.all(info["spectrum_bound"] > 1.5)   # probed, not Gershgorin's 2
+    # ... and the constant vector is in the null space of every Laplacian: L 1 = 0 to rounding
+    ones = torch.ones((g.n_points, 8), dtype=torch.float64, device="cuda")
+    assert float(g.laplacian_apply(ones).abs().max()) <= 1e-13
+    # three meshes against the oracle's scipy solve (BASELINE.json tolerance)
+    pre = out["eig_vecs_presort"].cpu().numpy()
+    for m in (0, 63, 100):
+        p_m = pts[off[m]:off[m + 1]]
+        rv, _ = port.recursive_eig(port.laplacian(port.adjacency(p_m, base.tris)), 7, 6, 1)
+        assert np.max(np.abs(vals[m] - np.sort(rv)) / np.sort(rv)) <= 1e-6
+    # K5: a smoothing pass is a convex combination -> the smoothed coordinates stay inside each mesh's bounding box
+    sm = out["smoothed_target_coords"].cpu().numpy()
+    for m in range(0, P, 7):
+        lo, hi = pts[off[m]:off[m + 1]].min(0), pts[off[m]:off[m + 1]].max(0)
+        s_m = sm[off[m]:off[m + 1]]
+        assert np.all(s_m >= lo - 1e-9) and np.all(s_m <= hi + 1e-9)
+    # K4: the pruned search is bit-identical to brute force at full size, and its answers are true nearest neighbours
+    nt = int(off[P])
+    smoothed, proj = out["smoothed_target_coords"], out["source_projected_on_target"]
+    ref_off = g.mesh_off[: P + 1].contiguous()
+    qry_off = (g.mesh_off[P:] - nt).contiguous()
+    kw = dict(k=1, ref_off=ref_off, query_off=qry_off, max_queries=n, max_refs=n)
+    i_p, d_p = _device.knn(smoothed, proj, **kw)
+    i_b, d_b = _device.knn(smoothed, proj, brute_force=True, **kw)
+    assert torch.equal(i_p, i_b) and torch.equal(d_p, d_b)
+    assert torch.equal(i_p[:, 0], out["final_idx"])
+    fin = out["final_idx"].cpu().numpy()
+    assert fin.min() >= 0 and fin.max() < n
+    rng = np.random.RandomState(0)
+    sm_h, pr_h = smoothed.cpu().numpy(), proj.cpu().numpy()
+    for p in (0, 31, 63):
+        q = rng.choice(n, 200, replace=False)
+        d_all = np.linalg.norm(sm_h[off[p]:off[p + 1]][None, :, :] - pr_h[p * n:(p + 1) * n][q][:, None, :], axis=2)
+        assert np.array_equal(np.argmin(d_all, axis=1), fin[p * n:(p + 1) * n][q])
+    # E3: weighted positions are convex combinations of target points
+    w = out["weighted_avg_transformed_points"].cpu().numpy()
+    for p in range(0, P, 9):
+        lo, hi = pts[off[p]:off[p + 1]].min(0), pts[off[p]:off[p + 1]].max(0)
+        assert np.all(w[p * n:(p + 1) * n] >= lo - 1e-9) and np.all(w[p * n:(p + 1) * n] <= hi + 1e-9)
+    # a pair run alone gives bit-identical correspondences to the same pair inside the batch
+    for p in (5, 40):
+        sel = np.concatenate([np.arange(off[p], off[p + 1]), np.arange(off[P + p], off[P + p + 1])])
+        tri1 = np.concatenate([base.tris, base.tris + n]).astype(np.int32)
+        one = sb.run(torch.from_numpy(pts[sel]).cuda(), torch.from_numpy(tri1).cuda(), np.array([0, n, 2 * n], np.int32), 1,
+                     idx_t=out["idx_t"][p:p + 1], idx_s=out["idx_s"][p:p + 1])
+        assert np.array_equal(one["final_idx"].cpu().numpy(), fin[p * n:(p + 1) * n])
