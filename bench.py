@@ -207,6 +207,8 @@ def run_ours(a):
     launches = _lib.launch_count() - l0
     prof = np.zeros(4)
     lib.focusr_profile_get(prof.ctypes.data)
+    prof32 = np.zeros(4)
+    lib.focusr_profile_get_lowp(prof32.ctypes.data)  # the filter passes that ran on fp32 blocks (k_spmm_f32)
     clocks = sampler.stop() if sampler else None
     step_e2e()
     ms_e2e = timed(step_e2e, a.steps)
@@ -241,7 +243,14 @@ def run_ours(a):
             roofline["traffic"] = rec["dram_bytes_per_launch"]
             roofline["traffic_source"] = rec["source"]
     knn_q = P * n  # queries per KNN call and GPU
+    achieved32 = prof32[2] / (prof32[0] / 1e3) / 1e9 if prof32[0] > 0 else None
     secondary = {"spmv_filter_hbm_gbs": achieved,
+                 "filter_fp32_passes": {"kernel": "k_spmm_f32<16,4,0> (same step on fp32 blocks: probe + first pass)",
+                                        "achieved_gbs": achieved32, "frac_of_peak": (achieved32 / peak) if achieved32 else None,
+                                        "launches": int(prof32[1]),
+                                        "avg_launch_ms": (prof32[0] / prof32[1]) if prof32[1] else None,
+                                        "bytes_per_launch": (prof32[2] / prof32[1]) if prof32[1] else None,
+                                        "share_of_step": (prof32[0] / ms) if ms else None},
                  "knn_queries_per_s": {"initial_k1_d3": knn_q / (stages["knn_initial"] / 1e3) if stages.get("knn_initial") else None,
                                        "final_k3_d3": knn_q / (stages["knn_final"] / 1e3) if stages.get("knn_final") else None}}
     if world == 1 and not a.no_cpu_baseline:

@@ -156,7 +156,7 @@ class DeviceGraph:
         info = dict(status=res_i[:, 0].copy(), n_found=res_i[:, 1].copy(), k_final=res_i[:, 2].copy(),
                     outer_iterations=res_i[:, 3].copy(), filter_degree=res_i[:, 4].copy(), block_size=b,
                     symmetric=res_i[:, 6].copy(), restarts=restarts, max_residual=res_d[:, 0].copy(),
-                    spectrum_bound=res_d[:, 1].copy())
+                    spectrum_bound=res_d[:, 1].copy(), fp32_filter_degree=res_i[:, 7].copy())
         return vals, vecs, info
 
     def laplacian_apply(self, x):

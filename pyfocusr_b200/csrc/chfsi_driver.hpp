@@ -9,6 +9,11 @@
 //                                          host complex-Schur if not, see nonsym_host.hpp)
 //     X <- X W, residuals                 (GPU)
 //     X <- p_m(L) X                       (m fused SpMM+axpby Chebyshev steps, GPU: the hot loop)
+// Mixed precision: rounding in a filter step perturbs the block by eps relative to its current size, and what
+// matters is the part of that perturbation outside the wanted subspace, which the remaining steps do not
+// amplify -- so a pass in fp32 can bring residuals down to ~1e-6 (measured floor) but not below.  A pass whose
+// predicted landing stays above `lowp_floor` is therefore run with fp32 blocks (40% fewer bytes per step); the
+// Rayleigh-Ritz steps, every residual that is tested, and each pass that lands below the floor stay fp64.
 // with (g, h) = (D~, 1) for a symmetric adjacency (L is self-adjoint in the D~ inner product, so
 // H is symmetric) and (1, D~^-1) otherwise (Euclidean projection, H general).
 // The filter damps [a, beta], a = largest Ritz value of the block, beta = 2 (Gershgorin bound of
@@ -52,6 +57,8 @@ struct SolveParams {
   int probe_degree;  // > 0: tighten beta per mesh with a top-of-spectrum probe of this many filter steps
                      // (symmetric batches only); 0: filter up to `beta` as given
   double land;       // the sized pass aims at land * tol
+  double lowp_floor; // > 0: a filter pass that is predicted to leave every residual above this value runs with the
+                     // blocks stored and updated in fp32 (symmetric batches on a backend that offers it); 0: fp64 only
 };
 
 struct MeshResult {
@@ -63,6 +70,7 @@ struct MeshResult {
   int block;
   double max_residual;
   double beta;     // upper edge of the filter interval that was used
+  int lowp_degree; // filter steps (of total_degree, plus the probe) that ran in fp32
 };
 
 inline void cheb_table(double a, double a_low, double beta, int m, double* alpha, double* gamma,
@@ -234,7 +242,7 @@ void probe_upper_bound(BE& be, const SolveParams& p, double* beta_m) {
   be.init_block();
   for (int m = 0; m < M; ++m)
     cheb_table(0.0, p.beta, 1.0, deg, &alpha[(size_t)m * deg], &gamma[(size_t)m * deg], &center[m]);
-  be.filter(deg, alpha.data(), gamma.data(), center.data());
+  be.filter(deg, alpha.data(), gamma.data(), center.data(), p.lowp_floor > 0.0 && be.lowp_available());
   be.apply_DmA();
   be.gram();
   be.rr_sym();
@@ -271,9 +279,15 @@ int chfsi_solve(BE& be, const SolveParams& p, MeshResult* out) {
     out[m].total_degree = 0;
     out[m].block = B;
     out[m].max_residual = -1.0;
+    out[m].lowp_degree = 0;
   }
   std::vector<double> alpha, gamma, center(M), beta_m(M, p.beta);
-  if (sym && p.probe_degree > 0) probe_upper_bound(be, p, beta_m.data());
+  const bool lowp_on = sym && p.lowp_floor > 0.0 && be.lowp_available();
+  if (sym && p.probe_degree > 0) {
+    probe_upper_bound(be, p, beta_m.data());
+    if (lowp_on)
+      for (int m = 0; m < M; ++m) out[m].lowp_degree += p.probe_degree;
+  }
   for (int m = 0; m < M; ++m) out[m].beta = beta_m[m];
   be.init_block();
   int n_done = 0;
@@ -357,6 +371,7 @@ int chfsi_solve(BE& be, const SolveParams& p, MeshResult* out) {
 
     // --- next filter: per-mesh interval, one common degree
     int deg = 0;
+    bool lowp = lowp_on;
     for (int m = 0; m < M; ++m) {
       if (done[m]) continue;
       const double* th = &theta[(size_t)m * B];
@@ -394,6 +409,8 @@ int chfsi_solve(BE& be, const SolveParams& p, MeshResult* out) {
         const double cap = sym ? 1e7 : 1e4;
         if (need <= cap) amp = std::max(need, 30.0);
       }
+      // fp32 is enough for this pass only if no mesh is meant to land below the fp32 floor
+      if (!(worst > 0.0) || worst / amp < p.lowp_floor) lowp = false;
       deg = std::max(deg, cheb_degree(a, thk, beta, amp, p.max_degree));
     }
     if (n_done >= M) break;
@@ -402,9 +419,13 @@ int chfsi_solve(BE& be, const SolveParams& p, MeshResult* out) {
     for (int m = 0; m < M; ++m)
       cheb_table(last_a[m], last_alow[m], beta_m[m], deg, &alpha[(size_t)m * deg],
                  &gamma[(size_t)m * deg], &center[m]);
-    be.filter(deg, alpha.data(), gamma.data(), center.data());
+    if (deg < 3) lowp = false;
+    be.filter(deg, alpha.data(), gamma.data(), center.data(), lowp);
     for (int m = 0; m < M; ++m)
-      if (!done[m]) out[m].total_degree += deg;
+      if (!done[m]) {
+        out[m].total_degree += deg;
+        if (lowp) out[m].lowp_degree += deg;
+      }
   }
   for (int m = 0; m < M; ++m)
     if (!done[m]) rc = std::max(rc, (int)SOLVE_NOT_CONVERGED);

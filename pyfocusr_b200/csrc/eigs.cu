@@ -403,6 +403,10 @@ static thread_local PinnedPool g_pin_small, g_pin_tables;
 // Live profile of the dominant kernel (the Chebyshev SpMM step): CUDA events bracket every
 // filter() on the launching stream; the elapsed time is collected at the next synchronisation the
 // driver performs anyway.  bench.py turns {ms, launches, algorithmic bytes} into the roofline line.
+// fp32 filter passes (chfsi_driver.hpp, k_spmm_f32): a pass may run in fp32 if it is meant to leave every residual
+// above this value.  The fp32 floor measured on 15k-vertex meshes is ~5e-7 (a pass aimed lower stalls there).
+constexpr double LOWP_FLOOR = 2e-6;
+
 struct FilterProfile {
   double ms = 0.0;
   double launches = 0.0;
@@ -435,7 +439,8 @@ struct FilterProfile {
     pending = false;
   }
 };
-static FilterProfile g_filter_profile;
+static FilterProfile g_filter_profile;       // fp64 steps (k_spmm<b,.,0>)
+static FilterProfile g_filter_profile_lowp;  // fp32 steps (k_spmm_f32)
 
 // focusr_set_tuning(1, MB): L2 budget for blocking the filter over groups of meshes (0 = off)
 // Measured on B200 (gpurun_out/bench_l2_*.log, 128 pairs): 0 -> 641 pairs/s, 64 MB -> 548, 32 MB -> 341: groups
@@ -624,6 +629,8 @@ struct CudaBackend {
   int block() const { return B; }
   bool symmetric() const { return sym; }
   int zero_rows(int m) const { return info_host[4 * m + 2]; }
+  // fp32 filter passes: local solves only (the peer-shared blocks of the row-partitioned solve are fp64)
+  bool lowp_available() const { return dist == nullptr && g_mixed_precision != 0; }
 
   void fail(cudaError_t e, const char* what) {
     if (e != cudaSuccess && err == FB_OK) {
@@ -813,7 +820,8 @@ struct CudaBackend {
     memcpy(th, pin, bytes);
     memcpy(rs, pin + (size_t)M * B, bytes);
   }
-  void filter(int deg, const double* al, const double* ga, const double* ce) {
+  void filter(int deg, const double* al, const double* ga, const double* ce, bool lowp) {
+    lowp = lowp && lowp_available() && deg >= 3;
     // tables are uploaded in chunks of table_cap steps; pinned staging holds every chunk of this
     // filter until the next synchronisation (get_theta_res of the next outer iteration)
     const size_t total = (size_t)M * deg;
@@ -834,8 +842,15 @@ struct CudaBackend {
     const double rows = (double)(off_host[M] - off_host[0]);
     double nnz = 0.0;
     for (int m = 0; m < M; ++m) nnz += info_host[4 * m];
-    const double step_bytes = 12.0 * nnz + 4.0 * rows + 16.0 * rows + 24.0 * (double)B * rows;
-    g_filter_profile.begin(stream);
+    const double step_bytes = 12.0 * nnz + 4.0 * rows + 16.0 * rows + (lowp ? 12.0 : 24.0) * (double)B * rows;
+    FilterProfile& prof = lowp ? g_filter_profile_lowp : g_filter_profile;
+    prof.begin(stream);
+    // fp32 pass: the three fp32 blocks live in the two fp64 blocks that are free during a filter (Y: two of
+    // them, Xn: one); the first step reads X (fp64) and the last one writes X, so X holds the result again.
+    const size_t shift = (size_t)off_host[0] * B;  // X/Y/Xn are indexed by global row
+    float* f_cur = reinterpret_cast<float*>(Y + shift) - shift;
+    float* f_prev = reinterpret_cast<float*>(Y + shift) + (size_t)rows * B - shift;
+    float* f_next = reinterpret_cast<float*>(Xn + shift) - shift;
     for (int s0 = 0; s0 < deg; s0 += table_cap) {
       const int len = std::min(table_cap, deg - s0);
       double* pa = pin + pin_off;
@@ -854,6 +869,23 @@ struct CudaBackend {
       double per_mesh = 0.0;
       for (int m = 0; m < M; ++m)
         per_mesh = std::max(per_mesh, 12.0 * info_host[4 * m] + (20.0 + 24.0 * B) * (off_host[m + 1] - off_host[m]));
+      if (lowp) {
+        for (int s = 0; s < len; ++s) {
+          const int gs = s0 + s;
+          if (gs == 0) {  // X (fp64) -> f_cur, fp32 copy of X -> f_prev
+            launch_spmm_f32(1, B, g, X, nullptr, f_cur, f_prev, alpha, gamma, center, s, len, stream);
+          } else {
+            const bool last = gs == deg - 1;
+            launch_spmm_f32(last ? 2 : 0, B, g, f_cur, f_prev, last ? (void*)X : (void*)f_next, nullptr, alpha, gamma,
+                            center, s, len, stream);
+            float* t = f_prev;
+            f_prev = f_cur;
+            f_cur = f_next;
+            f_next = t;
+          }
+        }
+        continue;
+      }
       int group = M;
       if (g_l2_budget_mb > 0) group = std::max(1, (int)((double)g_l2_budget_mb * 1048576.0 / per_mesh));
       if (group >= M || len < 2) {
@@ -880,14 +912,15 @@ struct CudaBackend {
         next = t;
       }
     }
-    g_filter_profile.end(stream, (double)deg, (double)deg * step_bytes);
-    // rotate names so that X is the filtered block again
-    double* nx = cur;
-    double* ny = prev;
-    double* nn = next;
-    X = nx;
-    Y = ny;
-    Xn = nn;
+    prof.end(stream, (double)deg, (double)deg * step_bytes);
+    if (!lowp) {  // rotate names so that X is the filtered block again
+      double* nx = cur;
+      double* ny = prev;
+      double* nn = next;
+      X = nx;
+      Y = ny;
+      Xn = nn;
+    }
     check("filter");
   }
   void finalize(const int* fl, const int* sl, const int* no) {
@@ -960,6 +993,16 @@ extern "C" {
 void focusr_profile_reset(void) {
   g_filter_profile.collect();
   g_filter_profile.ms = g_filter_profile.launches = g_filter_profile.bytes = 0.0;
+  g_filter_profile_lowp.collect();
+  g_filter_profile_lowp.ms = g_filter_profile_lowp.launches = g_filter_profile_lowp.bytes = 0.0;
+}
+
+void focusr_profile_get_lowp(double* out4_host) {
+  g_filter_profile_lowp.collect();
+  out4_host[0] = g_filter_profile_lowp.ms;
+  out4_host[1] = g_filter_profile_lowp.launches;
+  out4_host[2] = g_filter_profile_lowp.bytes;
+  out4_host[3] = 0.0;
 }
 
 void focusr_profile_get(double* out4_host) {
@@ -1029,6 +1072,7 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
   // 0: probe the top of the spectrum and filter only up to it; > 0: trust the caller; < 0: Gershgorin as is
   p.probe_degree = spectrum_upper_bound == 0.0 ? 10 : 0;
   p.land = 0.2;
+  p.lowp_floor = LOWP_FLOOR;
 
   // contiguous runs of meshes with the same symmetry class are solved as one batch
   int rc_all = FB_OK;
@@ -1073,6 +1117,7 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
     if (be.err != FB_OK) return be.err;
     FB_CUDA(cudaStreamSynchronize(stream));
     g_filter_profile.collect();
+    g_filter_profile_lowp.collect();
     for (int m = m0; m < m1; ++m) {
       int* ri = result_i_host + 8 * m;
       ri[0] = results[m].status;
@@ -1082,7 +1127,7 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
       ri[4] = results[m].total_degree;
       ri[5] = B;
       ri[6] = sym ? 1 : 0;
-      ri[7] = 0;
+      ri[7] = results[m].lowp_degree;
       result_d_host[2 * m] = results[m].max_residual;
       result_d_host[2 * m + 1] = results[m].beta;
     }
@@ -1245,6 +1290,7 @@ int focusr_eigs_smallest_dist(const int* row_ptr, const int* cols_local, const d
   // 0: probe the top of the spectrum and filter only up to it; > 0: trust the caller; < 0: Gershgorin as is
   p.probe_degree = spectrum_upper_bound == 0.0 ? 10 : 0;
   p.land = 0.2;
+  p.lowp_floor = LOWP_FLOOR;
 
   DistCtx d;
   d.comm = g_dist_comm;

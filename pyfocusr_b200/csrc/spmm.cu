@@ -219,6 +219,7 @@ k_spmm_staged(const int* __restrict__ row_ptr, const int* __restrict__ cols, con
 }
 
 int g_spmm_variant = 0;  // focusr_set_tuning(0, v): 0 = register-capped gather kernel, 1 = TMA-staged window
+int g_mixed_precision = 1;  // focusr_set_tuning(3, v): 1 = early filter passes in fp32 (default), 0 = fp64 throughout
 
 template <int B, int TPR>
 static int launch_spmm_b(int mode, const SpmmGraph& g, const double* y, const double* x_prev, double* out,
@@ -289,6 +290,137 @@ int launch_spmm(int mode, int b, const SpmmGraph& g, const double* y, const doub
     FB_CASE(96, 16)
     default:
       set_error("spmm: unsupported block size %d (multiples of 8 up to 96)", b);
+      return FB_ERR_UNSUPPORTED;
+  }
+#undef FB_CASE
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Mixed-precision filter step: the same fused SpMM + three-term update with the vector blocks stored
+// and updated in fp32 (matrix entries, degree and table values are rounded to fp32 as they are loaded;
+// fmaf throughout).  Used by the driver only for passes that are meant to land above the fp32 floor
+// (chfsi_driver.hpp); what is tested and returned is always computed in fp64.  Algorithmic bytes per
+// step and mesh: 12 nnz + 20 N + 12 b N (against 24 b N): 284 N instead of 476 N at b = 16.
+//   IO 0: y, x_prev, out fp32.
+//   IO 1: first step of a pass -- y is the fp64 block; writes out (fp32) and an fp32 copy of y, which
+//         is the next step's x_prev (gamma is 0 at step 0, x_prev is not read).
+//   IO 2: last step of a pass -- y, x_prev fp32, out is written as fp64.
+// A thread owns B/(4*TPR) float4 slices of a row, so gathers stay 16-byte loads.
+// ---------------------------------------------------------------------------------------------
+template <int B, int TPR, int IO>
+__global__ void __launch_bounds__(SPMM_THREADS, (B / (4 * TPR) == 1) ? 8 : ((B / (4 * TPR) == 2) ? 6 : 3))
+k_spmm_f32(const int* __restrict__ row_ptr, const int* __restrict__ cols, const double* __restrict__ weights,
+           const double* __restrict__ degree, const double* __restrict__ degree_inv,
+           const int* __restrict__ mesh_off, const void* __restrict__ y_, const float* __restrict__ x_prev,
+           void* __restrict__ out_, float* __restrict__ y_copy, const double* __restrict__ alpha,
+           const double* __restrict__ gamma, const double* __restrict__ center, int step, int n_steps) {
+  constexpr int VPT = B / (4 * TPR);
+  static_assert(VPT * 4 * TPR == B, "block size must be a multiple of 4*TPR");
+  const int mesh = blockIdx.y;
+  const int r0 = mesh_off[mesh] + blockIdx.x * SPMM_ROWS_PER_BLOCK;
+  const int r1 = min(mesh_off[mesh + 1], r0 + SPMM_ROWS_PER_BLOCK);
+  if (r0 >= r1) return;
+  const float al = (float)alpha[(size_t)mesh * n_steps + step];
+  const float ga = (float)gamma[(size_t)mesh * n_steps + step];
+  const float cc = (float)center[mesh];
+  const int g = threadIdx.x / TPR, t = threadIdx.x % TPR;
+  auto load_y = [&](int r, int slice) -> float4 {
+    if (IO == 1) {
+      const double2* src = reinterpret_cast<const double2*>(static_cast<const double*>(y_) + (size_t)r * B) + 2 * slice;
+      const double2 a = __ldg(src), b = __ldg(src + 1);
+      return make_float4((float)a.x, (float)a.y, (float)b.x, (float)b.y);
+    } else {
+      return __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(y_) + (size_t)r * B) + slice);
+    }
+  };
+  for (int row = r0 + g; row < r1; row += SPMM_THREADS / TPR) {
+    float4 acc[VPT];
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int p0 = row_ptr[row], p1 = row_ptr[row + 1];
+#pragma unroll 4
+    for (int p = p0; p < p1; ++p) {
+      const int c = cols[p];
+      const float w = (float)weights[p];
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) {
+        const float4 a = load_y(c, t + v * TPR);
+        acc[v].x = fmaf(w, a.x, acc[v].x);
+        acc[v].y = fmaf(w, a.y, acc[v].y);
+        acc[v].z = fmaf(w, a.z, acc[v].z);
+        acc[v].w = fmaf(w, a.w, acc[v].w);
+      }
+    }
+    const float d = (float)degree[row];
+    const float di = (float)degree_inv[row];
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      const int slice = t + v * TPR;
+      const float4 yv = load_y(row, slice);
+      float4 r;
+      r.x = al * (di * (d * yv.x - acc[v].x) - cc * yv.x);
+      r.y = al * (di * (d * yv.y - acc[v].y) - cc * yv.y);
+      r.z = al * (di * (d * yv.z - acc[v].z) - cc * yv.z);
+      r.w = al * (di * (d * yv.w - acc[v].w) - cc * yv.w);
+      if (IO != 1 && ga != 0.f) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x_prev + (size_t)row * B) + slice);
+        r.x -= ga * xv.x;
+        r.y -= ga * xv.y;
+        r.z -= ga * xv.z;
+        r.w -= ga * xv.w;
+      }
+      if (IO == 2) {
+        double2* o = reinterpret_cast<double2*>(static_cast<double*>(out_) + (size_t)row * B) + 2 * slice;
+        o[0] = make_double2((double)r.x, (double)r.y);
+        o[1] = make_double2((double)r.z, (double)r.w);
+      } else {
+        reinterpret_cast<float4*>(static_cast<float*>(out_) + (size_t)row * B)[slice] = r;
+      }
+      if (IO == 1) reinterpret_cast<float4*>(y_copy + (size_t)row * B)[slice] = yv;
+    }
+  }
+}
+
+template <int B, int TPR>
+static int launch_spmm_f32_b(int io, const SpmmGraph& g, const void* y, const float* x_prev, void* out, float* y_copy,
+                             const double* alpha, const double* gamma, const double* center, int step, int n_steps,
+                             cudaStream_t stream) {
+  dim3 grid(div_up(g.max_mesh_rows, SPMM_ROWS_PER_BLOCK), g.n_meshes);
+  if (io == 0)
+    k_spmm_f32<B, TPR, 0><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv, g.mesh_off,
+                                                             y, x_prev, out, y_copy, alpha, gamma, center, step, n_steps);
+  else if (io == 1)
+    k_spmm_f32<B, TPR, 1><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv, g.mesh_off,
+                                                             y, x_prev, out, y_copy, alpha, gamma, center, step, n_steps);
+  else
+    k_spmm_f32<B, TPR, 2><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv, g.mesh_off,
+                                                             y, x_prev, out, y_copy, alpha, gamma, center, step, n_steps);
+  FB_COUNT_LAUNCH(1);
+  return FB_OK;
+}
+
+int launch_spmm_f32(int io, int b, const SpmmGraph& g, const void* y, const float* x_prev, void* out, float* y_copy,
+                    const double* alpha, const double* gamma, const double* center, int step, int n_steps,
+                    cudaStream_t stream) {
+#define FB_CASE(BB, TT) \
+  case BB:              \
+    return launch_spmm_f32_b<BB, TT>(io, g, y, x_prev, out, y_copy, alpha, gamma, center, step, n_steps, stream);
+  switch (b) {
+    FB_CASE(8, 2)
+    FB_CASE(16, 4)
+    FB_CASE(24, 2)
+    FB_CASE(32, 4)
+    FB_CASE(40, 2)
+    FB_CASE(48, 4)
+    FB_CASE(56, 2)
+    FB_CASE(64, 4)
+    FB_CASE(72, 2)
+    FB_CASE(80, 4)
+    FB_CASE(88, 2)
+    FB_CASE(96, 4)
+    default:
+      set_error("spmm (fp32): unsupported block size %d (multiples of 8 up to 96)", b);
       return FB_ERR_UNSUPPORTED;
   }
 #undef FB_CASE
@@ -500,6 +632,10 @@ int focusr_set_tuning(int key, int value) {
   }
   if (key == 2) {
     fb::g_smooth_variant = value;
+    return 0;
+  }
+  if (key == 3) {
+    fb::g_mixed_precision = value;
     return 0;
   }
   fb::set_error("set_tuning: unknown key %d", key);

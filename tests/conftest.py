@@ -48,6 +48,8 @@ def hostsim():
     lib.hostsim_eigs.argtypes = [ip, ip, dp, dp, dp, dp, C.c_int, ip, C.c_int, C.c_int, ip, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int,
                                  dp, dp, ip, dp]
+    lib.hostsim_set_lowp.argtypes = [C.c_double]
+    lib.hostsim_set_lowp.restype = None
     lib.hostsim_rr_sym.argtypes = [dp, dp, dp, dp, C.c_int]
     lib.hostsim_eig_general.argtypes = [dp, C.c_int, dp, dp]
     lib.hostsim_edge_weight.argtypes = [dp, dp, C.c_int]

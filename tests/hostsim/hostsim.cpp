@@ -16,6 +16,9 @@
 
 namespace {
 
+double g_lowp_floor = 0.0;   // hostsim_set_lowp: SolveParams::lowp_floor of the next solves
+int g_last_lowp_degree = 0;  // lowp_degree of mesh 0 of the last solve
+
 struct HostBackend {
   const int* rp;
   const int* cols;
@@ -36,6 +39,7 @@ struct HostBackend {
   int block() const { return B; }
   bool symmetric() const { return sym; }
   int zero_rows(int m) const { return zr[m]; }
+  bool lowp_available() const { return true; }
 
   void init_block() {
     X.assign((size_t)N * B, 0.0);
@@ -149,7 +153,40 @@ struct HostBackend {
     std::memcpy(th, theta.data(), theta.size() * sizeof(double));
     std::memcpy(rs, res.data(), res.size() * sizeof(double));
   }
-  void filter(int deg_m, const double* alpha, const double* gamma, const double* center) {
+  // fp32 pass as k_spmm_f32 runs it: blocks, matrix entries and table values rounded to float, float arithmetic
+  void filter_lowp(int deg_m, const double* alpha, const double* gamma, const double* center) {
+    std::vector<float> p(X.size()), y(X.size()), n(X.size()), acc(B);
+    for (size_t t = 0; t < X.size(); ++t) y[t] = (float)X[t];
+    for (int s = 0; s < deg_m; ++s) {
+      for (int m = 0; m < M; ++m) {
+        const float al = (float)alpha[(size_t)m * deg_m + s], ga = (float)gamma[(size_t)m * deg_m + s], c = (float)center[m];
+        for (int i = off[m]; i < off[m + 1]; ++i) {
+          for (int k = 0; k < B; ++k) acc[k] = 0.0f;
+          for (int q = rp[i]; q < rp[i + 1]; ++q) {
+            const float wq = (float)w[q];
+            const float* row = &y[(size_t)cols[q] * B];
+            for (int k = 0; k < B; ++k) acc[k] += wq * row[k];
+          }
+          const float d = (float)deg[i], di = (float)dinv[i];
+          for (int k = 0; k < B; ++k) {
+            const float yv = y[(size_t)i * B + k];
+            const float ly = di * (d * yv - acc[k]);
+            float r = al * (ly - c * yv);
+            if (ga != 0.0f) r -= ga * p[(size_t)i * B + k];
+            n[(size_t)i * B + k] = r;
+          }
+        }
+      }
+      p.swap(y);
+      y.swap(n);
+    }
+    for (size_t t = 0; t < X.size(); ++t) X[t] = (double)y[t];
+  }
+  void filter(int deg_m, const double* alpha, const double* gamma, const double* center, bool lowp) {
+    if (lowp) {
+      filter_lowp(deg_m, alpha, gamma, center);
+      return;
+    }
     std::vector<double> acc(B);
     Y = X;  // Y = current, X = previous
     for (int s = 0; s < deg_m; ++s) {
@@ -208,9 +245,10 @@ int hostsim_eigs(const int* rp, const int* cols, const double* w, const double* 
   fb::SolveParams p;
   p.k0 = k0; p.n_needed = n_needed; p.k_buffer = k_buffer; p.min_eig = min_eig; p.tol = tol;
   p.max_outer = max_outer; p.amp_target = amp_target; p.max_degree = max_degree; p.beta = beta > 0.0 ? beta : 2.0; p.ldv = ldv;
-  p.probe_degree = beta == 0.0 ? 10 : 0; p.land = 0.2;
+  p.probe_degree = beta == 0.0 ? 10 : 0; p.land = 0.2; p.lowp_floor = g_lowp_floor;
   std::vector<fb::MeshResult> r(n_meshes);
   const int rc = fb::chfsi_solve(be, p, r.data());
+  g_last_lowp_degree = r[0].lowp_degree;
   for (int m = 0; m < n_meshes; ++m) {
     int* ri = result_i + 6 * m;
     ri[0] = r[m].status; ri[1] = r[m].n_out; ri[2] = r[m].k_final; ri[3] = r[m].outer_iters;
@@ -220,6 +258,9 @@ int hostsim_eigs(const int* rp, const int* cols, const double* w, const double* 
   }
   return rc;
 }
+
+void hostsim_set_lowp(double floor) { g_lowp_floor = floor; }
+int hostsim_last_lowp_degree(void) { return g_last_lowp_degree; }
 
 int hostsim_rr_sym(double* g, double* h, double* w, double* theta, int b) {
   std::vector<double> y((size_t)b * b), rot(b + 2);

@@ -218,6 +218,39 @@ def test_eigs_synthetic_and_batch_consistency(torch, synth):
     assert np.allclose(sv[0, :6].cpu().numpy(), vals[1, :6], rtol=1e-9, atol=0)
 
 
+@pytest.mark.parametrize("block", [16, 24, 32, 48])
+def test_eigs_mixed_precision_passes(torch, shipped_meshes, synth, block):
+    """The early filter passes run on fp32 blocks (k_spmm_f32; float4 slices, 2 or 4 threads per row) by default;
+    focusr_set_tuning(3, 0) keeps fp64 throughout.  Both meet the fp64 tolerance and the oracle; the fp32 passes
+    cost no extra filter degree."""
+    from pyfocusr_b200 import _lib
+    from pyfocusr_b200._device import DeviceGraph
+
+    ms = [shipped_meshes["target_mesh"], synth["ell20a"], synth["ell39"]]
+    g = DeviceGraph([m.points for m in ms], [m.tris for m in ms])
+    out = {}
+    try:
+        for mixed in (1, 0):
+            _lib.call("focusr_set_tuning", 3, mixed)
+            vals, vecs, info = g.eigs_smallest(k=7, n_k_needed=6, block_size=block)
+            out[mixed] = (vals.cpu().numpy(), vecs.cpu().numpy(), info)
+    finally:
+        _lib.call("focusr_set_tuning", 3, 1)
+    (v1, x1, i1), (v0, x0, i0) = out[1], out[0]
+    assert i1["status"].tolist() == [0, 0, 0] and i0["status"].tolist() == [0, 0, 0]
+    assert np.all(i0["fp32_filter_degree"] == 0)
+    assert np.all(i1["fp32_filter_degree"] > 10) and np.all(i1["fp32_filter_degree"] < 10 + i1["filter_degree"])
+    assert i1["filter_degree"].max() <= 1.15 * i0["filter_degree"].max()
+    assert i1["max_residual"].max() <= 1e-10 and i0["max_residual"].max() <= 1e-10
+    assert np.max(np.abs(v1[:, :6] - v0[:, :6]) / v0[:, :6]) <= 1e-9
+    for k, m in enumerate(ms):
+        o0, o1 = g.mesh_off_host[k], g.mesh_off_host[k + 1]
+        check_eigs(v1[k, :6], x1[o0:o1, :6], m, 6)
+    # bit-reproducible
+    _, x1b, _ = g.eigs_smallest(k=7, n_k_needed=6, block_size=block)
+    assert sha(x1b.cpu().numpy()) == sha(x1)
+
+
 def test_eigs_icosphere_multiplets(torch, synth):
     """Exact 3/5/7-fold multiplets: k=11 cuts the l=3 multiplet."""
     from oracle import port
