@@ -96,9 +96,11 @@ int focusr_gather_rows(const double* in, const long long* idx, const int* idx_ba
  * result_i_host [n_meshes][8]: {status, n_found, k_final, outer_iterations, total_filter_degree,
  * block_size, symmetric, filter steps that ran in fp32 (of the total, plus the probe's)};
  * result_d_host [n_meshes][2]: {max_residual, upper edge of the filter interval}.
- * Mixed precision: a filter pass that is meant to leave residuals above the fp32 floor (2e-6) runs with
- * fp32 vector blocks (k_spmm_f32, 40% fewer bytes per step); Rayleigh-Ritz, the residuals that are tested
- * and every pass that lands lower are fp64, so the returned pairs meet `tol` in fp64 either way.
+ * Mixed precision (symmetric adjacencies): a filter pass that is meant to leave residuals above the fp32 floor
+ * (1.4e-6) runs with fp32 vector blocks (k_spmm_f32, 40% fewer bytes per step); a pass that lands lower runs in
+ * fp32 CORRECTION form (k_spmm_corr): only z = p(L) x - x is iterated in fp32, driven by the fp64 residual of the
+ * Ritz pairs, so rounding is relative to the error of x, and x += z is fp64 (27% fewer bytes per step).
+ * Rayleigh-Ritz and every residual that is tested are fp64, so the returned pairs meet `tol` in fp64 either way.
  * focusr_set_tuning(3, 0) keeps every pass in fp64.
  * status: 0 ok, 1 not converged, 2 block too small, 3 numerical breakdown, 4 ldv too small.
  * `spectrum_upper_bound`: > 0 = filter up to this caller-guaranteed bound; 0 = start from the
@@ -162,17 +164,19 @@ int focusr_eigs_smallest_dist(const int* row_ptr, const int* cols_local, const d
 /* Live profile of the dominant kernel, the Chebyshev SpMM filter step (CUDA events on the launching
  * stream around every filter application since the last reset): out4_host = {milliseconds,
  * launches, algorithmic bytes (12 nnz + 20 N + 24 b N per launch), 0}.  bench.py's roofline line.
- * focusr_profile_get counts the fp64 steps (k_spmm), focusr_profile_get_lowp the fp32 steps
- * (k_spmm_f32: 12 nnz + 20 N + 12 b N per launch); reset clears both. */
+ * focusr_profile_get counts the fp64 steps (k_spmm); focusr_profile_get_kind(kind, ...) the steps of one kind:
+ * 0 = fp64, 1 = fp32 (k_spmm_f32: 12 nnz + 20 N + 12 b N per launch), 2 = fp32 correction form (k_spmm_corr:
+ * 12 nnz + 20 N + 16 b N per launch); reset clears all three. */
 void focusr_profile_reset(void);
 void focusr_profile_get(double* out4_host);
-void focusr_profile_get_lowp(double* out4_host);
+void focusr_profile_get_kind(int kind, double* out4_host);
 
 /* Tuning knobs (experiments and A/B profiling; see the tuning records in csrc/spmm.cu, csrc/eigs.cu).
  * key 2: variant of the persistent cluster smoothing kernel (0..3: threads x gather batch).
  * key 0: filter-step kernel (0 = register-capped gather kernel, 1 = TMA bulk-staged y window in
  * shared memory, b <= 32);  key 1: L2 budget in MB for blocking the filter over mesh groups (0 = off);
- * key 3: mixed-precision filter passes (1 = on, default; 0 = fp64 throughout). */
+ * key 3: mixed-precision filter passes (1 = on, default; 0 = fp64 throughout);
+ * key 4 / key 5: L2 prefetch variant (0..3) of the b = 16 fp64 / fp32 filter step (defaults 0 / 3). */
 int focusr_set_tuning(int key, int value);
 
 /* y = L x for a dense block of n_cols vectors (n_cols a multiple of 8, <= 96), used by tests and

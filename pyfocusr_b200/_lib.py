@@ -48,7 +48,7 @@ SIGNATURES = {
     "focusr_set_tuning": (_i, [_i, _i]),
     "focusr_profile_reset": (None, []),
     "focusr_profile_get": (None, [_vp]),
-    "focusr_profile_get_lowp": (None, [_vp]),
+    "focusr_profile_get_kind": (None, [_i, _vp]),
     "focusr_laplacian_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
     "focusr_normalize_columns": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp]),
     "focusr_flip_permute_columns": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp]),

@@ -12,6 +12,8 @@ Mesh order inside the batch graph: targets 0..P-1, then sources 0..P-1.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import _device, _lib
@@ -52,6 +54,12 @@ class SpectralBatch:
                                non_rigid_alpha=non_rigid_alpha, non_rigid_beta=non_rigid_beta,
                                non_rigid_n_eigens=non_rigid_n_eigens)
         self.smooth_l2_bytes = 0  # > 0: smoothing runs group by group of meshes that fit L2 (see DeviceGraph.mean_filter)
+        # The smoothing of the target vertices (graph.py:349-354, 300 passes) depends only on the target graphs, not on
+        # the spectral stages: with overlap_smoothing it is enqueued on a second CUDA stream right after the Laplacian
+        # build and joined where its result is first read; its CTAs fill the gaps the latency-bound filter steps leave
+        # (B200, 128 pairs: 1059 -> 1127 pairs/s).  Same kernels, same results; `timings` then attributes the overlapped
+        # passes to the eigensolve stage.
+        self.overlap_smoothing = os.environ.get("FOCUSR_OVERLAP_SMOOTHING", "1") == "1"
         self.timings = {}
 
     # ------------------------------------------------------------------------------------------
@@ -90,6 +98,17 @@ class SpectralBatch:
         g = DeviceGraph.from_device(points, tris, mesh_off_host)
         mark("laplacian")
         n, ns = self.n, self.ns
+        nt_total = int(g.mesh_off_host[P])
+        smoothed_t, side = None, None
+        if self.overlap_smoothing:
+            main = torch.cuda.current_stream()
+            if getattr(self, "_side_stream", None) is None:  # one stream for the life of the object: the caching
+                self._side_stream = torch.cuda.Stream(device=g.device)  # allocator keeps a pool per stream
+            side = self._side_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                smoothed_t = g.mean_filter(g.points, self.graph_smoothing_iterations, 0, nt_total, self.smooth_l2_bytes)
+            smoothed_t.record_stream(main)
         vals, vecs, info = g.eigs_smallest(k=n + 1, n_k_needed=n, k_buffer=1, tol=self.tol,
                                            block_size=self.block_size)
         n_found = info["n_found"]
@@ -134,7 +153,6 @@ class SpectralBatch:
         coords = g.spectral_coords(vecs, weights, ns)
         mark("eigsort")
 
-        nt_total = int(off[P])
         dev = g.device
         ref_off = g.mesh_off[: P + 1].contiguous()
         qry_off = (g.mesh_off[P:] - nt_total).contiguous()
@@ -147,7 +165,10 @@ class SpectralBatch:
         idx0, _ = _device.knn(coords[:nt_total], coords[nt_total:], k=1, ref_off=ref_off, query_off=qry_off,
                               max_queries=max_q, max_refs=max_r, want_dist=False)
         mark("knn_initial")
-        smoothed_t = g.mean_filter(g.points, self.graph_smoothing_iterations, 0, nt_total, self.smooth_l2_bytes)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+        else:
+            smoothed_t = g.mean_filter(g.points, self.graph_smoothing_iterations, 0, nt_total, self.smooth_l2_bytes)
         base_q = torch.repeat_interleave(g.mesh_off[:P], torch.from_numpy(sizes[P:].astype(np.int64)).to(dev)).to(torch.int32)
         staged = torch.empty_like(g.points)
         _lib.call("focusr_gather_rows", _lib.ptr(smoothed_t), _lib.ptr(idx0), _lib.ptr(base_q), g.n_points - nt_total, 3,

@@ -13,7 +13,12 @@
 // matters is the part of that perturbation outside the wanted subspace, which the remaining steps do not
 // amplify -- so a pass in fp32 can bring residuals down to ~1e-6 (measured floor) but not below.  A pass whose
 // predicted landing stays above `lowp_floor` is therefore run with fp32 blocks (40% fewer bytes per step); the
-// Rayleigh-Ritz steps, every residual that is tested, and each pass that lands below the floor stay fp64.
+// Rayleigh-Ritz steps and every residual that is tested stay fp64.
+// Below that floor fp32 still works in CORRECTION form: with (x_j, theta_j) a Ritz pair and r_j = L x_j - theta_j x_j
+// its fp64 residual, p(L) x_j = x_j + z with z_{k+1} = alpha_kj ((L - c) z_k + r_j) - gamma_kj z_{k-1}, z_0 = 0, when the
+// polynomial of column j is normalised to 1 at theta_j.  z is as small as the error of x_j, so fp32 rounding in z is
+// relative to that error, not to x_j: the pass behaves like the fp64 one down to LOWP_CORR_NOISE times the residual it
+// started from.  Only x_j, r_j and the final x_j + z are fp64.  16 b N vector bytes per step instead of 24 b N.
 // with (g, h) = (D~, 1) for a symmetric adjacency (L is self-adjoint in the D~ inner product, so
 // H is symmetric) and (1, D~^-1) otherwise (Euclidean projection, H general).
 // The filter damps [a, beta], a = largest Ritz value of the block, beta = 2 (Gershgorin bound of
@@ -59,6 +64,8 @@ struct SolveParams {
   double land;       // the sized pass aims at land * tol
   double lowp_floor; // > 0: a filter pass that is predicted to leave every residual above this value runs with the
                      // blocks stored and updated in fp32 (symmetric batches on a backend that offers it); 0: fp64 only
+  double lowp_aim;   // residual a sized plain-fp32 pass aims at (>= lowp_floor), from where the fp32 correction
+                     // form can reach the tolerance
 };
 
 struct MeshResult {
@@ -72,6 +79,12 @@ struct MeshResult {
   double beta;     // upper edge of the filter interval that was used
   int lowp_degree; // filter steps (of total_degree, plus the probe) that ran in fp32
 };
+
+enum PassKind { PASS_FP64 = 0, PASS_FP32 = 1, PASS_FP32_CORR = 2 };
+
+// Noise floor of an fp32 correction pass relative to the residual it starts from (measured 1.5e-5 on 15k-vertex
+// meshes: 2.5e-6 -> 3.7e-11 of rounding noise next to the 2.8e-11 the polynomial leaves), with a margin.
+constexpr double LOWP_CORR_NOISE = 2.3e-5;
 
 inline void cheb_table(double a, double a_low, double beta, int m, double* alpha, double* gamma,
                        double* center) {
@@ -371,7 +384,7 @@ int chfsi_solve(BE& be, const SolveParams& p, MeshResult* out) {
 
     // --- next filter: per-mesh interval, one common degree
     int deg = 0;
-    bool lowp = lowp_on;
+    int kind = -1;  // PASS_* common to the batch
     for (int m = 0; m < M; ++m) {
       if (done[m]) continue;
       const double* th = &theta[(size_t)m * B];
@@ -404,27 +417,63 @@ int chfsi_solve(BE& be, const SolveParams& p, MeshResult* out) {
       // Gram matrix of the filtered (Ritz-rotated, hence graded) block factorisable.
       double amp = p.amp_target;
       const double worst = out[m].max_residual;
+      const double cap = sym ? 1e7 : 1e4;
       if (outer >= 1 && worst > 0.0 && worst < 1e-2) {
         const double need = worst / (p.land * p.tol);
-        const double cap = sym ? 1e7 : 1e4;
         if (need <= cap) amp = std::max(need, 30.0);
       }
-      // fp32 is enough for this pass only if no mesh is meant to land below the fp32 floor
-      if (!(worst > 0.0) || worst / amp < p.lowp_floor) lowp = false;
+      // Precision of the pass (see the header comment).  With fp32 available every pass takes one of its two forms:
+      // blocks that are still far from converged are filtered on fp32 blocks, sized to land at lowp_aim; from 1e-3 down
+      // the correction form takes over, which cannot gain more than ~1 / LOWP_CORR_NOISE in one pass (its rounding
+      // noise is that fraction of the residual it starts from) -- a pass that needs more is followed by a short second one.
+      int k = PASS_FP64;
+      if (lowp_on && worst > 0.0) {
+        if (worst < 1e-3) {
+          k = PASS_FP32_CORR;
+          const double need = worst / (p.land * p.tol);
+          amp = std::max(std::min(need, std::min(cap, 0.5 / LOWP_CORR_NOISE)), 30.0);
+        } else if (worst < 1e-1) {
+          k = PASS_FP32;
+          amp = std::min(std::max(worst / p.lowp_aim, 30.0), cap);
+        } else if (worst / amp >= p.lowp_floor) {
+          k = PASS_FP32;  // unsettled block: default amplification, far above the fp32 floor
+        }
+      }
+      if (kind < 0) kind = k;
+      else if (kind != k)  // mixed batch: the correction form serves every fp32 case, fp64 serves all
+        kind = (kind == PASS_FP64 || k == PASS_FP64) ? PASS_FP64 : PASS_FP32_CORR;
       deg = std::max(deg, cheb_degree(a, thk, beta, amp, p.max_degree));
     }
     if (n_done >= M) break;
-    alpha.resize((size_t)M * deg);
-    gamma.resize((size_t)M * deg);
-    for (int m = 0; m < M; ++m)
-      cheb_table(last_a[m], last_alow[m], beta_m[m], deg, &alpha[(size_t)m * deg],
-                 &gamma[(size_t)m * deg], &center[m]);
-    if (deg < 3) lowp = false;
-    be.filter(deg, alpha.data(), gamma.data(), center.data(), lowp);
+    if (kind < 0 || deg < 3) kind = PASS_FP64;
+    if (kind == PASS_FP32_CORR) {
+      // y_k = x + z_k with the polynomial of column j normalised to 1 at theta_j: z_{k+1} = alpha_kj ((L - c) z_k + r_j) -
+      // gamma_kj z_{k-1}, z_0 = 0, r = L x - theta x from the Rayleigh-Ritz step (fp64); tables per column
+      alpha.resize((size_t)M * deg * B);
+      gamma.resize((size_t)M * deg * B);
+      std::vector<double> ta(deg), tg(deg);
+      for (int m = 0; m < M; ++m)
+        for (int j = 0; j < B; ++j) {
+          const double thj = std::min(theta[(size_t)m * B + j], last_a[m]);
+          cheb_table(last_a[m], thj, beta_m[m], deg, ta.data(), tg.data(), &center[m]);
+          for (int s = 0; s < deg; ++s) {
+            alpha[((size_t)m * deg + s) * B + j] = ta[s];
+            gamma[((size_t)m * deg + s) * B + j] = tg[s];
+          }
+        }
+      be.filter_correction(deg, alpha.data(), gamma.data(), center.data());
+    } else {
+      alpha.resize((size_t)M * deg);
+      gamma.resize((size_t)M * deg);
+      for (int m = 0; m < M; ++m)
+        cheb_table(last_a[m], last_alow[m], beta_m[m], deg, &alpha[(size_t)m * deg],
+                   &gamma[(size_t)m * deg], &center[m]);
+      be.filter(deg, alpha.data(), gamma.data(), center.data(), kind == PASS_FP32);
+    }
     for (int m = 0; m < M; ++m)
       if (!done[m]) {
         out[m].total_degree += deg;
-        if (lowp) out[m].lowp_degree += deg;
+        if (kind != PASS_FP64) out[m].lowp_degree += deg;
       }
   }
   for (int m = 0; m < M; ++m)

@@ -249,7 +249,8 @@ template <int B>
 __global__ void __launch_bounds__(GRAM_THREADS)
 k_rotate(double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ w,
          const double* __restrict__ theta, const double* __restrict__ degree_inv,
-         const int* __restrict__ mesh_off, double* __restrict__ partial_res, int chunks_max) {
+         const int* __restrict__ mesh_off, double* __restrict__ partial_res, int chunks_max,
+         float* __restrict__ r_out) {  // r_out != null: the residual block dinv Z' - X' theta, rounded to fp32
   constexpr int WS = (B % 16 == 0) ? B + 8 : B;  // row stride of W in smem: 2-wavefront fragment reads
   constexpr int KS = B / 4, JT = B / 8;
   extern __shared__ double sm[];
@@ -291,6 +292,7 @@ k_rotate(double* __restrict__ x, const double* __restrict__ z, const double* __r
       if (valid) *reinterpret_cast<double2*>(x + (size_t)row * B + c0) = make_double2(cx0, cx1);
       const double t0 = theta[(size_t)mesh * B + c0], t1 = theta[(size_t)mesh * B + c0 + 1];
       const double e0 = di * cz0 - t0 * cx0, e1 = di * cz1 - t1 * cx1;
+      if (r_out && valid) *reinterpret_cast<float2*>(r_out + (size_t)row * B + c0) = make_float2((float)e0, (float)e1);
       double n0 = e0 * e0, n1 = e1 * e1, d0 = cx0 * cx0, d1 = cx1 * cx1;
       // sum over the 8 rows of the tile (lanes with equal l&3), fixed tree
 #pragma unroll
@@ -405,7 +407,15 @@ static thread_local PinnedPool g_pin_small, g_pin_tables;
 // driver performs anyway.  bench.py turns {ms, launches, algorithmic bytes} into the roofline line.
 // fp32 filter passes (chfsi_driver.hpp, k_spmm_f32): a pass may run in fp32 if it is meant to leave every residual
 // above this value.  The fp32 floor measured on 15k-vertex meshes is ~5e-7 (a pass aimed lower stalls there).
-constexpr double LOWP_FLOOR = 2e-6;
+constexpr double LOWP_FLOOR = 1.4e-6;
+// A sized plain-fp32 pass aims here (lands at ~0.7 of its aim): low enough for the fp32 correction form to reach 1e-10
+// from it with its rounding noise (2.3e-5 of the starting residual, chfsi_driver.hpp) well below the tolerance.
+constexpr double LOWP_AIM = 1.5e-6;
+
+// The sized pass aims at SIZED_PASS_LAND * tol.  The prediction (residual / amplification of the slowest wanted pair) is
+// pessimistic by a steady factor: aimed at 0.2 / 0.35 / 0.5 tol, batches of 15k-vertex meshes land at 0.13 / 0.24 / 0.35 tol
+// with 282 / 274 / 269 filter steps.  A miss costs one more (short) pass, never accuracy.
+constexpr double SIZED_PASS_LAND = 0.4;
 
 struct FilterProfile {
   double ms = 0.0;
@@ -441,6 +451,7 @@ struct FilterProfile {
 };
 static FilterProfile g_filter_profile;       // fp64 steps (k_spmm<b,.,0>)
 static FilterProfile g_filter_profile_lowp;  // fp32 steps (k_spmm_f32)
+static FilterProfile g_filter_profile_corr;  // fp32 correction steps (k_spmm_corr)
 
 // focusr_set_tuning(1, MB): L2 budget for blocking the filter over groups of meshes (0 = off)
 // Measured on B200 (gpurun_out/bench_l2_*.log, 128 pairs): 0 -> 641 pairs/s, 64 MB -> 548, 32 MB -> 341: groups
@@ -632,6 +643,13 @@ struct CudaBackend {
   // fp32 filter passes: local solves only (the peer-shared blocks of the row-partitioned solve are fp64)
   bool lowp_available() const { return dist == nullptr && g_mixed_precision != 0; }
 
+  // fp32 view number `half` (0 or 1) of an fp64 block, indexed by global row like the block itself
+  float* f32_view(double* blk, int half) const {
+    const size_t shift = (size_t)off_host[0] * B;
+    const size_t rows = (size_t)(off_host[M] - off_host[0]);
+    return reinterpret_cast<float*>(blk + shift) + (size_t)half * rows * B - shift;
+  }
+
   void fail(cudaError_t e, const char* what) {
     if (e != cudaSuccess && err == FB_OK) {
       set_error("eigs: %s -> %s", what, cudaGetErrorString(e));
@@ -709,7 +727,9 @@ struct CudaBackend {
       attr_set = true;
     }
     dim3 grid(chunks_max, M);
-    k_rotate<BB><<<grid, GRAM_THREADS, smem, stream>>>(X, Xn, W, theta, g.degree_inv, g.mesh_off, partial_res, chunks_max);
+    // the fp32 residual block goes to the first half of Y (dead between filters), where filter_correction reads it
+    k_rotate<BB><<<grid, GRAM_THREADS, smem, stream>>>(X, Xn, W, theta, g.degree_inv, g.mesh_off, partial_res, chunks_max,
+                                                       lowp_available() ? f32_view(Y, 0) : nullptr);
   }
 #define FB_DISPATCH_B(fn)                \
   switch (B) {                           \
@@ -847,10 +867,9 @@ struct CudaBackend {
     prof.begin(stream);
     // fp32 pass: the three fp32 blocks live in the two fp64 blocks that are free during a filter (Y: two of
     // them, Xn: one); the first step reads X (fp64) and the last one writes X, so X holds the result again.
-    const size_t shift = (size_t)off_host[0] * B;  // X/Y/Xn are indexed by global row
-    float* f_cur = reinterpret_cast<float*>(Y + shift) - shift;
-    float* f_prev = reinterpret_cast<float*>(Y + shift) + (size_t)rows * B - shift;
-    float* f_next = reinterpret_cast<float*>(Xn + shift) - shift;
+    float* f_cur = f32_view(Y, 0);
+    float* f_prev = f32_view(Y, 1);
+    float* f_next = f32_view(Xn, 0);
     for (int s0 = 0; s0 < deg; s0 += table_cap) {
       const int len = std::min(table_cap, deg - s0);
       double* pa = pin + pin_off;
@@ -922,6 +941,59 @@ struct CudaBackend {
       Xn = nn;
     }
     check("filter");
+  }
+  // fp32 correction pass (chfsi_driver.hpp): X += z_deg, z_{k+1} = alpha_kj ((L - c) z_k + r_j) - gamma_kj z_{k-1}, z_0 = 0.
+  // r (fp32) was left in the first half of Y by the last rotate_and_residual; the three z blocks live in the second
+  // half of Y and the two halves of Xn.  al / ga are per column: [M][deg][B].
+  void filter_correction(int deg, const double* al, const double* ga, const double* ce) {
+    const size_t total = (size_t)M * deg * B;
+    // the device tables (alpha, gamma: M * table_cap doubles each) hold M * cap_c * B floats
+    const int cap_c = std::max(1, (int)((size_t)table_cap * 2 / B));
+    float* pin = (float*)g_pin_tables.get(sizeof(float) * 2 * total + sizeof(double) * M);
+    if (!pin) {
+      fail(cudaErrorMemoryAllocation, "pinned tables");
+      return;
+    }
+    double* pc = reinterpret_cast<double*>(pin + 2 * total);
+    memcpy(pc, ce, sizeof(double) * M);
+    fail(cudaMemcpyAsync(center, pc, sizeof(double) * M, cudaMemcpyHostToDevice, stream), "H2D center");
+    const float* r = f32_view(Y, 0);
+    float* z_cur = f32_view(Y, 1);
+    float* z_prev = f32_view(Xn, 0);
+    float* z_next = f32_view(Xn, 1);
+    const double rows = (double)(off_host[M] - off_host[0]);
+    double nnz = 0.0;
+    for (int m = 0; m < M; ++m) nnz += info_host[4 * m];
+    const double step_bytes = 12.0 * nnz + 4.0 * rows + 16.0 * rows + 16.0 * (double)B * rows;
+    g_filter_profile_corr.begin(stream);
+    fail(cudaMemsetAsync(z_cur + (size_t)off_host[0] * B, 0, sizeof(float) * (size_t)rows * B, stream), "zero z");
+    size_t pin_off = 0;
+    float* d_al = reinterpret_cast<float*>(alpha);
+    float* d_ga = reinterpret_cast<float*>(gamma);
+    for (int s0 = 0; s0 < deg; s0 += cap_c) {
+      const int len = std::min(cap_c, deg - s0);
+      float* pa = pin + pin_off;
+      float* pg = pa + (size_t)M * len * B;
+      pin_off += 2 * (size_t)M * len * B;
+      for (int m = 0; m < M; ++m)
+        for (size_t e = 0; e < (size_t)len * B; ++e) {
+          pa[(size_t)m * len * B + e] = (float)al[((size_t)m * deg + s0) * B + e];
+          pg[(size_t)m * len * B + e] = (float)ga[((size_t)m * deg + s0) * B + e];
+        }
+      fail(cudaMemcpyAsync(d_al, pa, sizeof(float) * (size_t)M * len * B, cudaMemcpyHostToDevice, stream), "H2D alpha (columns)");
+      fail(cudaMemcpyAsync(d_ga, pg, sizeof(float) * (size_t)M * len * B, cudaMemcpyHostToDevice, stream), "H2D gamma (columns)");
+      for (int s = 0; s < len; ++s) {
+        const int gs = s0 + s;
+        const bool last = gs == deg - 1;
+        launch_spmm_corr(last, B, g, z_cur, z_prev, r, z_next, X, d_al, d_ga, center, s, len, gs > 0, stream);
+        float* t = z_prev;
+        z_prev = z_cur;
+        z_cur = z_next;
+        z_next = t;
+      }
+    }
+    g_filter_profile_corr.end(stream, (double)deg, (double)deg * step_bytes);
+    check("filter_correction");
   }
   void finalize(const int* fl, const int* sl, const int* no) {
     fail(cudaMemcpyAsync(flags, fl, sizeof(int) * M, cudaMemcpyHostToDevice, stream), "H2D flags");
@@ -995,13 +1067,16 @@ void focusr_profile_reset(void) {
   g_filter_profile.ms = g_filter_profile.launches = g_filter_profile.bytes = 0.0;
   g_filter_profile_lowp.collect();
   g_filter_profile_lowp.ms = g_filter_profile_lowp.launches = g_filter_profile_lowp.bytes = 0.0;
+  g_filter_profile_corr.collect();
+  g_filter_profile_corr.ms = g_filter_profile_corr.launches = g_filter_profile_corr.bytes = 0.0;
 }
 
-void focusr_profile_get_lowp(double* out4_host) {
-  g_filter_profile_lowp.collect();
-  out4_host[0] = g_filter_profile_lowp.ms;
-  out4_host[1] = g_filter_profile_lowp.launches;
-  out4_host[2] = g_filter_profile_lowp.bytes;
+void focusr_profile_get_kind(int kind, double* out4_host) {
+  FilterProfile& p = kind == 0 ? g_filter_profile : (kind == 1 ? g_filter_profile_lowp : g_filter_profile_corr);
+  p.collect();
+  out4_host[0] = p.ms;
+  out4_host[1] = p.launches;
+  out4_host[2] = p.bytes;
   out4_host[3] = 0.0;
 }
 
@@ -1071,8 +1146,9 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
   p.ldv = ldv;
   // 0: probe the top of the spectrum and filter only up to it; > 0: trust the caller; < 0: Gershgorin as is
   p.probe_degree = spectrum_upper_bound == 0.0 ? 10 : 0;
-  p.land = 0.2;
+  p.land = SIZED_PASS_LAND;
   p.lowp_floor = LOWP_FLOOR;
+  p.lowp_aim = LOWP_AIM;
 
   // contiguous runs of meshes with the same symmetry class are solved as one batch
   int rc_all = FB_OK;
@@ -1118,6 +1194,7 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
     FB_CUDA(cudaStreamSynchronize(stream));
     g_filter_profile.collect();
     g_filter_profile_lowp.collect();
+    g_filter_profile_corr.collect();
     for (int m = m0; m < m1; ++m) {
       int* ri = result_i_host + 8 * m;
       ri[0] = results[m].status;
@@ -1289,8 +1366,9 @@ int focusr_eigs_smallest_dist(const int* row_ptr, const int* cols_local, const d
   p.ldv = ldv;
   // 0: probe the top of the spectrum and filter only up to it; > 0: trust the caller; < 0: Gershgorin as is
   p.probe_degree = spectrum_upper_bound == 0.0 ? 10 : 0;
-  p.land = 0.2;
+  p.land = SIZED_PASS_LAND;
   p.lowp_floor = LOWP_FLOOR;
+  p.lowp_aim = LOWP_AIM;
 
   DistCtx d;
   d.comm = g_dist_comm;

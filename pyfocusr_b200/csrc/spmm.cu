@@ -31,7 +31,11 @@ constexpr int SPMM_ROWS_PER_BLOCK = 256;
 // warp's entry range with one coalesced load and distributing it by shuffles (3.1 TB/s), bringing the
 // CTA's window of y rows into shared memory with one TMA bulk copy (k_spmm_staged below: 3.7 TB/s in the
 // filter, 4 CTAs/SM), or blocking the filter over groups of meshes that fit the 126 MB L2 (eigs.cu).
-template <int B, int TPR, int MODE>
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// PF > 0 (focusr_set_tuning(4, PF), b = 16 filter steps only): the CTA asks L2 for the lines it will stream from HBM
+// before it starts walking rows: 1 = its x_prev rows, 2 = + its own y rows, 3 = + its slice of cols / weights.
+template <int B, int TPR, int MODE, int PF = 0>
 __global__ void __launch_bounds__(SPMM_THREADS, (B / (2 * TPR) == 1) ? 8 : ((B / (2 * TPR) == 2) ? 6 : 3))
 k_spmm(const int* __restrict__ row_ptr, const int* __restrict__ cols, const double* __restrict__ weights,
        const double* __restrict__ degree, const double* __restrict__ degree_inv,
@@ -49,6 +53,19 @@ k_spmm(const int* __restrict__ row_ptr, const int* __restrict__ cols, const doub
     al = alpha[(size_t)mesh * n_steps + step];
     ga = gamma[(size_t)mesh * n_steps + step];
     cc = center[mesh];
+  }
+  if (PF > 0) {
+    static_assert(PF == 0 || B * 8 == 128, "prefetch variants assume one 128-byte line per row");
+    const int pr = r0 + (int)threadIdx.x;  // SPMM_ROWS_PER_BLOCK == SPMM_THREADS: one row line per thread
+    if (pr < r1) {
+      if (ga != 0.0) prefetch_l2(x_prev + (size_t)pr * B);
+      if (PF >= 2) prefetch_l2(y + (size_t)pr * B);
+    }
+    if (PF >= 3) {
+      const int q0 = row_ptr[r0], q1 = row_ptr[r1];
+      for (int q = q0 + 32 * (int)threadIdx.x; q < q1; q += 32 * SPMM_THREADS) prefetch_l2(cols + q);
+      for (int q = q0 + 16 * (int)threadIdx.x; q < q1; q += 16 * SPMM_THREADS) prefetch_l2(weights + q);
+    }
   }
   const int g = threadIdx.x / TPR, t = threadIdx.x % TPR;
   for (int row = r0 + g; row < r1; row += SPMM_THREADS / TPR) {
@@ -218,6 +235,11 @@ k_spmm_staged(const int* __restrict__ row_ptr, const int* __restrict__ cols, con
   }
 }
 
+// L2 prefetch variants of the b = 16 filter steps (see k_spmm).  Measured on B200, 256 meshes x 15 212 vertices, variants
+// 0/1/2/3: fp64 step 4295 / 4136 / 4070 / 4059 GB/s (the prefetches compete with a memory system that is already
+// busy), fp32 step 4483 / 4521 / 4687 / 4758 GB/s (half the bytes per row: more latency-bound, so asking early pays).
+int g_spmm_prefetch = 0;      // focusr_set_tuning(4, v): fp64 step
+int g_spmm_prefetch_f32 = 3;  // focusr_set_tuning(5, v): fp32 step
 int g_spmm_variant = 0;  // focusr_set_tuning(0, v): 0 = register-capped gather kernel, 1 = TMA-staged window
 int g_mixed_precision = 1;  // focusr_set_tuning(3, v): 1 = early filter passes in fp32 (default), 0 = fp64 throughout
 
@@ -247,7 +269,18 @@ static int launch_spmm_b(int mode, const SpmmGraph& g, const double* y, const do
     FB_COUNT_LAUNCH(1);
     return FB_OK;
   }
-  if (mode == 0)
+  if (mode == 0 && B == 16 && g_spmm_prefetch > 0) {
+    constexpr int BB = B == 16 ? B : 16, TT = B == 16 ? TPR : 8;  // only instantiated for b = 16
+    if (g_spmm_prefetch == 1)
+      k_spmm<BB, TT, 0, 1><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv,
+                                                              g.mesh_off, y, x_prev, out, alpha, gamma, center, step, n_steps);
+    else if (g_spmm_prefetch == 2)
+      k_spmm<BB, TT, 0, 2><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv,
+                                                              g.mesh_off, y, x_prev, out, alpha, gamma, center, step, n_steps);
+    else
+      k_spmm<BB, TT, 0, 3><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv,
+                                                              g.mesh_off, y, x_prev, out, alpha, gamma, center, step, n_steps);
+  } else if (mode == 0)
     k_spmm<B, TPR, 0><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv,
                                                          g.mesh_off, y, x_prev, out, alpha, gamma, center, step, n_steps);
   else if (mode == 1)
@@ -308,7 +341,7 @@ int launch_spmm(int mode, int b, const SpmmGraph& g, const double* y, const doub
 //   IO 2: last step of a pass -- y, x_prev fp32, out is written as fp64.
 // A thread owns B/(4*TPR) float4 slices of a row, so gathers stay 16-byte loads.
 // ---------------------------------------------------------------------------------------------
-template <int B, int TPR, int IO>
+template <int B, int TPR, int IO, int PF = 0>
 __global__ void __launch_bounds__(SPMM_THREADS, (B / (4 * TPR) == 1) ? 8 : ((B / (4 * TPR) == 2) ? 6 : 3))
 k_spmm_f32(const int* __restrict__ row_ptr, const int* __restrict__ cols, const double* __restrict__ weights,
            const double* __restrict__ degree, const double* __restrict__ degree_inv,
@@ -324,6 +357,18 @@ k_spmm_f32(const int* __restrict__ row_ptr, const int* __restrict__ cols, const 
   const float al = (float)alpha[(size_t)mesh * n_steps + step];
   const float ga = (float)gamma[(size_t)mesh * n_steps + step];
   const float cc = (float)center[mesh];
+  if (PF > 0 && IO == 0) {  // same L2 prefetch variants as k_spmm
+    const int pr = r0 + (int)threadIdx.x;
+    if (pr < r1) {
+      if (ga != 0.f) prefetch_l2(x_prev + (size_t)pr * B);
+      if (PF >= 2) prefetch_l2(static_cast<const float*>(y_) + (size_t)pr * B);
+    }
+    if (PF >= 3) {
+      const int q0 = row_ptr[r0], q1 = row_ptr[r1];
+      for (int q = q0 + 32 * (int)threadIdx.x; q < q1; q += 32 * SPMM_THREADS) prefetch_l2(cols + q);
+      for (int q = q0 + 16 * (int)threadIdx.x; q < q1; q += 16 * SPMM_THREADS) prefetch_l2(weights + q);
+    }
+  }
   const int g = threadIdx.x / TPR, t = threadIdx.x % TPR;
   auto load_y = [&](int r, int slice) -> float4 {
     if (IO == 1) {
@@ -382,12 +427,159 @@ k_spmm_f32(const int* __restrict__ row_ptr, const int* __restrict__ cols, const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// fp32 CORRECTION step (chfsi_driver.hpp): z_next = alpha_j ((L - c) z + r_j) - gamma_j z_prev per column j, where
+// r = L x - theta x is the fp64 residual block of the Ritz vectors rounded to fp32, the tables are per column (the
+// polynomial of column j is normalised to 1 at theta_j) and z starts at 0, so that p(L) x = x + z.  z is as small as
+// the error of x: fp32 rounding here is relative to that error.  LAST: the fp64 block is updated, x += z_next.
+// Algorithmic bytes per step and mesh: 12 nnz + 20 N + 16 b N (z, z_prev, r read; z_next written).
+// ---------------------------------------------------------------------------------------------
+template <int B, int TPR, int LAST>
+__global__ void __launch_bounds__(SPMM_THREADS, (B / (4 * TPR) == 1) ? 8 : ((B / (4 * TPR) == 2) ? 6 : 3))
+k_spmm_corr(const int* __restrict__ row_ptr, const int* __restrict__ cols, const double* __restrict__ weights,
+            const double* __restrict__ degree, const double* __restrict__ degree_inv,
+            const int* __restrict__ mesh_off, const float* __restrict__ z, const float* __restrict__ z_prev,
+            const float* __restrict__ r, float* __restrict__ z_next, double* __restrict__ x,
+            const float* __restrict__ alpha_c, const float* __restrict__ gamma_c, const double* __restrict__ center,
+            int step, int n_steps, int has_prev, int prefetch) {
+  constexpr int VPT = B / (4 * TPR);
+  static_assert(VPT * 4 * TPR == B, "block size must be a multiple of 4*TPR");
+  const int mesh = blockIdx.y;
+  const int r0 = mesh_off[mesh] + blockIdx.x * SPMM_ROWS_PER_BLOCK;
+  const int r1 = min(mesh_off[mesh + 1], r0 + SPMM_ROWS_PER_BLOCK);
+  if (r0 >= r1) return;
+  if (prefetch) {  // ask L2 early for what this CTA streams from HBM (pays for the fp32 steps, see g_spmm_prefetch_f32)
+    const int pr = r0 + (int)threadIdx.x;
+    if (pr < r1) {
+      if (has_prev) prefetch_l2(z_prev + (size_t)pr * B);
+      prefetch_l2(z + (size_t)pr * B);
+      prefetch_l2(r + (size_t)pr * B);
+    }
+    const int q0 = row_ptr[r0], q1 = row_ptr[r1];
+    for (int q = q0 + 32 * (int)threadIdx.x; q < q1; q += 32 * SPMM_THREADS) prefetch_l2(cols + q);
+    for (int q = q0 + 16 * (int)threadIdx.x; q < q1; q += 16 * SPMM_THREADS) prefetch_l2(weights + q);
+  }
+  const float cc = (float)center[mesh];
+  const int g = threadIdx.x / TPR, t = threadIdx.x % TPR;
+  const float4* al_p = reinterpret_cast<const float4*>(alpha_c + ((size_t)mesh * n_steps + step) * B);
+  const float4* ga_p = reinterpret_cast<const float4*>(gamma_c + ((size_t)mesh * n_steps + step) * B);
+  for (int row = r0 + g; row < r1; row += SPMM_THREADS / TPR) {
+    float4 acc[VPT];
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int p0 = row_ptr[row], p1 = row_ptr[row + 1];
+#pragma unroll 4
+    for (int p = p0; p < p1; ++p) {
+      const int c = cols[p];
+      const float w = (float)weights[p];
+      const float4* src = reinterpret_cast<const float4*>(z + (size_t)c * B);
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) {
+        const float4 a = __ldg(src + t + v * TPR);
+        acc[v].x = fmaf(w, a.x, acc[v].x);
+        acc[v].y = fmaf(w, a.y, acc[v].y);
+        acc[v].z = fmaf(w, a.z, acc[v].z);
+        acc[v].w = fmaf(w, a.w, acc[v].w);
+      }
+    }
+    const float d = (float)degree[row];
+    const float di = (float)degree_inv[row];
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      const int slice = t + v * TPR;
+      const float4 zv = __ldg(reinterpret_cast<const float4*>(z + (size_t)row * B) + slice);
+      const float4 rv = __ldg(reinterpret_cast<const float4*>(r + (size_t)row * B) + slice);
+      const float4 al = __ldg(al_p + slice);
+      float4 o;
+      o.x = al.x * ((di * (d * zv.x - acc[v].x) - cc * zv.x) + rv.x);
+      o.y = al.y * ((di * (d * zv.y - acc[v].y) - cc * zv.y) + rv.y);
+      o.z = al.z * ((di * (d * zv.z - acc[v].z) - cc * zv.z) + rv.z);
+      o.w = al.w * ((di * (d * zv.w - acc[v].w) - cc * zv.w) + rv.w);
+      if (has_prev) {
+        const float4 ga = __ldg(ga_p + slice);
+        const float4 pv = __ldg(reinterpret_cast<const float4*>(z_prev + (size_t)row * B) + slice);
+        o.x -= ga.x * pv.x;
+        o.y -= ga.y * pv.y;
+        o.z -= ga.z * pv.z;
+        o.w -= ga.w * pv.w;
+      }
+      if (LAST) {
+        double2* xo = reinterpret_cast<double2*>(x + (size_t)row * B) + 2 * slice;
+        double2 a = xo[0], b = xo[1];
+        a.x += (double)o.x;
+        a.y += (double)o.y;
+        b.x += (double)o.z;
+        b.y += (double)o.w;
+        xo[0] = a;
+        xo[1] = b;
+      } else {
+        reinterpret_cast<float4*>(z_next + (size_t)row * B)[slice] = o;
+      }
+    }
+  }
+}
+
+template <int B, int TPR>
+static int launch_spmm_corr_b(bool last, const SpmmGraph& g, const float* z, const float* z_prev, const float* r,
+                              float* z_next, double* x, const float* alpha_c, const float* gamma_c, const double* center,
+                              int step, int n_steps, bool has_prev, cudaStream_t stream) {
+  dim3 grid(div_up(g.max_mesh_rows, SPMM_ROWS_PER_BLOCK), g.n_meshes);
+  const int pf = (B == 16 && g_spmm_prefetch_f32 > 0) ? 1 : 0;
+  if (last)
+    k_spmm_corr<B, TPR, 1><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv, g.mesh_off, z,
+                                                              z_prev, r, z_next, x, alpha_c, gamma_c, center, step, n_steps,
+                                                              has_prev ? 1 : 0, pf);
+  else
+    k_spmm_corr<B, TPR, 0><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv, g.mesh_off, z,
+                                                              z_prev, r, z_next, x, alpha_c, gamma_c, center, step, n_steps,
+                                                              has_prev ? 1 : 0, pf);
+  FB_COUNT_LAUNCH(1);
+  return FB_OK;
+}
+
+int launch_spmm_corr(bool last, int b, const SpmmGraph& g, const float* z, const float* z_prev, const float* r, float* z_next,
+                     double* x, const float* alpha_c, const float* gamma_c, const double* center, int step, int n_steps,
+                     bool has_prev, cudaStream_t stream) {
+#define FB_CASE(BB, TT) \
+  case BB:              \
+    return launch_spmm_corr_b<BB, TT>(last, g, z, z_prev, r, z_next, x, alpha_c, gamma_c, center, step, n_steps, has_prev, stream);
+  switch (b) {
+    FB_CASE(8, 2)
+    FB_CASE(16, 4)
+    FB_CASE(24, 2)
+    FB_CASE(32, 4)
+    FB_CASE(40, 2)
+    FB_CASE(48, 4)
+    FB_CASE(56, 2)
+    FB_CASE(64, 4)
+    FB_CASE(72, 2)
+    FB_CASE(80, 4)
+    FB_CASE(88, 2)
+    FB_CASE(96, 4)
+    default:
+      set_error("spmm (fp32 correction): unsupported block size %d (multiples of 8 up to 96)", b);
+      return FB_ERR_UNSUPPORTED;
+  }
+#undef FB_CASE
+}
+
 template <int B, int TPR>
 static int launch_spmm_f32_b(int io, const SpmmGraph& g, const void* y, const float* x_prev, void* out, float* y_copy,
                              const double* alpha, const double* gamma, const double* center, int step, int n_steps,
                              cudaStream_t stream) {
   dim3 grid(div_up(g.max_mesh_rows, SPMM_ROWS_PER_BLOCK), g.n_meshes);
-  if (io == 0)
+  if (io == 0 && B == 16 && g_spmm_prefetch_f32 > 0) {
+    constexpr int BB = B == 16 ? B : 16, TT = B == 16 ? TPR : 4;  // only instantiated for b = 16
+    if (g_spmm_prefetch_f32 == 1)
+      k_spmm_f32<BB, TT, 0, 1><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv, g.mesh_off,
+                                                                  y, x_prev, out, y_copy, alpha, gamma, center, step, n_steps);
+    else if (g_spmm_prefetch_f32 == 2)
+      k_spmm_f32<BB, TT, 0, 2><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv, g.mesh_off,
+                                                                  y, x_prev, out, y_copy, alpha, gamma, center, step, n_steps);
+    else
+      k_spmm_f32<BB, TT, 0, 3><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv, g.mesh_off,
+                                                                  y, x_prev, out, y_copy, alpha, gamma, center, step, n_steps);
+  } else if (io == 0)
     k_spmm_f32<B, TPR, 0><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv, g.mesh_off,
                                                              y, x_prev, out, y_copy, alpha, gamma, center, step, n_steps);
   else if (io == 1)
@@ -636,6 +828,14 @@ int focusr_set_tuning(int key, int value) {
   }
   if (key == 3) {
     fb::g_mixed_precision = value;
+    return 0;
+  }
+  if (key == 4) {
+    fb::g_spmm_prefetch = value;
+    return 0;
+  }
+  if (key == 5) {
+    fb::g_spmm_prefetch_f32 = value;
     return 0;
   }
   fb::set_error("set_tuning: unknown key %d", key);

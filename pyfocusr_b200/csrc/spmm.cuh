@@ -33,6 +33,12 @@ int launch_spmm_f32(int io, int b, const SpmmGraph& g, const void* y, const floa
                     const double* alpha, const double* gamma, const double* center, int step, int n_steps,
                     cudaStream_t stream);
 
+// fp32 correction step: z_next = alpha_j ((L - c) z + r_j) - gamma_j z_prev with per-column tables [mesh][step][b];
+// last: x (fp64) += z_next instead of storing it
+int launch_spmm_corr(bool last, int b, const SpmmGraph& g, const float* z, const float* z_prev, const float* r, float* z_next,
+                     double* x, const float* alpha_c, const float* gamma_c, const double* center, int step, int n_steps,
+                     bool has_prev, cudaStream_t stream);
+
 // row-partitioned multi-GPU: remote columns are gathered from the owning rank's memory (NVLink P2P)
 int launch_spmm_p2p(int mode, int b, const SpmmGraph& g, int n_loc, const double* y, const double* const* peer_y,
                     const int* ghost_peer, const int* ghost_row, const double* x_prev, double* out, const double* alpha,

@@ -33,7 +33,7 @@ struct HostBackend {
   double* out_vals;
   double* out_vecs;
   int ldv;
-  std::vector<double> X, Y, Xn, Z, G, H, W, theta, res;
+  std::vector<double> X, Y, Xn, Z, G, H, W, theta, res, R;
 
   int n_meshes() const { return M; }
   int block() const { return B; }
@@ -138,9 +138,11 @@ struct HostBackend {
           xr[j] = a;
           zr_[j] = b2;
         }
+        if (R.size() != X.size()) R.assign(X.size(), 0.0);
         for (int j = 0; j < B; ++j) {
           x[j] = xr[j];
           const double r = dinv[i] * zr_[j] - theta[(size_t)m * B + j] * xr[j];
+          R[(size_t)i * B + j] = r;  // residual block, consumed by filter_correction
           num[(size_t)m * B + j] += r * r;
           den[(size_t)m * B + j] += xr[j] * xr[j];
         }
@@ -181,6 +183,38 @@ struct HostBackend {
       y.swap(n);
     }
     for (size_t t = 0; t < X.size(); ++t) X[t] = (double)y[t];
+  }
+  // fp32 correction pass as k_spmm_corr runs it: X += z_deg, z_{k+1} = alpha_kj ((L - c) z_k + r_j) - gamma_kj z_{k-1}, z_0 = 0;
+  // z, r, matrix entries and tables rounded to float, float arithmetic; tables are [mesh][step][column]
+  void filter_correction(int deg_m, const double* alpha, const double* gamma, const double* center) {
+    std::vector<float> p(X.size(), 0.f), z(X.size(), 0.f), n(X.size()), acc(B), r(X.size());
+    for (size_t t = 0; t < X.size(); ++t) r[t] = (float)R[t];
+    for (int s = 0; s < deg_m; ++s) {
+      for (int m = 0; m < M; ++m) {
+        const float c = (float)center[m];
+        const double* al = &alpha[((size_t)m * deg_m + s) * B];
+        const double* ga = &gamma[((size_t)m * deg_m + s) * B];
+        for (int i = off[m]; i < off[m + 1]; ++i) {
+          for (int k = 0; k < B; ++k) acc[k] = 0.0f;
+          for (int q = rp[i]; q < rp[i + 1]; ++q) {
+            const float wq = (float)w[q];
+            const float* row = &z[(size_t)cols[q] * B];
+            for (int k = 0; k < B; ++k) acc[k] += wq * row[k];
+          }
+          const float d = (float)deg[i], di = (float)dinv[i];
+          for (int k = 0; k < B; ++k) {
+            const float zv = z[(size_t)i * B + k];
+            const float lz = di * (d * zv - acc[k]);
+            float o = (float)al[k] * ((lz - c * zv) + r[(size_t)i * B + k]);
+            if (s > 0) o -= (float)ga[k] * p[(size_t)i * B + k];
+            n[(size_t)i * B + k] = o;
+          }
+        }
+      }
+      p.swap(z);
+      z.swap(n);
+    }
+    for (size_t t = 0; t < X.size(); ++t) X[t] += (double)z[t];
   }
   void filter(int deg_m, const double* alpha, const double* gamma, const double* center, bool lowp) {
     if (lowp) {
@@ -245,7 +279,7 @@ int hostsim_eigs(const int* rp, const int* cols, const double* w, const double* 
   fb::SolveParams p;
   p.k0 = k0; p.n_needed = n_needed; p.k_buffer = k_buffer; p.min_eig = min_eig; p.tol = tol;
   p.max_outer = max_outer; p.amp_target = amp_target; p.max_degree = max_degree; p.beta = beta > 0.0 ? beta : 2.0; p.ldv = ldv;
-  p.probe_degree = beta == 0.0 ? 10 : 0; p.land = 0.2; p.lowp_floor = g_lowp_floor;
+  p.probe_degree = beta == 0.0 ? 10 : 0; p.land = 0.4; p.lowp_floor = g_lowp_floor; p.lowp_aim = 1.5e-6;
   std::vector<fb::MeshResult> r(n_meshes);
   const int rc = fb::chfsi_solve(be, p, r.data());
   g_last_lowp_degree = r[0].lowp_degree;

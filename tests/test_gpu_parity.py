@@ -220,9 +220,9 @@ def test_eigs_synthetic_and_batch_consistency(torch, synth):
 
 @pytest.mark.parametrize("block", [16, 24, 32, 48])
 def test_eigs_mixed_precision_passes(torch, shipped_meshes, synth, block):
-    """The early filter passes run on fp32 blocks (k_spmm_f32; float4 slices, 2 or 4 threads per row) by default;
-    focusr_set_tuning(3, 0) keeps fp64 throughout.  Both meet the fp64 tolerance and the oracle; the fp32 passes
-    cost no extra filter degree."""
+    """By default the filter passes iterate in fp32 (k_spmm_f32 on fp32 blocks, then k_spmm_corr: the correction form
+    driven by the fp64 residual; float4 slices, 2 or 4 threads per row); focusr_set_tuning(3, 0) keeps fp64 throughout.
+    Both meet the fp64 tolerance and the oracle; the fp32 passes cost no extra filter degree."""
     from pyfocusr_b200 import _lib
     from pyfocusr_b200._device import DeviceGraph
 
@@ -239,8 +239,9 @@ def test_eigs_mixed_precision_passes(torch, shipped_meshes, synth, block):
     (v1, x1, i1), (v0, x0, i0) = out[1], out[0]
     assert i1["status"].tolist() == [0, 0, 0] and i0["status"].tolist() == [0, 0, 0]
     assert np.all(i0["fp32_filter_degree"] == 0)
-    assert np.all(i1["fp32_filter_degree"] > 10) and np.all(i1["fp32_filter_degree"] < 10 + i1["filter_degree"])
+    assert np.all(i1["fp32_filter_degree"] > 10) and np.all(i1["fp32_filter_degree"] <= 10 + i1["filter_degree"])
     assert i1["filter_degree"].max() <= 1.15 * i0["filter_degree"].max()
+    assert i1["outer_iterations"].max() <= i0["outer_iterations"].max() + 1
     assert i1["max_residual"].max() <= 1e-10 and i0["max_residual"].max() <= 1e-10
     assert np.max(np.abs(v1[:, :6] - v0[:, :6]) / v0[:, :6]) <= 1e-9
     for k, m in enumerate(ms):

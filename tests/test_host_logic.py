@@ -106,31 +106,32 @@ def test_driver_symmetric_batch(hostsim, shipped_meshes):
 
 
 def test_driver_mixed_precision_passes(hostsim, shipped_meshes):
-    """A filter pass that is meant to land above the fp32 floor runs with fp32 blocks (the test double rounds as
-    k_spmm_f32 does); the passes that land lower stay fp64, so tolerance, parity and the total degree hold."""
+    """Filter passes in fp32 (the test double rounds as k_spmm_f32 / k_spmm_corr do): a pass that lands above the fp32
+    floor runs on fp32 blocks, the pass that reaches the tolerance runs in fp32 correction form (z = p(L)x - x driven by
+    the fp64 residual).  Rayleigh-Ritz and residuals stay fp64, so tolerance and parity hold, at no extra degree."""
     ms = [shipped_meshes["target_mesh"], fmesh.perturbed_ellipsoid(20, 3)]
     rc0, vals0, vecs0, ri0, offs, sym = _solve(hostsim, ms, 7, 6, 16)
     assert hostsim.hostsim_last_lowp_degree() == 0
-    hostsim.hostsim_set_lowp(2e-6)
+    hostsim.hostsim_set_lowp(1.4e-6)
     try:
         rc, vals, vecs, ri, offs, sym, rd = _solve(hostsim, ms, 7, 6, 16, full=True)
         lowp = hostsim.hostsim_last_lowp_degree()
-        # an aim below the floor would stall: with the floor at 0.5 every pass is predicted lower -> none in fp32
-        hostsim.hostsim_set_lowp(0.5)
-        _solve(hostsim, ms, 7, 6, 16)
-        assert hostsim.hostsim_last_lowp_degree() == 10      # only the spectrum probe
     finally:
         hostsim.hostsim_set_lowp(0.0)
     assert rc == 0 and rc0 == 0 and sym and ri[:, 1].tolist() == [6, 6]
-    assert 10 < lowp < 10 + ri[0, 4]                           # probe + first pass, not the last one
+    assert lowp == 10 + ri[0, 4]                               # probe and every pass ran in an fp32 form
     assert ri[:, 4].max() <= ri0[:, 4].max() * 1.15            # fp32 rounding does not cost filter degree
+    assert ri[:, 3].max() <= ri0[:, 3].max() + 1
     assert rd[:, 0].max() <= 1e-10
     assert np.max(np.abs(vals[:, :6] - vals0[:, :6]) / vals0[:, :6]) <= 1e-9
     for k, m in enumerate(ms):
         _check(m, vals[k, :6], vecs[offs[k]:offs[k + 1], :6], 6)
-    # the non-symmetric path never takes fp32 passes
-    hostsim.hostsim_set_lowp(2e-6)
+    # a tighter tolerance than the correction form's noise allows in one go: more passes, still converges
+    hostsim.hostsim_set_lowp(1.4e-6)
     try:
+        rc, vals, vecs, ri, offs, sym, rd = _solve(hostsim, ms[:1], 7, 6, 16, tol=1e-12, full=True)
+        assert rc == 0 and rd[0, 0] <= 1e-12
+        # the non-symmetric path never takes fp32 passes
         _solve(hostsim, [shipped_meshes["target_mesh_15k"]], 7, 6, 48)
         assert hostsim.hostsim_last_lowp_degree() == 0
     finally:
