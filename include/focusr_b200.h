@@ -97,9 +97,9 @@ int focusr_gather_rows(const double* in, const long long* idx, const int* idx_ba
  * block_size, symmetric, filter steps that ran in fp32 (of the total, plus the probe's)};
  * result_d_host [n_meshes][2]: {max_residual, upper edge of the filter interval}.
  * Mixed precision (symmetric adjacencies): a filter pass that is meant to leave residuals above the fp32 floor
- * (1.4e-6) runs with fp32 vector blocks (k_spmm_f32, 40% fewer bytes per step); a pass that lands lower runs in
+ * (1.4e-6) runs with fp32 vector blocks (k_spmm_f32, 47% fewer bytes per step); a pass that lands lower runs in
  * fp32 CORRECTION form (k_spmm_corr): only z = p(L) x - x is iterated in fp32, driven by the fp64 residual of the
- * Ritz pairs, so rounding is relative to the error of x, and x += z is fp64 (27% fewer bytes per step).
+ * Ritz pairs, so rounding is relative to the error of x, and x += z is fp64 (34% fewer bytes per step).
  * Rayleigh-Ritz and every residual that is tested are fp64, so the returned pairs meet `tol` in fp64 either way.
  * focusr_set_tuning(3, 0) keeps every pass in fp64.
  * status: 0 ok, 1 not converged, 2 block too small, 3 numerical breakdown, 4 ldv too small.
@@ -109,6 +109,10 @@ int focusr_gather_rows(const double* in, const long long* idx, const int* idx_ba
  * underestimate is detected and reverts to 2); < 0 = Gershgorin bound as is.
  * ------------------------------------------------------------------------------------------- */
 size_t focusr_eigs_workspace_bytes(int n_points, int n_meshes, int max_mesh_points, int block_size);
+/* The same plus room for the fp32 copy of the matrix (4 bytes per stored entry, 8 per row) that the fp32 filter passes
+ * read; focusr_eigs_smallest takes fp32 passes only when the workspace it is given is at least this large. */
+size_t focusr_eigs_workspace_bytes_mixed(int n_points, long long nnz, int n_meshes, int max_mesh_points,
+                                         int block_size);
 int focusr_eigs_block_size(int k, int n_k_needed, int k_buffer, int max_one_way, int max_zero_rows);
 int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weights,
                          const double* degree, const double* degree_inv, const double* points,
@@ -165,8 +169,8 @@ int focusr_eigs_smallest_dist(const int* row_ptr, const int* cols_local, const d
  * stream around every filter application since the last reset): out4_host = {milliseconds,
  * launches, algorithmic bytes (12 nnz + 20 N + 24 b N per launch), 0}.  bench.py's roofline line.
  * focusr_profile_get counts the fp64 steps (k_spmm); focusr_profile_get_kind(kind, ...) the steps of one kind:
- * 0 = fp64, 1 = fp32 (k_spmm_f32: 12 nnz + 20 N + 12 b N per launch), 2 = fp32 correction form (k_spmm_corr:
- * 12 nnz + 20 N + 16 b N per launch); reset clears all three. */
+ * 0 = fp64, 1 = fp32 (k_spmm_f32: 8 nnz + 12 N + 12 b N per launch), 2 = fp32 correction form (k_spmm_corr:
+ * 8 nnz + 12 N + 16 b N per launch); reset clears all three. */
 void focusr_profile_reset(void);
 void focusr_profile_get(double* out4_host);
 void focusr_profile_get_kind(int kind, double* out4_host);

@@ -129,7 +129,7 @@ class DeviceGraph:
         while True:
             vals = torch.zeros((m, ldv_use), dtype=torch.float64, device=self.device)
             vecs = torch.zeros((n, ldv_use), dtype=torch.float64, device=self.device)
-            ws_bytes = int(lib.focusr_eigs_workspace_bytes(n, m, self.max_mesh_points, b))
+            ws_bytes = int(lib.focusr_eigs_workspace_bytes_mixed(n, int(self.nnz), m, self.max_mesh_points, b))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
             try:
                 _lib.call("focusr_eigs_smallest", _lib.ptr(self.row_ptr), _lib.ptr(self.cols), _lib.ptr(self.weights),

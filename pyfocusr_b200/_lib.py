@@ -31,6 +31,7 @@ SIGNATURES = {
     "focusr_mean_filter_meshes": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
     "focusr_gather_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "focusr_eigs_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "focusr_eigs_workspace_bytes_mixed": (_sz, [_i, C.c_longlong, _i, _i, _i]),
     "focusr_eigs_block_size": (_i, [_i, _i, _i, _i, _i]),
     "focusr_eigs_smallest": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _d, _d, _i, _i, _d,
                                   _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),

@@ -641,7 +641,7 @@ struct CudaBackend {
   bool symmetric() const { return sym; }
   int zero_rows(int m) const { return info_host[4 * m + 2]; }
   // fp32 filter passes: local solves only (the peer-shared blocks of the row-partitioned solve are fp64)
-  bool lowp_available() const { return dist == nullptr && g_mixed_precision != 0; }
+  bool lowp_available() const { return dist == nullptr && g_mixed_precision != 0 && g.weights_f != nullptr; }
 
   // fp32 view number `half` (0 or 1) of an fp64 block, indexed by global row like the block itself
   float* f32_view(double* blk, int half) const {
@@ -862,7 +862,9 @@ struct CudaBackend {
     const double rows = (double)(off_host[M] - off_host[0]);
     double nnz = 0.0;
     for (int m = 0; m < M; ++m) nnz += info_host[4 * m];
-    const double step_bytes = 12.0 * nnz + 4.0 * rows + 16.0 * rows + (lowp ? 12.0 : 24.0) * (double)B * rows;
+    // fp32 passes read the fp32 copy of the matrix (4 + 4 bytes per entry, 8 bytes of (d, 1/d~) per row)
+    const double step_bytes = lowp ? 8.0 * nnz + 4.0 * rows + 8.0 * rows + 12.0 * (double)B * rows
+                                   : 12.0 * nnz + 4.0 * rows + 16.0 * rows + 24.0 * (double)B * rows;
     FilterProfile& prof = lowp ? g_filter_profile_lowp : g_filter_profile;
     prof.begin(stream);
     // fp32 pass: the three fp32 blocks live in the two fp64 blocks that are free during a filter (Y: two of
@@ -964,7 +966,7 @@ struct CudaBackend {
     const double rows = (double)(off_host[M] - off_host[0]);
     double nnz = 0.0;
     for (int m = 0; m < M; ++m) nnz += info_host[4 * m];
-    const double step_bytes = 12.0 * nnz + 4.0 * rows + 16.0 * rows + 16.0 * (double)B * rows;
+    const double step_bytes = 8.0 * nnz + 4.0 * rows + 8.0 * rows + 16.0 * (double)B * rows;
     g_filter_profile_corr.begin(stream);
     fail(cudaMemsetAsync(z_cur + (size_t)off_host[0] * B, 0, sizeof(float) * (size_t)rows * B, stream), "zero z");
     size_t pin_off = 0;
@@ -1092,6 +1094,17 @@ size_t focusr_eigs_workspace_bytes(int n_points, int n_meshes, int max_mesh_poin
   return eigs_ws_layout(n_points, n_meshes, max_mesh_points, block_size, nullptr, nullptr, 0);
 }
 
+// room for the fp32 copy of the matrix (weights: 4 bytes per stored entry; (degree, 1/degree~): 8 bytes per row) at the
+// end of the workspace; focusr_eigs_smallest runs its fp32 filter passes only if the workspace it is given has it
+static size_t eigs_f32_matrix_bytes(long long nnz, int n_points) {
+  return align_up(sizeof(float) * (size_t)nnz) + align_up(sizeof(float2) * (size_t)n_points) + 256;
+}
+
+size_t focusr_eigs_workspace_bytes_mixed(int n_points, long long nnz, int n_meshes, int max_mesh_points, int block_size) {
+  return eigs_ws_layout(n_points, n_meshes, max_mesh_points, block_size, nullptr, nullptr, 0) +
+         eigs_f32_matrix_bytes(nnz, n_points);
+}
+
 int focusr_eigs_block_size(int k, int n_k_needed, int k_buffer, int max_one_way, int max_zero_rows) {
   // pinned pairs needed if the null space is {constant} + zero rows
   int k_cur = k;
@@ -1150,6 +1163,29 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
   p.lowp_floor = LOWP_FLOOR;
   p.lowp_aim = LOWP_AIM;
 
+  // fp32 copy of the matrix for the fp32 filter passes, at the end of the workspace if it has the room
+  // (focusr_eigs_workspace_bytes_mixed); without it every pass is fp64
+  float* wf = nullptr;
+  float2* ddi = nullptr;
+  size_t ws_main = workspace_bytes;
+  {
+    long long nnz_total = 0;
+    bool any_sym = false;
+    for (int m = 0; m < n_meshes; ++m) {
+      nnz_total += mesh_info_host[4 * m];
+      any_sym = any_sym || mesh_info_host[4 * m + 1] == 0;
+    }
+    const size_t extra = eigs_f32_matrix_bytes(nnz_total, n_points);
+    const size_t base = eigs_ws_layout(n_points, n_meshes, max_rows, B, nullptr, nullptr, 0);
+    if (any_sym && g_mixed_precision != 0 && workspace_bytes >= base + extra) {
+      ws_main = workspace_bytes - extra;
+      char* tail = reinterpret_cast<char*>(workspace) + ws_main;
+      tail += (256 - (reinterpret_cast<uintptr_t>(tail) & 255)) & 255;
+      wf = reinterpret_cast<float*>(tail);
+      ddi = reinterpret_cast<float2*>(tail + align_up(sizeof(float) * (size_t)nnz_total));
+      launch_matrix_f32(weights, degree, degree_inv, nnz_total, n_points, wf, ddi, stream);
+    }
+  }
   // contiguous runs of meshes with the same symmetry class are solved as one batch
   int rc_all = FB_OK;
   std::vector<MeshResult> results(n_meshes);
@@ -1161,14 +1197,16 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
     const int M = m1 - m0;
     CudaBackend be;
     be.g = SpmmGraph{row_ptr, cols, weights, degree, degree_inv, nullptr, M, 0};
+    be.g.weights_f = wf;
+    be.g.ddi_f = ddi;
     int run_max = 0;
     for (int m = m0; m < m1; ++m)
       run_max = std::max(run_max, mesh_point_off_host[m + 1] - mesh_point_off_host[m]);
     be.g.max_mesh_rows = run_max;
     const int run_rows = mesh_point_off_host[m1] - mesh_point_off_host[m0];
-    const size_t need = eigs_ws_layout(run_rows, M, run_max, B, &be, workspace, workspace_bytes);
-    if (need > workspace_bytes) {
-      set_error("eigs: workspace too small (%zu < %zu)", workspace_bytes, need);
+    const size_t need = eigs_ws_layout(run_rows, M, run_max, B, &be, workspace, ws_main);
+    if (need > ws_main) {
+      set_error("eigs: workspace too small (%zu < %zu)", ws_main, need);
       return FB_ERR_WORKSPACE;
     }
     // X/Y/Xn index rows globally: shift the base so that row r of the batch maps into the run's block

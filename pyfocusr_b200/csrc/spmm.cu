@@ -240,6 +240,7 @@ k_spmm_staged(const int* __restrict__ row_ptr, const int* __restrict__ cols, con
 // busy), fp32 step 4483 / 4521 / 4687 / 4758 GB/s (half the bytes per row: more latency-bound, so asking early pays).
 int g_spmm_prefetch = 0;      // focusr_set_tuning(4, v): fp64 step
 int g_spmm_prefetch_f32 = 3;  // focusr_set_tuning(5, v): fp32 step
+int g_spmm_hint = 0;          // focusr_set_tuning(6, v): streaming cache operators in the fp32 correction step
 int g_spmm_variant = 0;  // focusr_set_tuning(0, v): 0 = register-capped gather kernel, 1 = TMA-staged window
 int g_mixed_precision = 1;  // focusr_set_tuning(3, v): 1 = early filter passes in fp32 (default), 0 = fp64 throughout
 
@@ -331,10 +332,10 @@ int launch_spmm(int mode, int b, const SpmmGraph& g, const double* y, const doub
 
 // ---------------------------------------------------------------------------------------------
 // Mixed-precision filter step: the same fused SpMM + three-term update with the vector blocks stored
-// and updated in fp32 (matrix entries, degree and table values are rounded to fp32 as they are loaded;
-// fmaf throughout).  Used by the driver only for passes that are meant to land above the fp32 floor
+// and updated in fp32 (the matrix comes from its fp32 copy -- k_matrix_f32: weights, (degree, 1/degree~) per row --,
+// table values are rounded as they are loaded; fmaf throughout).  Used by the driver only for passes that are meant to land above the fp32 floor
 // (chfsi_driver.hpp); what is tested and returned is always computed in fp64.  Algorithmic bytes per
-// step and mesh: 12 nnz + 20 N + 12 b N (against 24 b N): 284 N instead of 476 N at b = 16.
+// step and mesh: 8 nnz + 12 N + 12 b N (against 12 nnz + 20 N + 24 b N): 252 N instead of 476 N at b = 16.
 //   IO 0: y, x_prev, out fp32.
 //   IO 1: first step of a pass -- y is the fp64 block; writes out (fp32) and an fp32 copy of y, which
 //         is the next step's x_prev (gamma is 0 at step 0, x_prev is not read).
@@ -343,8 +344,8 @@ int launch_spmm(int mode, int b, const SpmmGraph& g, const double* y, const doub
 // ---------------------------------------------------------------------------------------------
 template <int B, int TPR, int IO, int PF = 0>
 __global__ void __launch_bounds__(SPMM_THREADS, (B / (4 * TPR) == 1) ? 8 : ((B / (4 * TPR) == 2) ? 6 : 3))
-k_spmm_f32(const int* __restrict__ row_ptr, const int* __restrict__ cols, const double* __restrict__ weights,
-           const double* __restrict__ degree, const double* __restrict__ degree_inv,
+k_spmm_f32(const int* __restrict__ row_ptr, const int* __restrict__ cols, const float* __restrict__ weights,
+           const float2* __restrict__ ddi,
            const int* __restrict__ mesh_off, const void* __restrict__ y_, const float* __restrict__ x_prev,
            void* __restrict__ out_, float* __restrict__ y_copy, const double* __restrict__ alpha,
            const double* __restrict__ gamma, const double* __restrict__ center, int step, int n_steps) {
@@ -366,7 +367,7 @@ k_spmm_f32(const int* __restrict__ row_ptr, const int* __restrict__ cols, const 
     if (PF >= 3) {
       const int q0 = row_ptr[r0], q1 = row_ptr[r1];
       for (int q = q0 + 32 * (int)threadIdx.x; q < q1; q += 32 * SPMM_THREADS) prefetch_l2(cols + q);
-      for (int q = q0 + 16 * (int)threadIdx.x; q < q1; q += 16 * SPMM_THREADS) prefetch_l2(weights + q);
+      for (int q = q0 + 32 * (int)threadIdx.x; q < q1; q += 32 * SPMM_THREADS) prefetch_l2(weights + q);
     }
   }
   const int g = threadIdx.x / TPR, t = threadIdx.x % TPR;
@@ -387,7 +388,7 @@ k_spmm_f32(const int* __restrict__ row_ptr, const int* __restrict__ cols, const 
 #pragma unroll 4
     for (int p = p0; p < p1; ++p) {
       const int c = cols[p];
-      const float w = (float)weights[p];
+      const float w = weights[p];
 #pragma unroll
       for (int v = 0; v < VPT; ++v) {
         const float4 a = load_y(c, t + v * TPR);
@@ -397,8 +398,8 @@ k_spmm_f32(const int* __restrict__ row_ptr, const int* __restrict__ cols, const 
         acc[v].w = fmaf(w, a.w, acc[v].w);
       }
     }
-    const float d = (float)degree[row];
-    const float di = (float)degree_inv[row];
+    const float2 dd = ddi[row];
+    const float d = dd.x, di = dd.y;
 #pragma unroll
     for (int v = 0; v < VPT; ++v) {
       const int slice = t + v * TPR;
@@ -432,12 +433,14 @@ k_spmm_f32(const int* __restrict__ row_ptr, const int* __restrict__ cols, const 
 // r = L x - theta x is the fp64 residual block of the Ritz vectors rounded to fp32, the tables are per column (the
 // polynomial of column j is normalised to 1 at theta_j) and z starts at 0, so that p(L) x = x + z.  z is as small as
 // the error of x: fp32 rounding here is relative to that error.  LAST: the fp64 block is updated, x += z_next.
-// Algorithmic bytes per step and mesh: 12 nnz + 20 N + 16 b N (z, z_prev, r read; z_next written).
+// Algorithmic bytes per step and mesh: 8 nnz + 12 N + 16 b N (z, z_prev, r read; z_next written): 316 N at b = 16.
 // ---------------------------------------------------------------------------------------------
-template <int B, int TPR, int LAST>
+// HINT 1 (focusr_set_tuning(6, 1), b = 16): single-use streams (z_prev, r, the matrix, z_next) are accessed with the
+// streaming cache operators so that the gathered rows of z, which are reused, stay in L2.
+template <int B, int TPR, int LAST, int HINT = 0>
 __global__ void __launch_bounds__(SPMM_THREADS, (B / (4 * TPR) == 1) ? 8 : ((B / (4 * TPR) == 2) ? 6 : 3))
-k_spmm_corr(const int* __restrict__ row_ptr, const int* __restrict__ cols, const double* __restrict__ weights,
-            const double* __restrict__ degree, const double* __restrict__ degree_inv,
+k_spmm_corr(const int* __restrict__ row_ptr, const int* __restrict__ cols, const float* __restrict__ weights,
+            const float2* __restrict__ ddi,
             const int* __restrict__ mesh_off, const float* __restrict__ z, const float* __restrict__ z_prev,
             const float* __restrict__ r, float* __restrict__ z_next, double* __restrict__ x,
             const float* __restrict__ alpha_c, const float* __restrict__ gamma_c, const double* __restrict__ center,
@@ -457,7 +460,7 @@ k_spmm_corr(const int* __restrict__ row_ptr, const int* __restrict__ cols, const
     }
     const int q0 = row_ptr[r0], q1 = row_ptr[r1];
     for (int q = q0 + 32 * (int)threadIdx.x; q < q1; q += 32 * SPMM_THREADS) prefetch_l2(cols + q);
-    for (int q = q0 + 16 * (int)threadIdx.x; q < q1; q += 16 * SPMM_THREADS) prefetch_l2(weights + q);
+    for (int q = q0 + 32 * (int)threadIdx.x; q < q1; q += 32 * SPMM_THREADS) prefetch_l2(weights + q);
   }
   const float cc = (float)center[mesh];
   const int g = threadIdx.x / TPR, t = threadIdx.x % TPR;
@@ -470,8 +473,8 @@ k_spmm_corr(const int* __restrict__ row_ptr, const int* __restrict__ cols, const
     const int p0 = row_ptr[row], p1 = row_ptr[row + 1];
 #pragma unroll 4
     for (int p = p0; p < p1; ++p) {
-      const int c = cols[p];
-      const float w = (float)weights[p];
+      const int c = HINT ? __ldcs(cols + p) : cols[p];
+      const float w = HINT ? __ldcs(weights + p) : weights[p];
       const float4* src = reinterpret_cast<const float4*>(z + (size_t)c * B);
 #pragma unroll
       for (int v = 0; v < VPT; ++v) {
@@ -482,13 +485,14 @@ k_spmm_corr(const int* __restrict__ row_ptr, const int* __restrict__ cols, const
         acc[v].w = fmaf(w, a.w, acc[v].w);
       }
     }
-    const float d = (float)degree[row];
-    const float di = (float)degree_inv[row];
+    const float2 dd = ddi[row];
+    const float d = dd.x, di = dd.y;
 #pragma unroll
     for (int v = 0; v < VPT; ++v) {
       const int slice = t + v * TPR;
       const float4 zv = __ldg(reinterpret_cast<const float4*>(z + (size_t)row * B) + slice);
-      const float4 rv = __ldg(reinterpret_cast<const float4*>(r + (size_t)row * B) + slice);
+      const float4* r_p = reinterpret_cast<const float4*>(r + (size_t)row * B) + slice;
+      const float4 rv = HINT ? __ldcs(r_p) : __ldg(r_p);
       const float4 al = __ldg(al_p + slice);
       float4 o;
       o.x = al.x * ((di * (d * zv.x - acc[v].x) - cc * zv.x) + rv.x);
@@ -497,7 +501,8 @@ k_spmm_corr(const int* __restrict__ row_ptr, const int* __restrict__ cols, const
       o.w = al.w * ((di * (d * zv.w - acc[v].w) - cc * zv.w) + rv.w);
       if (has_prev) {
         const float4 ga = __ldg(ga_p + slice);
-        const float4 pv = __ldg(reinterpret_cast<const float4*>(z_prev + (size_t)row * B) + slice);
+        const float4* p_p = reinterpret_cast<const float4*>(z_prev + (size_t)row * B) + slice;
+        const float4 pv = HINT ? __ldcs(p_p) : __ldg(p_p);
         o.x -= ga.x * pv.x;
         o.y -= ga.y * pv.y;
         o.z -= ga.z * pv.z;
@@ -513,7 +518,9 @@ k_spmm_corr(const int* __restrict__ row_ptr, const int* __restrict__ cols, const
         xo[0] = a;
         xo[1] = b;
       } else {
-        reinterpret_cast<float4*>(z_next + (size_t)row * B)[slice] = o;
+        float4* o_p = reinterpret_cast<float4*>(z_next + (size_t)row * B) + slice;
+        if (HINT) __stcs(o_p, o);
+        else *o_p = o;
       }
     }
   }
@@ -525,12 +532,17 @@ static int launch_spmm_corr_b(bool last, const SpmmGraph& g, const float* z, con
                               int step, int n_steps, bool has_prev, cudaStream_t stream) {
   dim3 grid(div_up(g.max_mesh_rows, SPMM_ROWS_PER_BLOCK), g.n_meshes);
   const int pf = (B == 16 && g_spmm_prefetch_f32 > 0) ? 1 : 0;
-  if (last)
-    k_spmm_corr<B, TPR, 1><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv, g.mesh_off, z,
+  if (!last && B == 16 && g_spmm_hint == 1) {
+    constexpr int BB = B == 16 ? B : 16, TT = B == 16 ? TPR : 4;  // only instantiated for b = 16
+    k_spmm_corr<BB, TT, 0, 1><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights_f, g.ddi_f, g.mesh_off, z,
+                                                                 z_prev, r, z_next, x, alpha_c, gamma_c, center, step, n_steps,
+                                                                 has_prev ? 1 : 0, pf);
+  } else if (last)
+    k_spmm_corr<B, TPR, 1><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights_f, g.ddi_f, g.mesh_off, z,
                                                               z_prev, r, z_next, x, alpha_c, gamma_c, center, step, n_steps,
                                                               has_prev ? 1 : 0, pf);
   else
-    k_spmm_corr<B, TPR, 0><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv, g.mesh_off, z,
+    k_spmm_corr<B, TPR, 0><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights_f, g.ddi_f, g.mesh_off, z,
                                                               z_prev, r, z_next, x, alpha_c, gamma_c, center, step, n_steps,
                                                               has_prev ? 1 : 0, pf);
   FB_COUNT_LAUNCH(1);
@@ -563,6 +575,22 @@ int launch_spmm_corr(bool last, int b, const SpmmGraph& g, const float* z, const
 #undef FB_CASE
 }
 
+__global__ void k_matrix_f32(const double* __restrict__ weights, const double* __restrict__ degree,
+                             const double* __restrict__ degree_inv, long long nnz, int n_rows, float* __restrict__ wf,
+                             float2* __restrict__ ddi) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nnz) wf[t] = (float)weights[t];
+  if (t < n_rows) ddi[t] = make_float2((float)degree[t], (float)degree_inv[t]);
+}
+
+int launch_matrix_f32(const double* weights, const double* degree, const double* degree_inv, long long nnz, int n_rows,
+                      float* wf, float2* ddi, cudaStream_t stream) {
+  const long long n = nnz > n_rows ? nnz : n_rows;
+  k_matrix_f32<<<div_up(n, 256), 256, 0, stream>>>(weights, degree, degree_inv, nnz, n_rows, wf, ddi);
+  FB_COUNT_LAUNCH(1);
+  return FB_OK;
+}
+
 template <int B, int TPR>
 static int launch_spmm_f32_b(int io, const SpmmGraph& g, const void* y, const float* x_prev, void* out, float* y_copy,
                              const double* alpha, const double* gamma, const double* center, int step, int n_steps,
@@ -571,22 +599,22 @@ static int launch_spmm_f32_b(int io, const SpmmGraph& g, const void* y, const fl
   if (io == 0 && B == 16 && g_spmm_prefetch_f32 > 0) {
     constexpr int BB = B == 16 ? B : 16, TT = B == 16 ? TPR : 4;  // only instantiated for b = 16
     if (g_spmm_prefetch_f32 == 1)
-      k_spmm_f32<BB, TT, 0, 1><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv, g.mesh_off,
+      k_spmm_f32<BB, TT, 0, 1><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights_f, g.ddi_f, g.mesh_off,
                                                                   y, x_prev, out, y_copy, alpha, gamma, center, step, n_steps);
     else if (g_spmm_prefetch_f32 == 2)
-      k_spmm_f32<BB, TT, 0, 2><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv, g.mesh_off,
+      k_spmm_f32<BB, TT, 0, 2><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights_f, g.ddi_f, g.mesh_off,
                                                                   y, x_prev, out, y_copy, alpha, gamma, center, step, n_steps);
     else
-      k_spmm_f32<BB, TT, 0, 3><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv, g.mesh_off,
+      k_spmm_f32<BB, TT, 0, 3><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights_f, g.ddi_f, g.mesh_off,
                                                                   y, x_prev, out, y_copy, alpha, gamma, center, step, n_steps);
   } else if (io == 0)
-    k_spmm_f32<B, TPR, 0><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv, g.mesh_off,
+    k_spmm_f32<B, TPR, 0><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights_f, g.ddi_f, g.mesh_off,
                                                              y, x_prev, out, y_copy, alpha, gamma, center, step, n_steps);
   else if (io == 1)
-    k_spmm_f32<B, TPR, 1><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv, g.mesh_off,
+    k_spmm_f32<B, TPR, 1><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights_f, g.ddi_f, g.mesh_off,
                                                              y, x_prev, out, y_copy, alpha, gamma, center, step, n_steps);
   else
-    k_spmm_f32<B, TPR, 2><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv, g.mesh_off,
+    k_spmm_f32<B, TPR, 2><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights_f, g.ddi_f, g.mesh_off,
                                                              y, x_prev, out, y_copy, alpha, gamma, center, step, n_steps);
   FB_COUNT_LAUNCH(1);
   return FB_OK;
@@ -836,6 +864,10 @@ int focusr_set_tuning(int key, int value) {
   }
   if (key == 5) {
     fb::g_spmm_prefetch_f32 = value;
+    return 0;
+  }
+  if (key == 6) {
+    fb::g_spmm_hint = value;
     return 0;
   }
   fb::set_error("set_tuning: unknown key %d", key);

@@ -13,6 +13,9 @@ struct SpmmGraph {
   const int* mesh_off;  // device [n_meshes + 1]
   int n_meshes;
   int max_mesh_rows;
+  // fp32 copy of the matrix for the fp32 filter steps (k_matrix_f32): weights, and (degree, 1/degree~) per row
+  const float* weights_f = nullptr;
+  const float2* ddi_f = nullptr;
 };
 
 bool spmm_block_supported(int b);
@@ -27,6 +30,10 @@ extern int g_mixed_precision;  // focusr_set_tuning(3, v): fp32 early filter pas
 int launch_spmm(int mode, int b, const SpmmGraph& g, const double* y, const double* x_prev, double* out,
                 const double* alpha, const double* gamma, const double* center, int step, int n_steps,
                 cudaStream_t stream);
+
+// fp32 copy of the matrix: wf[p] = (float)weights[p], ddi[i] = ((float)degree[i], (float)degree_inv[i])
+int launch_matrix_f32(const double* weights, const double* degree, const double* degree_inv, long long nnz, int n_rows,
+                      float* wf, float2* ddi, cudaStream_t stream);
 
 // filter step on fp32 blocks (io 0), entering from (io 1) / returning to (io 2) the fp64 block; see spmm.cu
 int launch_spmm_f32(int io, int b, const SpmmGraph& g, const void* y, const float* x_prev, void* out, float* y_copy,
