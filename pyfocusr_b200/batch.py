@@ -13,6 +13,7 @@ Mesh order inside the batch graph: targets 0..P-1, then sources 0..P-1.
 from __future__ import annotations
 
 import os
+import threading
 
 import numpy as np
 
@@ -53,6 +54,8 @@ class SpectralBatch:
                                non_rigid_max_iterations=non_rigid_max_iterations, non_rigid_tolerance=non_rigid_tolerance,
                                non_rigid_alpha=non_rigid_alpha, non_rigid_beta=non_rigid_beta,
                                non_rigid_n_eigens=non_rigid_n_eigens)
+        self._tls = threading.local()
+        self._pool = None
         self.smooth_l2_bytes = 0  # > 0: smoothing runs group by group of meshes that fit L2 (see DeviceGraph.mean_filter)
         # The smoothing of the target vertices (graph.py:349-354, 300 passes) depends only on the target graphs, not on
         # the spectral stages: with overlap_smoothing it is enqueued on a second CUDA stream right after the Laplacian
@@ -102,9 +105,9 @@ class SpectralBatch:
         smoothed_t, side = None, None
         if self.overlap_smoothing:
             main = torch.cuda.current_stream()
-            if getattr(self, "_side_stream", None) is None:  # one stream for the life of the object: the caching
-                self._side_stream = torch.cuda.Stream(device=g.device)  # allocator keeps a pool per stream
-            side = self._side_stream
+            if getattr(self._tls, "side_stream", None) is None:  # one stream per host thread for the life of the object:
+                self._tls.side_stream = torch.cuda.Stream(device=g.device)  # the caching allocator keeps a pool per stream
+            side = self._tls.side_stream
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 smoothed_t = g.mean_filter(g.points, self.graph_smoothing_iterations, 0, nt_total, self.smooth_l2_bytes)
@@ -194,6 +197,42 @@ class SpectralBatch:
                     eig_vecs_presort=presort, cpd_idx=cpd_idx, coords_b4_reg=coords_b4_reg)
 
     # ------------------------------------------------------------------------------------------
+    def run_concurrent(self, sub_batches, **kw):
+        """Several independent sub-batches at once, one host thread and one CUDA stream each: ``sub_batches`` is a list
+        of ``(points, tris, mesh_off_host, n_pairs)`` or of dicts of ``run`` keyword arguments.  A batch is a chain of
+        HBM-bound stages (Laplacian, filter steps, smoothing) followed by FP64-ALU / latency-bound ones (eigsort costs,
+        KNN) with a few host visits in between; two sub-batches in flight let one's KNN and host visits hide under the
+        other's filter steps (B200, 128 pairs as 2 x 64: 1186 -> see DESIGN.md).  Results are those of ``run`` on each
+        sub-batch (deterministic kernels, no shared state); returns the list of result dicts in order."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        torch = _lib.require_cuda()
+        jobs = [dict(zip(("points", "tris", "mesh_off_host", "n_pairs"), b)) if not isinstance(b, dict) else dict(b)
+                for b in sub_batches]
+        if len(jobs) == 1:
+            return [self.run(**jobs[0], **kw)]
+        if self._pool is None or self._pool._max_workers < len(jobs):
+            self._pool = ThreadPoolExecutor(max_workers=len(jobs))  # kept: workers own pinned pools and streams
+        main = torch.cuda.current_stream()
+        device = torch.cuda.current_device()
+
+        def work(job):
+            with torch.cuda.device(device):
+                if getattr(self._tls, "stream", None) is None:
+                    self._tls.stream = torch.cuda.Stream(device=device)
+                st = self._tls.stream
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    out = self.run(**job, **kw)
+                return out, st
+
+        results = []
+        for out, st in self._pool.map(work, jobs):
+            main.wait_stream(st)
+            results.append(out)
+        return results
+
+    # ------------------------------------------------------------------------------------------
     def _register_pairs(self, coords, off, P, sizes):
         """focusr.py:537-543 per pair: affine on fresh random subsets, transform all target coordinates, then
         deformable on fresh subsets, transform again.  Returns the index draws [(s_aff, t_aff, s_def, t_def)].
@@ -261,28 +300,29 @@ class SpectralBatch:
                     main.wait_stream(st)
         return draws
 
-    def fetch(self, out, keys=("final_idx", "weighted_avg_transformed_points")):
+    def fetch(self, out, keys=("final_idx", "weighted_avg_transformed_points"), slot=0):
         """Device -> host read-back of the per-vertex results into reusable pinned buffers (one
         asynchronous copy each, then a single synchronisation).  Returns numpy views that stay valid
-        until the next ``fetch``."""
+        until the next ``fetch`` with the same ``slot`` (one slot per sub-batch of ``run_concurrent``)."""
         torch = _lib.require_cuda()
         if not hasattr(self, "_pinned"):
             self._pinned = {}
         res = {}
         for k in keys:
             t = out[k]
-            buf = self._pinned.get(k)
+            buf = self._pinned.get((slot, k))
             if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
                 buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-                self._pinned[k] = buf
+                self._pinned[(slot, k)] = buf
             buf.copy_(t, non_blocking=True)
             res[k] = buf
         torch.cuda.current_stream().synchronize()
         return {k: v.numpy() for k, v in res.items()}
 
     # ------------------------------------------------------------------------------------------
-    def run_meshes(self, targets, sources, **kw):
-        """Convenience: lists of PolyData-like meshes (``.points``, ``.tris``)."""
+    @staticmethod
+    def pack_meshes(targets, sources):
+        """Lists of PolyData-like meshes (``.points``, ``.tris``) -> ``(points, tris, mesh_off_host, n_pairs)`` of ``run``."""
         torch = _lib.require_cuda()
         meshes = list(targets) + list(sources)
         sizes = [m.points.shape[0] for m in meshes]
@@ -291,4 +331,9 @@ class SpectralBatch:
         pts = torch.from_numpy(np.ascontiguousarray(np.concatenate([m.points for m in meshes])))
         tris = torch.from_numpy(np.ascontiguousarray(np.concatenate(
             [m.tris.astype(np.int64) + int(o) for m, o in zip(meshes, off[:-1])]).astype(np.int32)))
-        return self.run(pts, tris, off, len(targets), **kw)
+        return pts, tris, off, len(targets)
+
+    def run_meshes(self, targets, sources, **kw):
+        """Convenience: lists of PolyData-like meshes (``.points``, ``.tris``)."""
+        pts, tris, off, n_pairs = self.pack_meshes(targets, sources)
+        return self.run(pts, tris, off, n_pairs, **kw)

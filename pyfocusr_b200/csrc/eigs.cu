@@ -9,6 +9,7 @@
 //   k_rotate  X <- X W (DMMA) fused with the residual norms ||L x - theta x||;
 //   k_write_pairs  unit-norm, sign-fixed eigenvectors into the caller's [n_points][ldv] block.
 // All reductions use fixed trees / fixed chunk order: results are bit-reproducible run to run.
+#include <mutex>
 #include <vector>
 
 #include "chfsi_driver.hpp"
@@ -417,13 +418,18 @@ constexpr double LOWP_AIM = 1.5e-6;
 // with 282 / 274 / 269 filter steps.  A miss costs one more (short) pass, never accuracy.
 constexpr double SIZED_PASS_LAND = 0.4;
 
+// Totals are shared (solves may run on several host threads, one stream each); the event pair and the pending
+// bracket belong to the calling thread.
+struct FilterTotals {
+  std::mutex mu;
+  double ms = 0.0, launches = 0.0, bytes = 0.0;
+};
 struct FilterProfile {
-  double ms = 0.0;
-  double launches = 0.0;
-  double bytes = 0.0;
+  FilterTotals* tot;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   bool pending = false;
   double pending_launches = 0.0, pending_bytes = 0.0;
+  explicit FilterProfile(FilterTotals* t) : tot(t) {}
   void begin(cudaStream_t s) {
     if (!e0) {
       cudaEventCreate(&e0);
@@ -442,16 +448,18 @@ struct FilterProfile {
     if (!pending) return;
     float t = 0.f;
     if (cudaEventSynchronize(e1) == cudaSuccess && cudaEventElapsedTime(&t, e0, e1) == cudaSuccess) {
-      ms += t;
-      launches += pending_launches;
-      bytes += pending_bytes;
+      std::lock_guard<std::mutex> lock(tot->mu);
+      tot->ms += t;
+      tot->launches += pending_launches;
+      tot->bytes += pending_bytes;
     }
     pending = false;
   }
 };
-static FilterProfile g_filter_profile;       // fp64 steps (k_spmm<b,.,0>)
-static FilterProfile g_filter_profile_lowp;  // fp32 steps (k_spmm_f32)
-static FilterProfile g_filter_profile_corr;  // fp32 correction steps (k_spmm_corr)
+static FilterTotals g_totals[3];  // fp64 steps (k_spmm<b,.,0>), fp32 steps (k_spmm_f32), fp32 correction steps (k_spmm_corr)
+static thread_local FilterProfile g_filter_profile(&g_totals[0]);
+static thread_local FilterProfile g_filter_profile_lowp(&g_totals[1]);
+static thread_local FilterProfile g_filter_profile_corr(&g_totals[2]);
 
 // focusr_set_tuning(1, MB): L2 budget for blocking the filter over groups of meshes (0 = off)
 // Measured on B200 (gpurun_out/bench_l2_*.log, 128 pairs): 0 -> 641 pairs/s, 64 MB -> 548, 32 MB -> 341: groups
@@ -1066,29 +1074,27 @@ extern "C" {
 
 void focusr_profile_reset(void) {
   g_filter_profile.collect();
-  g_filter_profile.ms = g_filter_profile.launches = g_filter_profile.bytes = 0.0;
   g_filter_profile_lowp.collect();
-  g_filter_profile_lowp.ms = g_filter_profile_lowp.launches = g_filter_profile_lowp.bytes = 0.0;
   g_filter_profile_corr.collect();
-  g_filter_profile_corr.ms = g_filter_profile_corr.launches = g_filter_profile_corr.bytes = 0.0;
+  for (FilterTotals& t : g_totals) {
+    std::lock_guard<std::mutex> lock(t.mu);
+    t.ms = t.launches = t.bytes = 0.0;
+  }
 }
 
 void focusr_profile_get_kind(int kind, double* out4_host) {
-  FilterProfile& p = kind == 0 ? g_filter_profile : (kind == 1 ? g_filter_profile_lowp : g_filter_profile_corr);
-  p.collect();
-  out4_host[0] = p.ms;
-  out4_host[1] = p.launches;
-  out4_host[2] = p.bytes;
+  g_filter_profile.collect();
+  g_filter_profile_lowp.collect();
+  g_filter_profile_corr.collect();
+  FilterTotals& t = g_totals[kind == 0 ? 0 : (kind == 1 ? 1 : 2)];
+  std::lock_guard<std::mutex> lock(t.mu);
+  out4_host[0] = t.ms;
+  out4_host[1] = t.launches;
+  out4_host[2] = t.bytes;
   out4_host[3] = 0.0;
 }
 
-void focusr_profile_get(double* out4_host) {
-  g_filter_profile.collect();
-  out4_host[0] = g_filter_profile.ms;
-  out4_host[1] = g_filter_profile.launches;
-  out4_host[2] = g_filter_profile.bytes;
-  out4_host[3] = 0.0;
-}
+void focusr_profile_get(double* out4_host) { focusr_profile_get_kind(0, out4_host); }
 
 size_t focusr_eigs_workspace_bytes(int n_points, int n_meshes, int max_mesh_points, int block_size) {
   return eigs_ws_layout(n_points, n_meshes, max_mesh_points, block_size, nullptr, nullptr, 0);

@@ -555,6 +555,36 @@ def test_batch_equals_oracle_and_single(torch, synth):
     assert np.array_equal(o1["weighted_avg_transformed_points"].cpu().numpy(), wavg[: n_s[0]])
 
 
+def test_concurrent_sub_batches_equal_separate_runs(torch, synth, shipped_meshes):
+    """SpectralBatch.run_concurrent (one host thread + CUDA stream per sub-batch, target smoothing on a side stream
+    each) returns exactly what `run` returns for every sub-batch on its own."""
+    from pyfocusr_b200 import SpectralBatch
+
+    kw = dict(n_coords_spectral_ordering=2000, graph_smoothing_iterations=30, projection_smooth_iterations=10)
+    subs = [([synth["ell20a"], synth["ico20"]], [synth["ell20b"], synth["ell20a"]]),
+            ([synth["ell39"]], [synth["ell39"]]),
+            ([shipped_meshes["target_mesh"]], [shipped_meshes["source_mesh"]])]
+    sb = SpectralBatch(**kw)
+    packed = [sb.pack_meshes(t, s) for t, s in subs]
+    rng = np.random.RandomState(5)
+    jobs = []
+    for pts, tris, off, P in packed:
+        sizes = np.diff(off)
+        jobs.append(dict(points=pts, tris=tris, mesh_off_host=off, n_pairs=P, idx_t=sb.sample_indices(sizes[:P], rng),
+                         idx_s=sb.sample_indices(sizes[P:], rng)))
+    keys = ("final_idx", "weighted_avg_transformed_points", "eig_vecs", "smoothed_target_coords", "knn3_dist")
+    for rep in range(2):  # second round: worker threads, streams and pinned pools are reused
+        outs = sb.run_concurrent(jobs)
+        torch.cuda.synchronize()
+        assert len(outs) == 3
+        for job, out in zip(jobs, outs):
+            ref = SpectralBatch(**kw)
+            ref.overlap_smoothing = False
+            alone = ref.run(**job)
+            for k in keys:
+                assert torch.equal(out[k], alone[k]), (rep, k)
+
+
 def test_knn_pruned_is_bit_identical_to_brute_force(torch, shipped_meshes, synth):
     """Morton-tile pruning must change nothing: indices AND distances equal the brute-force kernel's
     (and the oracle's) on surfaces, clustered points with duplicates, and higher dimensions."""
