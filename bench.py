@@ -216,13 +216,16 @@ def run_ours(a):
     ms = timed(step_resident, a.steps)
     launches = _lib.launch_count() - l0
     ms_kernels, kernel_pass = ms, "the timed region"
-    if S > 1:
-        # with several sub-batches in flight the launches of different streams interleave and a kernel's duration is not
-        # defined; the per-kernel numbers (roofline) come from the same K steps run again right away, still under the clock
-        # sampler, with the sub-batches one after the other -- same launches, same sizes, nothing else on the GPU
+    if S > 1 or sb.overlap_smoothing:
+        # with several streams in flight (sub-batches, the smoothing side stream) launches interleave and a kernel's
+        # duration is not defined; the per-kernel numbers (roofline) come from the same K steps run again right away,
+        # still under the clock sampler, one stream only: sub-batches one after the other, smoothing in line -- same
+        # launches, same sizes, nothing else on the GPU
         lib.focusr_profile_reset()
+        ov, sb.overlap_smoothing = sb.overlap_smoothing, False
         ms_kernels = timed(lambda: [sb.run(**job) for job in jobs], a.steps)
-        kernel_pass = "a second pass of the same %d steps with the sub-batches one after the other (%.1f ms per step)" % (
+        sb.overlap_smoothing = ov
+        kernel_pass = "a second pass of the same %d steps on one stream (sub-batches one after the other, smoothing in line: %.1f ms per step)" % (
             a.steps, ms_kernels / a.steps)
     prof = np.zeros(4)
     lib.focusr_profile_get(prof.ctypes.data)
