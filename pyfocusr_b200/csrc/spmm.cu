@@ -240,6 +240,10 @@ k_spmm_staged(const int* __restrict__ row_ptr, const int* __restrict__ cols, con
 // busy), fp32 step 4483 / 4521 / 4687 / 4758 GB/s (half the bytes per row: more latency-bound, so asking early pays).
 int g_spmm_prefetch = 0;      // focusr_set_tuning(4, v): fp64 step
 int g_spmm_prefetch_f32 = 3;  // focusr_set_tuning(5, v): fp32 step
+// focusr_set_tuning(7, v): resident CTAs per SM the correction step is compiled for (0 = 8 at 32 registers; 6 -> 40, 5 -> 48
+// registers).  Measured on B200 (128 pairs per launch): 5032 / 4978 / 4701 GB/s for 8 / 6 / 5 -- occupancy wins again.
+// focusr_set_tuning(6, 1) (streaming cache operators on the single-use streams): 0.252 ms against 0.2445 ms per launch.
+int g_spmm_minb = 0;
 int g_spmm_hint = 0;          // focusr_set_tuning(6, v): streaming cache operators in the fp32 correction step
 int g_spmm_variant = 0;  // focusr_set_tuning(0, v): 0 = register-capped gather kernel, 1 = TMA-staged window
 int g_mixed_precision = 1;  // focusr_set_tuning(3, v): 1 = early filter passes in fp32 (default), 0 = fp64 throughout
@@ -437,8 +441,8 @@ k_spmm_f32(const int* __restrict__ row_ptr, const int* __restrict__ cols, const 
 // ---------------------------------------------------------------------------------------------
 // HINT 1 (focusr_set_tuning(6, 1), b = 16): single-use streams (z_prev, r, the matrix, z_next) are accessed with the
 // streaming cache operators so that the gathered rows of z, which are reused, stay in L2.
-template <int B, int TPR, int LAST, int HINT = 0>
-__global__ void __launch_bounds__(SPMM_THREADS, (B / (4 * TPR) == 1) ? 8 : ((B / (4 * TPR) == 2) ? 6 : 3))
+template <int B, int TPR, int LAST, int HINT = 0, int MINB = 0>
+__global__ void __launch_bounds__(SPMM_THREADS, MINB ? MINB : ((B / (4 * TPR) == 1) ? 8 : ((B / (4 * TPR) == 2) ? 6 : 3)))
 k_spmm_corr(const int* __restrict__ row_ptr, const int* __restrict__ cols, const float* __restrict__ weights,
             const float2* __restrict__ ddi,
             const int* __restrict__ mesh_off, const float* __restrict__ z, const float* __restrict__ z_prev,
@@ -532,7 +536,17 @@ static int launch_spmm_corr_b(bool last, const SpmmGraph& g, const float* z, con
                               int step, int n_steps, bool has_prev, cudaStream_t stream) {
   dim3 grid(div_up(g.max_mesh_rows, SPMM_ROWS_PER_BLOCK), g.n_meshes);
   const int pf = (B == 16 && g_spmm_prefetch_f32 > 0) ? 1 : 0;
-  if (!last && B == 16 && g_spmm_hint == 1) {
+  if (!last && B == 16 && g_spmm_minb > 0) {  // occupancy A/B (focusr_set_tuning(7, v)): 6 or 5 CTAs per SM instead of 8
+    constexpr int BB = B == 16 ? B : 16, TT = B == 16 ? TPR : 4;
+    if (g_spmm_minb == 6)
+      k_spmm_corr<BB, TT, 0, 0, 6><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights_f, g.ddi_f, g.mesh_off, z,
+                                                                      z_prev, r, z_next, x, alpha_c, gamma_c, center, step, n_steps,
+                                                                      has_prev ? 1 : 0, pf);
+    else
+      k_spmm_corr<BB, TT, 0, 0, 5><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights_f, g.ddi_f, g.mesh_off, z,
+                                                                      z_prev, r, z_next, x, alpha_c, gamma_c, center, step, n_steps,
+                                                                      has_prev ? 1 : 0, pf);
+  } else if (!last && B == 16 && g_spmm_hint == 1) {
     constexpr int BB = B == 16 ? B : 16, TT = B == 16 ? TPR : 4;  // only instantiated for b = 16
     k_spmm_corr<BB, TT, 0, 1><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights_f, g.ddi_f, g.mesh_off, z,
                                                                  z_prev, r, z_next, x, alpha_c, gamma_c, center, step, n_steps,
@@ -868,6 +882,10 @@ int focusr_set_tuning(int key, int value) {
   }
   if (key == 6) {
     fb::g_spmm_hint = value;
+    return 0;
+  }
+  if (key == 7) {
+    fb::g_spmm_minb = value;
     return 0;
   }
   fb::set_error("set_tuning: unknown key %d", key);
