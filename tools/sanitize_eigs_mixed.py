@@ -1,6 +1,7 @@
 """Small eigensolves that reach every form of the filter step (fp32 blocks with fp64 in / out steps, the fp32 correction
 form and its last step, fp64) and the fp32 matrix copy at the workspace tail, in a batch whose symmetric run does not
-start at row 0, for `compute-sanitizer --tool memcheck python tools/sanitize_eigs_mixed.py`."""
+start at row 0.  Written for `compute-sanitizer --tool memcheck python tools/sanitize_eigs_mixed.py`; the sanitizer is closed on
+this GPU pool (gpurun_out/san_memcheck.log), so it serves as a plain smoke run of these paths (gpurun_out/san_plain.log)."""
 import os
 import sys
 
