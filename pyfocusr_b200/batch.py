@@ -226,9 +226,21 @@ class SpectralBatch:
                     out = self.run(**job, **kw)
                 return out, st
 
+        def hand_over(obj):  # results were allocated on the worker's stream and are used on the caller's from here on
+            for v in (obj.values() if isinstance(obj, dict) else vars(obj).values()):
+                if isinstance(v, torch.Tensor) and v.is_cuda:
+                    v.record_stream(main)
+                elif isinstance(v, (tuple, list)):
+                    for w in v:
+                        if isinstance(w, torch.Tensor) and w.is_cuda:
+                            w.record_stream(main)
+
         results = []
         for out, st in self._pool.map(work, jobs):
             main.wait_stream(st)
+            hand_over(out)
+            if out.get("graph") is not None:
+                hand_over(out["graph"])
             results.append(out)
         return results
 
