@@ -138,6 +138,33 @@ def test_driver_mixed_precision_passes(hostsim, shipped_meshes):
         hostsim.hostsim_set_lowp(0.0)
 
 
+def test_driver_mixed_precision_on_rough_anisotropic_and_shuffled_meshes(hostsim):
+    """The fp32 pass logic away from the smooth bench meshes: vertex noise of a quarter edge length, an 8 : 1 : 0.3
+    ellipsoid (poor start block: several short unsettled passes first), a random vertex order, all in one batch and
+    alone with k = 14.  Same answers as fp64, no more than one extra Rayleigh-Ritz step, no extra filter degree to speak of."""
+    rng = np.random.RandomState(0)
+    base = fmesh.perturbed_ellipsoid(14, 7)
+    e = np.linalg.norm(base.points[base.tris[:, 0]] - base.points[base.tris[:, 1]], axis=1).mean()
+    rough = fmesh.PolyData(base.points + rng.standard_normal(base.points.shape) * 0.25 * e, base.tris)
+    thin = fmesh.PolyData(base.points * np.array([8.0, 1.0, 0.3]), base.tris)
+    perm = rng.permutation(base.points.shape[0])
+    shuf = fmesh.PolyData(base.points[perm], np.argsort(perm)[base.tris].astype(base.tris.dtype))
+    for ms, k, b in (([rough, thin, shuf], 7, 16), ([rough], 14, 24)):
+        rc0, vals0, vecs0, ri0, offs, sym = _solve(hostsim, ms, k, k - 1, b)
+        hostsim.hostsim_set_lowp(1.4e-6)
+        try:
+            rc, vals, vecs, ri, offs, sym, rd = _solve(hostsim, ms, k, k - 1, b, full=True)
+            lowp = hostsim.hostsim_last_lowp_degree()
+        finally:
+            hostsim.hostsim_set_lowp(0.0)
+        assert rc == 0 and rc0 == 0 and sym and lowp == 10 + ri[0, 4]
+        assert rd[:, 0].max() <= 1e-10
+        assert ri[:, 3].max() <= ri0[:, 3].max() + 1 and ri[:, 4].max() <= 1.2 * ri0[:, 4].max()
+        assert np.max(np.abs(vals[:, :k - 1] - vals0[:, :k - 1]) / vals0[:, :k - 1]) <= 1e-9
+        for i, m in enumerate(ms):
+            _check(m, vals[i, :k - 1], vecs[offs[i]:offs[i + 1], :k - 1], k - 1)
+
+
 def test_driver_nonsymmetric_with_retry(hostsim, shipped_meshes):
     """15k source: 8 one-way entries (complex eigenvalue pairs), 2 unreferenced vertices -> k=14, 11 pairs."""
     m = shipped_meshes["source_mesh_15k"]
