@@ -9,22 +9,24 @@
 //                                          host complex-Schur if not, see nonsym_host.hpp)
 //     X <- X W, residuals                 (GPU)
 //     X <- p_m(L) X                       (m fused SpMM+axpby Chebyshev steps, GPU: the hot loop)
-// Mixed precision: rounding in a filter step perturbs the block by eps relative to its current size, and what
-// matters is the part of that perturbation outside the wanted subspace, which the remaining steps do not
-// amplify -- so a pass in fp32 can bring residuals down to ~1e-6 (measured floor) but not below.  A pass whose
-// predicted landing stays above `lowp_floor` is therefore run with fp32 blocks (40% fewer bytes per step); the
-// Rayleigh-Ritz steps and every residual that is tested stay fp64.
-// Below that floor fp32 still works in CORRECTION form: with (x_j, theta_j) a Ritz pair and r_j = L x_j - theta_j x_j
-// its fp64 residual, p(L) x_j = x_j + z with z_{k+1} = alpha_kj ((L - c) z_k + r_j) - gamma_kj z_{k-1}, z_0 = 0, when the
-// polynomial of column j is normalised to 1 at theta_j.  z is as small as the error of x_j, so fp32 rounding in z is
-// relative to that error, not to x_j: the pass behaves like the fp64 one down to LOWP_CORR_NOISE times the residual it
-// started from.  Only x_j, r_j and the final x_j + z are fp64.  16 b N vector bytes per step instead of 24 b N.
 // with (g, h) = (D~, 1) for a symmetric adjacency (L is self-adjoint in the D~ inner product, so
 // H is symmetric) and (1, D~^-1) otherwise (Euclidean projection, H general).
 // The filter damps [a, beta], a = largest Ritz value of the block, beta = 2 (Gershgorin bound of
 // the random-walk Laplacian).  Zero-degree rows (unreferenced vertices) are exact null vectors
 // e_i; they are pinned to zero in X (an invariant of every step) and accounted for analytically
 // in the retry count, reproducing `k_final` of SURVEY.md section 7.3-2.
+//
+// Mixed precision: rounding in a filter step perturbs the block by eps relative to its current size, and what
+// matters is the part of that perturbation outside the wanted subspace, which the remaining steps do not
+// amplify -- so a pass in fp32 can bring residuals down to ~1e-6 (measured floor) but not below.  A pass whose
+// predicted landing stays above `lowp_floor` is therefore run with fp32 blocks (47% fewer bytes per step, with the
+// fp32 copy of the matrix); the Rayleigh-Ritz steps and every residual that is tested stay fp64.
+// Below that floor fp32 still works in CORRECTION form: with (x_j, theta_j) a Ritz pair and r_j = L x_j - theta_j x_j
+// its fp64 residual, p(L) x_j = x_j + z with z_{k+1} = alpha_kj ((L - c) z_k + r_j) - gamma_kj z_{k-1}, z_0 = 0, when the
+// polynomial of column j is normalised to 1 at theta_j.  z is as small as the error of x_j, so fp32 rounding in z is
+// relative to that error, not to x_j: the pass behaves like the fp64 one down to LOWP_CORR_NOISE times the residual it
+// started from.  Only x_j, r_j and the final x_j + z are fp64.  16 b N vector bytes per step instead of 24 b N.
+// The driver picks the form per pass (PassKind below); a batch takes one form per pass, the common denominator of its meshes.
 //
 // This header is pure C++ (no CUDA types): the N-sized work is behind the `Backend` concept.
 // The product backend is CudaBackend (eigs.cu); tests/hostsim has a plain-loop backend used
@@ -62,8 +64,8 @@ struct SolveParams {
   int probe_degree;  // > 0: tighten beta per mesh with a top-of-spectrum probe of this many filter steps
                      // (symmetric batches only); 0: filter up to `beta` as given
   double land;       // the sized pass aims at land * tol
-  double lowp_floor; // > 0: a filter pass that is predicted to leave every residual above this value runs with the
-                     // blocks stored and updated in fp32 (symmetric batches on a backend that offers it); 0: fp64 only
+  double lowp_floor; // > 0: fp32 filter passes are allowed (symmetric batches on a backend that offers them); a pass on
+                     // fp32 blocks must be predicted to leave every residual above this value.  0: fp64 only
   double lowp_aim;   // residual a sized plain-fp32 pass aims at (>= lowp_floor), from where the fp32 correction
                      // form can reach the tolerance
 };
