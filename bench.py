@@ -167,7 +167,7 @@ def run_ours(a):
     if os.environ.get("FOCUSR_SMOOTH_L2_MB"):
         sb.smooth_l2_bytes = int(os.environ["FOCUSR_SMOOTH_L2_MB"]) << 20
     rng = np.random.RandomState(rank)
-    jobs, jobs_e2e, h2d, n = [], [], 0, 0
+    jobs, jobs_e2e, h2d, n, f = [], [], 0, 0, 0
     for sidx in range(S):
         ids = my_pairs[sidx * P // S:(sidx + 1) * P // S]
         pts, tris, off, n, f, _ = make_pairs(ids, a.nu)
@@ -293,6 +293,19 @@ def run_ours(a):
                  "filter_share_of_step": sum(st["share_of_step"] or 0.0 for st in stats.values()),
                  "knn_queries_per_s": {"initial_k1_d3": knn_q / (stages["knn_initial"] / 1e3) if stages.get("knn_initial") else None,
                                        "final_k3_d3": knn_q / (stages["knn_final"] / 1e3) if stages.get("knn_final") else None}}
+    # the other two HBM streams of the path by their compulsory bytes over the one-stream stage
+    # times -- Laplacian build (read 24 N + 12 F, write adjacency + degree arrays: 12 nnz + 4 N + 16 N per mesh; the
+    # row sort in between is not counted) and the smoothing passes (12 nnz + 12 N + 48 N per pass and mesh, 3 columns)
+    try:
+        nnz_mesh, meshes = 3.0 * f, 2.0 * P
+        lap_bytes = meshes * (24.0 * n + 12.0 * f + 12.0 * nnz_mesh + 20.0 * n)
+        smooth_bytes = P * (SMOOTH_T + SMOOTH_S) * (12.0 * nnz_mesh + 60.0 * n)
+        secondary["other_hbm_streams"] = {
+            "laplacian_build_gbs": lap_bytes / (stages["laplacian"] / 1e3) / 1e9 if stages.get("laplacian") else None,
+            "smoothing_gbs": smooth_bytes / (stages["smoothing"] / 1e3) / 1e9 if stages.get("smoothing") else None,
+            "smoothing_frac_of_peak": smooth_bytes / (stages["smoothing"] / 1e3) / 1e9 / peak if stages.get("smoothing") else None}
+    except Exception as exc:  # a reporting extra must never cost the bench line
+        secondary["other_hbm_streams"] = {"error": repr(exc)}
     if world == 1 and not a.no_cpu_baseline:
         secondary["widened_rows_ms"] = widened_rows_timing(a.nu)
     cpu = None

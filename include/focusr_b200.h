@@ -180,7 +180,10 @@ void focusr_profile_get_kind(int kind, double* out4_host);
  * key 0: filter-step kernel (0 = register-capped gather kernel, 1 = TMA bulk-staged y window in
  * shared memory, b <= 32);  key 1: L2 budget in MB for blocking the filter over mesh groups (0 = off);
  * key 3: mixed-precision filter passes (1 = on, default; 0 = fp64 throughout);
- * key 4 / key 5: L2 prefetch variant (0..3) of the b = 16 fp64 / fp32 filter step (defaults 0 / 3). */
+ * key 4 / key 5: L2 prefetch variant (0..3) of the b = 16 fp64 / fp32 filter step (defaults 0 / 3);
+ * key 6: 1 = streaming cache operators on the single-use streams of the fp32 correction step (default 0);
+ * key 7: resident CTAs per SM the b = 16 correction step is compiled for (0 = 8, or 6, 5).
+ * The knobs are process-wide and not synchronised: set them before concurrent solves start. */
 int focusr_set_tuning(int key, int value);
 
 /* y = L x for a dense block of n_cols vectors (n_cols a multiple of 8, <= 96), used by tests and

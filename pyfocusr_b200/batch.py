@@ -334,8 +334,12 @@ class SpectralBatch:
     # ------------------------------------------------------------------------------------------
     @staticmethod
     def pack_meshes(targets, sources):
-        """Lists of PolyData-like meshes (``.points``, ``.tris``) -> ``(points, tris, mesh_off_host, n_pairs)`` of ``run``."""
-        torch = _lib.require_cuda()
+        """Lists of PolyData-like meshes (``.points``, ``.tris``) -> ``(points, tris, mesh_off_host, n_pairs)`` of ``run``
+        (host tensors; targets first, then sources; triangle vertex ids made global)."""
+        import torch
+
+        if len(targets) != len(sources) or not targets:
+            raise ValueError("need as many source meshes as target meshes (at least one pair)")
         meshes = list(targets) + list(sources)
         sizes = [m.points.shape[0] for m in meshes]
         off = np.zeros(len(meshes) + 1, dtype=np.int32)

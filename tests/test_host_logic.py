@@ -406,3 +406,23 @@ def test_legacy_vtk_reader_ascii_binary_and_v5_layout(tmp_path, shipped_meshes):
     open(bad, "wb").write(b"not a vtk file\n\n\n\n")
     with pytest.raises(ValueError):
         fmesh.read_vtk_mesh(bad)
+
+
+def test_pack_meshes_offsets_and_global_ids():
+    """SpectralBatch.pack_meshes: targets then sources, triangle ids shifted by each mesh's row offset."""
+    from pyfocusr_b200 import SpectralBatch
+
+    a, b, c = fmesh.icosphere(2), fmesh.icosphere(3), fmesh.perturbed_ellipsoid(2, 1)
+    pts, tris, off, n_pairs = SpectralBatch.pack_meshes([a, b], [c, a])
+    sizes = [m.points.shape[0] for m in (a, b, c, a)]
+    assert n_pairs == 2 and off.dtype == np.int32 and off.tolist() == np.concatenate([[0], np.cumsum(sizes)]).tolist()
+    assert tuple(pts.shape) == (sum(sizes), 3) and str(pts.dtype) == "torch.float64" and str(tris.dtype) == "torch.int32"
+    t = tris.numpy()
+    f0 = 0
+    for m, o in zip((a, b, c, a), off[:-1]):
+        f1 = f0 + m.tris.shape[0]
+        assert np.array_equal(t[f0:f1], m.tris + o)
+        assert np.array_equal(pts.numpy()[o:o + m.points.shape[0]], m.points)
+        f0 = f1
+    with pytest.raises(ValueError):
+        SpectralBatch.pack_meshes([a], [])
