@@ -165,6 +165,23 @@ def test_driver_mixed_precision_on_rough_anisotropic_and_shuffled_meshes(hostsim
             _check(m, vals[i, :k - 1], vecs[offs[i]:offs[i + 1], :k - 1], k - 1)
 
 
+def test_driver_pass_plan_on_a_bench_mesh(hostsim):
+    """The filter degree IS the cost of the eigensolve on the GPU (one launch per degree over the whole batch), so the pass
+    plan on a bench mesh (BASELINE.json configs[2]: nu = 39, 15 212 vertices) is pinned here, where no GPU is needed: probe
+    + 3 Rayleigh-Ritz steps, every filter step in an fp32 form, ~275 steps in all (292 with the first fp64-only driver)."""
+    m = fmesh.perturbed_ellipsoid(39, 0)
+    hostsim.hostsim_set_lowp(1.4e-6)
+    try:
+        rc, vals, vecs, ri, offs, sym, rd = _solve(hostsim, [m], 7, 6, 16, full=True)
+        lowp = hostsim.hostsim_last_lowp_degree()
+    finally:
+        hostsim.hostsim_set_lowp(0.0)
+    assert rc == 0 and sym and ri[0, 1] == 6 and ri[0, 3] == 3
+    assert 240 <= ri[0, 4] <= 285 and lowp == 10 + ri[0, 4]
+    assert rd[0, 0] <= 6e-11 and 1.5 < rd[0, 1] < 1.56        # lands well inside the tolerance; probed spectrum bound
+    _check(m, vals[0, :6], vecs[:, :6], 6)
+
+
 def test_driver_nonsymmetric_with_retry(hostsim, shipped_meshes):
     """15k source: 8 one-way entries (complex eigenvalue pairs), 2 unreferenced vertices -> k=14, 11 pairs."""
     m = shipped_meshes["source_mesh_15k"]
