@@ -453,8 +453,13 @@ int chfsi_solve(BE& be, const SolveParams& p, MeshResult* out) {
       // gamma_kj z_{k-1}, z_0 = 0, r = L x - theta x from the Rayleigh-Ritz step (fp64); tables per column
       alpha.resize((size_t)M * deg * B);
       gamma.resize((size_t)M * deg * B);
-      std::vector<double> ta(deg), tg(deg);
-      for (int m = 0; m < M; ++m)
+      // M * B recurrences of `deg` steps: a few ms on one core for a bench batch, with the GPU waiting -- the meshes are
+      // independent, so one host thread each when compiled with OpenMP (as for the non-symmetric Rayleigh-Ritz above)
+#if defined(_OPENMP)
+#pragma omp parallel for schedule(static) if (M >= 8) num_threads(M < 32 ? M : 32)
+#endif
+      for (int m = 0; m < M; ++m) {
+        std::vector<double> ta(deg), tg(deg);
         for (int j = 0; j < B; ++j) {
           const double thj = std::min(theta[(size_t)m * B + j], last_a[m]);
           cheb_table(last_a[m], thj, beta_m[m], deg, ta.data(), tg.data(), &center[m]);
@@ -463,6 +468,7 @@ int chfsi_solve(BE& be, const SolveParams& p, MeshResult* out) {
             gamma[((size_t)m * deg + s) * B + j] = tg[s];
           }
         }
+      }
       be.filter_correction(deg, alpha.data(), gamma.data(), center.data());
     } else {
       alpha.resize((size_t)M * deg);

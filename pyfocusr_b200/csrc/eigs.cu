@@ -985,6 +985,9 @@ struct CudaBackend {
       float* pa = pin + pin_off;
       float* pg = pa + (size_t)M * len * B;
       pin_off += 2 * (size_t)M * len * B;
+#if defined(_OPENMP)
+#pragma omp parallel for schedule(static) if (M >= 8) num_threads(M < 32 ? M : 32)
+#endif
       for (int m = 0; m < M; ++m)
         for (size_t e = 0; e < (size_t)len * B; ++e) {
           pa[(size_t)m * len * B + e] = (float)al[((size_t)m * deg + s0) * B + e];
