@@ -454,9 +454,10 @@ int chfsi_solve(BE& be, const SolveParams& p, MeshResult* out) {
       alpha.resize((size_t)M * deg * B);
       gamma.resize((size_t)M * deg * B);
       // M * B recurrences of `deg` steps: a few ms on one core for a bench batch, with the GPU waiting -- the meshes are
-      // independent, so one host thread each when compiled with OpenMP (as for the non-symmetric Rayleigh-Ritz above)
+      // independent, so they are spread over a small OpenMP team (8 threads: with one process per GPU and two sub-batches
+      // in flight per process, larger teams would oversubscribe the host)
 #if defined(_OPENMP)
-#pragma omp parallel for schedule(static) if (M >= 8) num_threads(M < 32 ? M : 32)
+#pragma omp parallel for schedule(static) if (M >= 8) num_threads(8)
 #endif
       for (int m = 0; m < M; ++m) {
         std::vector<double> ta(deg), tg(deg);

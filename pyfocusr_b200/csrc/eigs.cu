@@ -986,7 +986,7 @@ struct CudaBackend {
       float* pg = pa + (size_t)M * len * B;
       pin_off += 2 * (size_t)M * len * B;
 #if defined(_OPENMP)
-#pragma omp parallel for schedule(static) if (M >= 8) num_threads(M < 32 ? M : 32)
+#pragma omp parallel for schedule(static) if (M >= 8) num_threads(8)
 #endif
       for (int m = 0; m < M; ++m)
         for (size_t e = 0; e < (size_t)len * B; ++e) {
