@@ -158,7 +158,6 @@ def run_ours(a):
     torch.cuda.set_device(local)
     fdist.init("nccl")
     P = a.pairs_per_gpu
-    S = max(1, min(a.sub_batches, P))
     # pair i of the global batch lives on rank i mod world; no data-path collective.  On a GPU
     # the rank's pairs are processed as S sub-batches in flight at once (SpectralBatch.run_concurrent: one host thread +
     # CUDA stream each), so that the ALU-/latency-bound tail of one (eigsort, KNN) hides under the HBM-bound filter of another
@@ -168,8 +167,9 @@ def run_ours(a):
         sb.smooth_l2_bytes = int(os.environ["FOCUSR_SMOOTH_L2_MB"]) << 20
     rng = np.random.RandomState(rank)
     jobs, jobs_e2e, h2d, n, f = [], [], 0, 0, 0
-    for sidx in range(S):
-        ids = my_pairs[sidx * P // S:(sidx + 1) * P // S]
+    groups = fdist.sub_batches(my_pairs, a.sub_batches)
+    S = len(groups)
+    for ids in groups:
         pts, tris, off, n, f, _ = make_pairs(ids, a.nu)
         pts_pin = torch.from_numpy(pts).pin_memory()
         tris_dev = torch.from_numpy(tris).cuda()

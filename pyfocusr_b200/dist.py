@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import os
 
-__all__ = ["pair_shard", "init", "world", "barrier", "all_reduce_max", "all_reduce_sum", "gather_objects", "finalize"]
+__all__ = ["pair_shard", "sub_batches", "init", "world", "barrier", "all_reduce_max", "all_reduce_sum", "gather_objects", "finalize"]
 
 
 def pair_shard(n_pairs_total, rank, world_size):
@@ -20,6 +20,14 @@ def pair_shard(n_pairs_total, rank, world_size):
     if not (0 <= rank < world_size):
         raise ValueError("rank %d outside world of %d" % (rank, world_size))
     return list(range(rank, n_pairs_total, world_size))
+
+
+def sub_batches(pair_ids, n_sub):
+    """A rank's pair ids as ``n_sub`` contiguous, non-empty, near-equal groups (fewer if there are fewer pairs): the
+    sub-batches ``SpectralBatch.run_concurrent`` keeps in flight on one GPU."""
+    ids = list(pair_ids)
+    n_sub = max(1, min(int(n_sub), len(ids)))
+    return [ids[k * len(ids) // n_sub:(k + 1) * len(ids) // n_sub] for k in range(n_sub)]
 
 
 def world():

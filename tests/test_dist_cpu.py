@@ -58,3 +58,15 @@ def test_pair_shard_single_process_and_errors():
     with pytest.raises(ValueError):
         fdist.pair_shard(4, 2, 2)
     assert fdist.all_reduce_max(3.5) == 3.5 and fdist.gather_objects("x") == ["x"]
+
+
+def test_sub_batches_of_a_rank():
+    sys.path.insert(0, ROOT)
+    from pyfocusr_b200 import dist as fdist
+
+    mine = fdist.pair_shard(1024, 3, 8)
+    for n_sub in (1, 2, 3, 4, 128, 500):
+        groups = fdist.sub_batches(mine, n_sub)
+        assert len(groups) == min(n_sub, 128) and sum(groups, []) == mine          # contiguous, in order, complete
+        assert min(map(len, groups)) >= 1 and max(map(len, groups)) - min(map(len, groups)) <= 1
+    assert fdist.sub_batches([7], 2) == [[7]] and fdist.sub_batches([1, 2, 3], 0) == [[1, 2, 3]]
