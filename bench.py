@@ -163,8 +163,9 @@ def run_ours(a):
     # CUDA stream each), so that the ALU-/latency-bound tail of one (eigsort, KNN) hides under the HBM-bound filter of another
     my_pairs = fdist.pair_shard(P * world, rank, world)
     sb = SpectralBatch(N_SPECTRAL, N_EXTRA, N_SAMPLES, SMOOTH_T, SMOOTH_S, seed=rank)
-    if os.environ.get("FOCUSR_SMOOTH_L2_MB"):
-        sb.smooth_l2_bytes = int(os.environ["FOCUSR_SMOOTH_L2_MB"]) << 20
+    # A/B knobs (per-call options, no process-wide state): FOCUSR_EIGS_OPTS="filter_policy=3,filter_min_blocks=6"
+    if os.environ.get("FOCUSR_EIGS_OPTS"):
+        sb.eigs_options = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in os.environ["FOCUSR_EIGS_OPTS"].split(",") if "=" in kv}
     rng = np.random.RandomState(rank)
     jobs, jobs_e2e, h2d, n, f = [], [], 0, 0, 0
     groups = fdist.sub_batches(my_pairs, a.sub_batches)
@@ -181,9 +182,6 @@ def run_ours(a):
         jobs_e2e.append(dict(points=pts_pin, **common))   # H2D of the vertices inside the timed region
         h2d += pts_pin.numel() * 8
     lib = _lib.load()
-    for kv in os.environ.get("FOCUSR_TUNING", "").split(","):  # A/B knobs, e.g. FOCUSR_TUNING=1=64 (L2 budget MB)
-        if "=" in kv:
-            lib.focusr_set_tuning(int(kv.split("=")[0]), int(kv.split("=")[1]))
 
     barrier = fdist.barrier
 

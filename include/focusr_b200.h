@@ -28,6 +28,10 @@ extern "C" {
 
 typedef void* focusr_stream_t;
 
+/* ints per mesh in `mesh_info`: {nnz(A), one-way entries (A_ij stored, A_ji not), zero-degree rows, non-finite
+ * weights, longest row, 0, 0, 0} */
+#define FOCUSR_MESH_INFO_INTS 8
+
 const char* focusr_last_error(void);
 int focusr_version(void);
 /* kernels launched by this library since load (bench.py's `gpu_launches`) */
@@ -38,8 +42,8 @@ unsigned long long focusr_launch_count(void);
  * Python loop over cells x edges filling a lil_matrix), get_degree_matrix (graph.py:216-219).
  * Output: canonical CSR of the weighted adjacency A (columns ascending, duplicates collapsed),
  * degree d = A.sum(axis=1) (sequential ascending-column sum, bit-identical to scipy) and
- * 1/(d+1e-8).  `cols`/`weights` need capacity 3*n_tris.  `mesh_info` is [n_meshes][4] int:
- * {nnz(A), one-way entries (A_ij stored, A_ji not), zero-degree rows, non-finite weights}.
+ * 1/(d+1e-8).  `cols`/`weights` need capacity 3*n_tris.  `mesh_info` is [n_meshes][FOCUSR_MESH_INFO_INTS] int
+ * (layout above).
  * `points` is [n_points][point_dim]: point_dim = 3 (xyz) by default, or 3 + f when
  * include_features_in_adj_matrix appends f range-scaled node features to the position
  * (graph.py:166-175); the edge weight is 1/||p1 - p2|| over all point_dim coordinates.
@@ -61,26 +65,17 @@ int focusr_laplacian_csr(const int* row_ptr, const int* cols, const double* weig
 
 /* ---------------------------------------------------------------------------------------------
  * K5  Graph.mean_filter_graph (graph.py:320-354): values <- M^iterations values with
- * M = diag(1/(1+d)) (A + I), for rows [row_begin, row_end) of the batch graph (values are
- * indexed by global row).  Accumulation order and rounding reproduce scipy's CSR product
- * bit-for-bit (descending columns, multiply then add).  `scratch` is one more
- * [n_points][n_cols] buffer; the result lands in values_out (values_in is not modified).
+ * M = diag(1/(1+d)) (A + I), for rows [row_begin, row_end) of the batch graph, which must be whole meshes
+ * (values are indexed by global row; values_in is not modified; the result lands in values_out).
+ * Accumulation order and rounding reproduce scipy's CSR product bit-for-bit (descending columns, multiply
+ * then add).  The passes are chained by programmatic dependent launch.  The workspace holds the two ping-pong
+ * iterates (not needed for a single iteration).
  * ------------------------------------------------------------------------------------------- */
+size_t focusr_mean_filter_workspace_bytes(int n_rows, int n_cols);
 int focusr_mean_filter(const int* row_ptr, const int* cols, const double* weights,
                        const double* degree, int row_begin, int row_end, const double* values_in,
-                       double* values_out, double* scratch, int n_cols, int iterations,
-                       focusr_stream_t stream);
-
-/* K5, persistent form: the same smoothing for whole meshes [mesh_begin, mesh_end) of the batch graph with
- * every mesh owned by one 16-CTA thread-block cluster for ALL `iterations` passes (vector and matrix slices in
- * distributed shared memory; one launch, no global traffic inside the loop).  Bit-identical to
- * focusr_mean_filter; measured about as fast (csrc/smooth_cluster.cu has the numbers), so optional.  n_cols 1 or 3; values_in / values_out indexed by global row, values_in not modified.
- * Returns 103 (unsupported) when the form does not apply (other n_cols, meshes too large for shared memory,
- * cluster size unavailable): call focusr_mean_filter instead. */
-int focusr_mean_filter_meshes(const int* row_ptr, const int* cols, const double* weights,
-                              const double* degree, const int* mesh_point_off, int mesh_begin,
-                              int mesh_end, int max_mesh_points, const double* values_in,
-                              double* values_out, int n_cols, int iterations, focusr_stream_t stream);
+                       double* values_out, int n_cols, int iterations, void* workspace,
+                       size_t workspace_bytes, focusr_stream_t stream);
 
 /* out[i][:] = in[idx[i]][:]  (focusr.py:387 `smoothed_target_coords[corresponding_idx, :]`;
  * focusr.py:429-431 nearest-neighbour positions).  `idx_base[i]` (nullable) is added to idx[i]. */
@@ -97,11 +92,11 @@ int focusr_gather_rows(const double* in, const long long* idx, const int* idx_ba
  * block_size, symmetric, filter steps that ran in fp32 (of the total, plus the probe's)};
  * result_d_host [n_meshes][2]: {max_residual, upper edge of the filter interval}.
  * Mixed precision (symmetric adjacencies): a filter pass that is meant to leave residuals above the fp32 floor
- * (1.4e-6) runs with fp32 vector blocks (k_spmm_f32, 47% fewer bytes per step); a pass that lands lower runs in
- * fp32 CORRECTION form (k_spmm_corr): only z = p(L) x - x is iterated in fp32, driven by the fp64 residual of the
+ * (1.4e-6) runs with fp32 vector blocks (k_filter_sell on a sliced-ELL fp32 copy of the matrix, 47% fewer bytes per
+ * step); a pass that lands lower runs in fp32 CORRECTION form: only z = p(L) x - x is iterated in fp32, driven by the fp64 residual of the
  * Ritz pairs, so rounding is relative to the error of x, and x += z is fp64 (34% fewer bytes per step).
  * Rayleigh-Ritz and every residual that is tested are fp64, so the returned pairs meet `tol` in fp64 either way.
- * focusr_set_tuning(3, 0) keeps every pass in fp64.
+ * options->mixed_precision = 0 keeps every pass in fp64.
  * status: 0 ok, 1 not converged, 2 block too small, 3 numerical breakdown, 4 ldv too small.
  * `spectrum_upper_bound`: > 0 = filter up to this caller-guaranteed bound; 0 = start from the
  * Gershgorin bound 2 and, for symmetric adjacencies, tighten it per mesh with a 10-step probe of the
@@ -109,10 +104,23 @@ int focusr_gather_rows(const double* in, const long long* idx, const int* idx_ba
  * underestimate is detected and reverts to 2); < 0 = Gershgorin bound as is.
  * ------------------------------------------------------------------------------------------- */
 size_t focusr_eigs_workspace_bytes(int n_points, int n_meshes, int max_mesh_points, int block_size);
-/* The same plus room for the fp32 copy of the matrix (4 bytes per stored entry, 8 per row) that the fp32 filter passes
- * read; focusr_eigs_smallest takes fp32 passes only when the workspace it is given is at least this large. */
-size_t focusr_eigs_workspace_bytes_mixed(int n_points, long long nnz, int n_meshes, int max_mesh_points,
-                                         int block_size);
+/* The same plus room for the fp32 copy of the matrix that the fp32 filter passes read (sliced-ELL: 8 bytes per padded
+ * entry, `sell_entries_cap` of them = focusr_sell_entries_cap(...); 8 bytes per row); focusr_eigs_smallest takes fp32
+ * passes only when the workspace it is given is at least this large. */
+long long focusr_sell_entries_cap(const int* mesh_point_off_host, const int* mesh_info_host, int n_meshes);
+size_t focusr_eigs_workspace_bytes_mixed(int n_points, long long sell_entries_cap, int n_meshes,
+                                         int max_mesh_points, int block_size);
+/* Per-call options of the eigensolver (NULL = defaults; no process-wide state).  filter_* select the kernel form of
+ * the fp32 filter steps and exist for A/B measurements (csrc/sell.cu has the record). */
+typedef struct focusr_eigs_options {
+  int mixed_precision;   /* 1 (default): fp32 filter passes for symmetric adjacencies; 0: every pass fp64 */
+  int filter_policy;     /* fp32 filter steps: bit 1 (default) = no L1 allocation + L2 evict_first on the single-use
+                            streams, bit 0 = L2 evict_last on the gathered block */
+  int filter_prefetch;   /* 1 (default): the CTA asks L2 early for the lines it will stream */
+  int filter_min_blocks; /* resident CTAs per SM the b = 16 kernels are compiled for: 8 (default), 6 or 5 */
+  int reserved[12];
+} focusr_eigs_options;
+void focusr_eigs_default_options(focusr_eigs_options* options);
 int focusr_eigs_block_size(int k, int n_k_needed, int k_buffer, int max_one_way, int max_zero_rows);
 int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weights,
                          const double* degree, const double* degree_inv, const double* points,
@@ -122,7 +130,7 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
                          double spectrum_upper_bound,
                          double* eig_vals, double* eig_vecs, int ldv, int* result_i_host,
                          double* result_d_host, void* workspace, size_t workspace_bytes,
-                         focusr_stream_t stream);
+                         const focusr_eigs_options* options, focusr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K2, row-partitioned across GPUs (BASELINE.json configs[3]): ONE mesh,
@@ -174,17 +182,6 @@ int focusr_eigs_smallest_dist(const int* row_ptr, const int* cols_local, const d
 void focusr_profile_reset(void);
 void focusr_profile_get(double* out4_host);
 void focusr_profile_get_kind(int kind, double* out4_host);
-
-/* Tuning knobs (experiments and A/B profiling; see the tuning records in csrc/spmm.cu, csrc/eigs.cu).
- * key 2: variant of the persistent cluster smoothing kernel (0..3: threads x gather batch).
- * key 0: filter-step kernel (0 = register-capped gather kernel, 1 = TMA bulk-staged y window in
- * shared memory, b <= 32);  key 1: L2 budget in MB for blocking the filter over mesh groups (0 = off);
- * key 3: mixed-precision filter passes (1 = on, default; 0 = fp64 throughout);
- * key 4 / key 5: L2 prefetch variant (0..3) of the b = 16 fp64 / fp32 filter step (defaults 0 / 3);
- * key 6: 1 = streaming cache operators on the single-use streams of the fp32 correction step (default 0);
- * key 7: resident CTAs per SM the b = 16 correction step is compiled for (0 = 8, or 6, 5).
- * The knobs are process-wide and not synchronised: set them before concurrent solves start. */
-int focusr_set_tuning(int key, int value);
 
 /* y = L x for a dense block of n_cols vectors (n_cols a multiple of 8, <= 96), used by tests and
  * residual checks: y[i][:] = dinv_i (d_i x_i - sum_j w_ij x_j). */

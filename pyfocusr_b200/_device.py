@@ -69,7 +69,7 @@ class DeviceGraph:
         self.weights = torch.empty(max(3 * f, 1), dtype=torch.float64, device=dev)
         self.degree = torch.empty(n, dtype=torch.float64, device=dev)
         self.degree_inv = torch.empty(n, dtype=torch.float64, device=dev)
-        mesh_info = torch.empty((m, 4), dtype=torch.int32, device=dev)
+        mesh_info = torch.empty((m, _lib.MESH_INFO_INTS), dtype=torch.int32, device=dev)
         lib = _lib.load()
         ws_bytes = int(lib.focusr_laplacian_workspace_bytes(n, f))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -77,7 +77,7 @@ class DeviceGraph:
         _lib.call("focusr_laplacian_build", _lib.ptr(ep), int(ep.shape[1]), _lib.ptr(self.tris), n, f, _lib.ptr(self.mesh_off), m,
                   _lib.ptr(self.row_ptr), _lib.ptr(self.cols), _lib.ptr(self.weights), _lib.ptr(self.degree),
                   _lib.ptr(self.degree_inv), _lib.ptr(mesh_info), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
-        # {nnz, one-way entries, zero-degree rows, non-finite weights} per mesh
+        # {nnz, one-way entries, zero-degree rows, non-finite weights, longest row, 0, 0, 0} per mesh
         self.mesh_info_host = np.ascontiguousarray(mesh_info.cpu().numpy())
         self.nnz = int(self.mesh_info_host[:, 0].sum())
         self._lap = None
@@ -111,9 +111,11 @@ class DeviceGraph:
 
     # --- K2 -----------------------------------------------------------------------------------
     def eigs_smallest(self, k, n_k_needed, k_buffer=1, min_eig_val=1e-10, tol=1e-10, max_outer=60,
-                      block_size=0, ldv=None, spectrum_upper_bound=0.0):
+                      block_size=0, ldv=None, spectrum_upper_bound=0.0, options=None):
         """Batched ``recursive_eig``.  Returns ``(vals [M][ldv], vecs [N][ldv], info)`` on the
-        device; ``info`` is a dict of host arrays (``n_found``, ``k_final``, ...)."""
+        device; ``info`` is a dict of host arrays (``n_found``, ``k_final``, ...).  ``options``: an
+        ``_lib.EigsOptions`` (or a dict of its fields); default = the library's defaults."""
+        import ctypes as C
         torch = _torch()
         lib = _lib.load()
         n, m = self.n_points, self.n_meshes
@@ -123,13 +125,17 @@ class DeviceGraph:
         res_i = np.zeros((m, 8), dtype=np.int32)
         res_d = np.zeros((m, 2), dtype=np.float64)
         restarts = 0
+        if isinstance(options, dict):
+            options = _lib.EigsOptions(**options)
+        opt_ptr = C.byref(options) if options is not None else None
+        sell_cap = int(lib.focusr_sell_entries_cap(_lib.ptr(self.mesh_off_host), _lib.ptr(self.mesh_info_host), m))
         # columns of the output block: one retry of the reference's recursion by default; the
         # solver reports status 4 if a mesh needs more and the call is repeated with ldv = block
         ldv_use = int(ldv) if ldv else int(k + k_buffer + n_k_needed)
         while True:
             vals = torch.zeros((m, ldv_use), dtype=torch.float64, device=self.device)
             vecs = torch.zeros((n, ldv_use), dtype=torch.float64, device=self.device)
-            ws_bytes = int(lib.focusr_eigs_workspace_bytes_mixed(n, int(self.nnz), m, self.max_mesh_points, b))
+            ws_bytes = int(lib.focusr_eigs_workspace_bytes_mixed(n, sell_cap, m, self.max_mesh_points, b))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
             try:
                 _lib.call("focusr_eigs_smallest", _lib.ptr(self.row_ptr), _lib.ptr(self.cols), _lib.ptr(self.weights),
@@ -137,7 +143,7 @@ class DeviceGraph:
                           _lib.ptr(self.mesh_off_host), m, _lib.ptr(self.mesh_info_host), int(k), int(n_k_needed),
                           int(k_buffer), float(min_eig_val), float(tol), int(max_outer), b, float(spectrum_upper_bound), _lib.ptr(vals),
                           _lib.ptr(vecs), ldv_use, _lib.ptr(res_i), _lib.ptr(res_d), _lib.ptr(ws), ws_bytes,
-                          _lib.stream_ptr())
+                          opt_ptr, _lib.stream_ptr())
                 break
             except _lib.FocusrB200Error as e:
                 status = int(res_i[:, 0].max()) if e.code < 100 else -1
@@ -191,47 +197,23 @@ class DeviceGraph:
         return out
 
     # --- K5 -----------------------------------------------------------------------------------
-    def mean_filter(self, values, iterations, row_begin=0, row_end=None, l2_group_bytes=0, cluster=False):
-        """values: device [n_points][c] (rows outside the range are ignored).  Returns a new tensor.
-        One launch per pass by default.  ``cluster=True``: when the range covers whole meshes and c is 1 or 3, every
-        mesh runs all its passes inside one thread-block cluster (``focusr_mean_filter_meshes``: one launch,
-        distributed shared memory; bit-identical; measured no faster, see csrc/smooth_cluster.cu).  ``l2_group_bytes`` > 0 (per-pass form only) runs all iterations on one group of
-        whole meshes after the other, each group sized to stay resident in L2 (126 MB on B200)."""
+    def mean_filter(self, values, iterations, row_begin=0, row_end=None):
+        """values: device [n_points][c]; rows [row_begin, row_end) must be whole meshes (rows outside are ignored).
+        Returns a new tensor.  One launch per pass, chained by programmatic dependent launch."""
         torch = _torch()
+        lib = _lib.load()
         row_end = self.n_points if row_end is None else row_end
         c = int(values.shape[1])
         out = torch.empty_like(values)
-        if cluster and c in (1, 3) and iterations >= 1 and not l2_group_bytes:
-            off = self.mesh_off_host
-            mb, me = int(np.searchsorted(off, row_begin)), int(np.searchsorted(off, row_end))
-            if mb < me <= self.n_meshes and off[mb] == row_begin and off[me] == row_end:
-                lib = _lib.load()
-                rc = lib.focusr_mean_filter_meshes(_lib.ptr(self.row_ptr), _lib.ptr(self.cols), _lib.ptr(self.weights),
-                                                   _lib.ptr(self.degree), _lib.ptr(self.mesh_off), mb, me,
-                                                   int(np.max(np.diff(off[mb:me + 1]))), _lib.ptr(values), _lib.ptr(out),
-                                                   c, int(iterations), _lib.stream_ptr())
-                if rc == 0:
-                    return out
-                if rc != 103:  # 103 = the cluster form does not apply here; anything else is an error
-                    raise _lib.FocusrB200Error("focusr_mean_filter_meshes", rc, lib.focusr_last_error().decode("utf-8", "replace"))
-        scratch = torch.empty_like(values)
-        ranges = [(int(row_begin), int(row_end))]
-        if l2_group_bytes and iterations > 1:
-            off = self.mesh_off_host
-            ms = [m for m in range(self.n_meshes) if off[m] >= row_begin and off[m + 1] <= row_end]
-            if ms and off[ms[0]] == row_begin and off[ms[-1] + 1] == row_end:
-                ranges, start, acc = [], ms[0], 0.0
-                for m in ms:
-                    need = 12.0 * self.mesh_info_host[m, 0] + (12.0 + 16.0 * c) * (off[m + 1] - off[m])
-                    if acc > 0 and acc + need > l2_group_bytes:
-                        ranges.append((int(off[start]), int(off[m])))
-                        start, acc = m, 0.0
-                    acc += need
-                ranges.append((int(off[start]), int(row_end)))
-        for r0, r1 in ranges:
-            _lib.call("focusr_mean_filter", _lib.ptr(self.row_ptr), _lib.ptr(self.cols), _lib.ptr(self.weights),
-                      _lib.ptr(self.degree), r0, r1, _lib.ptr(values), _lib.ptr(out), _lib.ptr(scratch),
-                      c, int(iterations), _lib.stream_ptr())
+        off = self.mesh_off_host
+        mb, me = int(np.searchsorted(off, row_begin)), int(np.searchsorted(off, row_end))
+        if not (mb < me <= self.n_meshes and off[mb] == row_begin and off[me] == row_end):
+            raise ValueError("mean_filter: the row range must cover whole meshes")
+        ws_bytes = int(lib.focusr_mean_filter_workspace_bytes(int(row_end - row_begin), c))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        _lib.call("focusr_mean_filter", _lib.ptr(self.row_ptr), _lib.ptr(self.cols), _lib.ptr(self.weights),
+                  _lib.ptr(self.degree), int(row_begin), int(row_end), _lib.ptr(values), _lib.ptr(out),
+                  c, int(iterations), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
         return out
 
 

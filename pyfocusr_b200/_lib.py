@@ -27,14 +27,16 @@ SIGNATURES = {
     "focusr_laplacian_workspace_bytes": (_sz, [_i, _i]),
     "focusr_laplacian_build": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "focusr_laplacian_csr": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "focusr_mean_filter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp]),
-    "focusr_mean_filter_meshes": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
+    "focusr_mean_filter_workspace_bytes": (_sz, [_i, _i]),
+    "focusr_mean_filter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _sz, _vp]),
     "focusr_gather_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "focusr_eigs_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "focusr_sell_entries_cap": (C.c_longlong, [_vp, _vp, _i]),
     "focusr_eigs_workspace_bytes_mixed": (_sz, [_i, C.c_longlong, _i, _i, _i]),
+    "focusr_eigs_default_options": (None, [_vp]),
     "focusr_eigs_block_size": (_i, [_i, _i, _i, _i, _i]),
     "focusr_eigs_smallest": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _d, _d, _i, _i, _d,
-                                  _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
+                                  _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp, _vp]),
     "focusr_dist_unique_id": (_i, [_vp]),
     "focusr_dist_init": (_i, [_vp, _i, _i]),
     "focusr_dist_finalize": (_i, []),
@@ -46,7 +48,6 @@ SIGNATURES = {
     "focusr_eigs_smallest_dist": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, C.c_longlong, C.c_longlong, _vp, _i, _vp,
                                        _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _d, _d, _i, _i, _d, _vp, _vp, _i, _vp,
                                        _vp, _vp, _sz, _vp]),
-    "focusr_set_tuning": (_i, [_i, _i]),
     "focusr_profile_reset": (None, []),
     "focusr_profile_get": (None, [_vp]),
     "focusr_profile_get_kind": (None, [_i, _vp]),
@@ -72,6 +73,24 @@ SIGNATURES = {
     "focusr_cpd_affine_apply": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
     "focusr_cpd_deformable_apply": (_i, [_vp, _i, _vp, _i, _i, _vp, _d, _vp, _vp]),
 }
+
+MESH_INFO_INTS = 8  # FOCUSR_MESH_INFO_INTS: {nnz, one-way entries, zero-degree rows, non-finite weights, longest row, ...}
+
+
+class EigsOptions(C.Structure):
+    """``focusr_eigs_options`` (include/focusr_b200.h): per-call options of the eigensolver; no process-wide state."""
+
+    _fields_ = [("mixed_precision", _i), ("filter_policy", _i), ("filter_prefetch", _i), ("filter_min_blocks", _i),
+                ("reserved", _i * 12)]
+
+    def __init__(self, **kw):
+        super().__init__()
+        load().focusr_eigs_default_options(C.byref(self))
+        for k, v in kw.items():
+            if k not in dict(self._fields_):
+                raise TypeError("unknown eigensolver option %r" % k)
+            setattr(self, k, int(v))
+
 
 _lib = None
 

@@ -56,7 +56,7 @@ class SpectralBatch:
                                non_rigid_n_eigens=non_rigid_n_eigens)
         self._tls = threading.local()
         self._pool = None
-        self.smooth_l2_bytes = 0  # > 0: smoothing runs group by group of meshes that fit L2 (see DeviceGraph.mean_filter)
+        self.eigs_options = None  # _lib.EigsOptions or dict: per-call options of the eigensolver (A/B measurements)
         # The smoothing of the target vertices (graph.py:349-354, 300 passes) depends only on the target graphs, not on
         # the spectral stages: with overlap_smoothing it is enqueued on a second CUDA stream right after the Laplacian
         # build and joined where its result is first read; its CTAs fill the gaps the latency-bound filter steps leave
@@ -110,10 +110,10 @@ class SpectralBatch:
             side = self._tls.side_stream
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                smoothed_t = g.mean_filter(g.points, self.graph_smoothing_iterations, 0, nt_total, self.smooth_l2_bytes)
+                smoothed_t = g.mean_filter(g.points, self.graph_smoothing_iterations, 0, nt_total)
             smoothed_t.record_stream(main)
         vals, vecs, info = g.eigs_smallest(k=n + 1, n_k_needed=n, k_buffer=1, tol=self.tol,
-                                           block_size=self.block_size)
+                                           block_size=self.block_size, options=self.eigs_options)
         n_found = info["n_found"]
         if int(n_found.min()) < n:
             raise RuntimeError("a mesh returned fewer than %d eigenpairs" % n)
@@ -171,12 +171,12 @@ class SpectralBatch:
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
         else:
-            smoothed_t = g.mean_filter(g.points, self.graph_smoothing_iterations, 0, nt_total, self.smooth_l2_bytes)
+            smoothed_t = g.mean_filter(g.points, self.graph_smoothing_iterations, 0, nt_total)
         base_q = torch.repeat_interleave(g.mesh_off[:P], torch.from_numpy(sizes[P:].astype(np.int64)).to(dev)).to(torch.int32)
         staged = torch.empty_like(g.points)
         _lib.call("focusr_gather_rows", _lib.ptr(smoothed_t), _lib.ptr(idx0), _lib.ptr(base_q), g.n_points - nt_total, 3,
                   _lib.ptr(staged[nt_total:]), _lib.stream_ptr())
-        src_proj = g.mean_filter(staged, self.projection_smooth_iterations, nt_total, g.n_points, self.smooth_l2_bytes)
+        src_proj = g.mean_filter(staged, self.projection_smooth_iterations, nt_total, g.n_points)
         mark("smoothing")
         # one k=3 search serves both focusr.py:391-392 (k=1: its first column, same distances and tie
         # rule) and focusr.py:409-413 (k=3)

@@ -104,6 +104,22 @@ inline void cheb_table(double a, double a_low, double beta, int m, double* alpha
   *center = c;
 }
 
+// Column j of the correction pass: cheb_table(a, min(theta_j, a), beta) step by step, handed to `put(step, alpha,
+// gamma)`.  Same operations in the same order as cheb_table, so host and device tables are bit-identical.
+template <class Put>
+FB_HD void corr_table_column(double a, double theta_j, double beta, int m, Put put) {
+  const double a_low = theta_j < a ? theta_j : a;
+  const double e = 0.5 * (beta - a), c = 0.5 * (beta + a);
+  double sigma = e / (a_low - c);
+  const double sigma1 = sigma;
+  put(0, sigma1 / e, 0.0);
+  for (int s = 1; s < m; ++s) {
+    const double sigma2 = 1.0 / (2.0 / sigma1 - sigma);
+    put(s, 2.0 * sigma2 / e, sigma * sigma2);
+    sigma = sigma2;
+  }
+}
+
 inline int cheb_degree(double a, double theta_k, double beta, double amp, int max_degree) {
   const double e = 0.5 * (beta - a);
   const double eps = std::max((a - theta_k) / e, 1e-14);
@@ -450,27 +466,10 @@ int chfsi_solve(BE& be, const SolveParams& p, MeshResult* out) {
     if (kind < 0 || deg < 3) kind = PASS_FP64;
     if (kind == PASS_FP32_CORR) {
       // y_k = x + z_k with the polynomial of column j normalised to 1 at theta_j: z_{k+1} = alpha_kj ((L - c) z_k + r_j) -
-      // gamma_kj z_{k-1}, z_0 = 0, r = L x - theta x from the Rayleigh-Ritz step (fp64); tables per column
-      alpha.resize((size_t)M * deg * B);
-      gamma.resize((size_t)M * deg * B);
-      // M * B recurrences of `deg` steps: a few ms on one core for a bench batch, with the GPU waiting -- the meshes are
-      // independent, so they are spread over a small OpenMP team (8 threads: with one process per GPU and two sub-batches
-      // in flight per process, larger teams would oversubscribe the host)
-#if defined(_OPENMP)
-#pragma omp parallel for schedule(static) if (M >= 8) num_threads(8)
-#endif
-      for (int m = 0; m < M; ++m) {
-        std::vector<double> ta(deg), tg(deg);
-        for (int j = 0; j < B; ++j) {
-          const double thj = std::min(theta[(size_t)m * B + j], last_a[m]);
-          cheb_table(last_a[m], thj, beta_m[m], deg, ta.data(), tg.data(), &center[m]);
-          for (int s = 0; s < deg; ++s) {
-            alpha[((size_t)m * deg + s) * B + j] = ta[s];
-            gamma[((size_t)m * deg + s) * B + j] = tg[s];
-          }
-        }
-      }
-      be.filter_correction(deg, alpha.data(), gamma.data(), center.data());
+      // gamma_kj z_{k-1}, z_0 = 0, r = L x - theta x from the Rayleigh-Ritz step (fp64).  The M * B per-column tables
+      // (corr_table_column below) are built by the backend from the Ritz values it already holds -- a kernel on the
+      // GPU, so that nothing N- or degree-sized is computed or uploaded by the host between two filter passes.
+      be.filter_correction(deg, last_a.data(), beta_m.data());
     } else {
       alpha.resize((size_t)M * deg);
       gamma.resize((size_t)M * deg);

@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "nccl_dyn.h"
 #include "rowops.h"
+#include "sell.cuh"
 #include "spmm.cuh"
 
 namespace fb {
@@ -461,11 +462,9 @@ static thread_local FilterProfile g_filter_profile(&g_totals[0]);
 static thread_local FilterProfile g_filter_profile_lowp(&g_totals[1]);
 static thread_local FilterProfile g_filter_profile_corr(&g_totals[2]);
 
-// focusr_set_tuning(1, MB): L2 budget for blocking the filter over groups of meshes (0 = off)
-// Measured on B200 (gpurun_out/bench_l2_*.log, 128 pairs): 0 -> 641 pairs/s, 64 MB -> 548, 32 MB -> 341: groups
-// that fit L2 are < 1 wave of CTAs and the kernel is latency-bound, so blocking loses.  Default off.
-int g_l2_budget_mb = 0;
-
+// Tuning record: blocking the filter over groups of meshes that fit the 126 MB L2 (all steps of a table chunk on one group
+// before the next) was measured on B200 at 128 pairs: off 641 pairs/s, 64 MB groups 548, 32 MB 341 -- groups that fit L2
+// are < 1 wave of CTAs and the kernel turns latency-bound -- and removed.
 template <int B>
 struct GramCfg {
   static constexpr int QT = (B <= 32) ? B / 8 : (B <= 64 ? 2 : 1);
@@ -623,17 +622,42 @@ struct PeerShared {
 static PeerShared g_shared;
 constexpr size_t PEER_FLAG_BYTES = 128;
 
+// Per-column tables of a correction pass, steps [s0, s0 + len) of `deg`: thread (mesh, column j) runs the three-term
+// coefficient recurrence of corr_table_column (chfsi_driver.hpp) from step 0 and stores its slice as floats
+// [mesh][len][B]; thread 0 of a mesh also writes the centre of the filter interval.  ab = {a[M], beta[M]}.
+__global__ void k_corr_tables(const double* __restrict__ theta, const double* __restrict__ ab, int M, int B, int deg, int s0,
+                              int len, float* __restrict__ alpha_c, float* __restrict__ gamma_c, double* __restrict__ center) {
+  const int m = blockIdx.x, j = threadIdx.x;
+  if (j >= B) return;
+  const double a = ab[m], beta = ab[M + m];
+  if (j == 0) center[m] = 0.5 * (beta + a);
+  float* al = alpha_c + (size_t)m * len * B + j;
+  float* ga = gamma_c + (size_t)m * len * B + j;
+  corr_table_column(a, theta[(size_t)m * B + j], beta, min(deg, s0 + len), [&](int s, double av, double gv) {
+    if (s >= s0) {
+      al[(size_t)(s - s0) * B] = (float)av;
+      ga[(size_t)(s - s0) * B] = (float)gv;
+    }
+  });
+}
+
+static void launch_corr_tables(const double* theta, const double* ab, int M, int B, int deg, int s0, int len, float* alpha_c,
+                               float* gamma_c, double* center, cudaStream_t stream) {
+  k_corr_tables<<<M, 96, 0, stream>>>(theta, ab, M, B, deg, s0, len, alpha_c, gamma_c, center);
+  FB_COUNT_LAUNCH(1);
+}
+
 struct CudaBackend {
   // graph of this run (rows are the run's meshes; pointers are global, offsets select the run)
   SpmmGraph g;
   const double* points;
   const int* off_host;   // [M+1] global row offsets of the run's meshes
-  const int* info_host;  // [M][4]
+  const int* info_host;  // [M][FOCUSR_MESH_INFO_INTS]
   int M, B, mesh_base;
   bool sym;
   cudaStream_t stream;
   // workspace
-  double *X, *Y, *Xn, *partial, *partial_res, *W, *theta, *res, *G, *H, *alpha, *gamma, *center;
+  double *X, *Y, *Xn, *partial, *partial_res, *W, *theta, *res, *G, *H, *alpha, *gamma, *center, *corr_ab;
   long long *lo, *hi;
   int *flags, *sel, *n_out, *rr_info;
   int chunks_max, table_cap;
@@ -643,13 +667,16 @@ struct CudaBackend {
   int ldv;
   int err = FB_OK;
   DistCtx* dist = nullptr;  // row-partitioned multi-GPU solve (one mesh); null = everything is local
+  bool mixed = true;        // fp32 filter passes allowed (focusr_eigs_options.mixed_precision)
+  FilterTuning tune;        // kernel form of the fp32 filter steps
+  SellF32 sell;             // SELL-64 fp32 copy of the matrix (tune.format == 0)
 
   int n_meshes() const { return M; }
   int block() const { return B; }
   bool symmetric() const { return sym; }
-  int zero_rows(int m) const { return info_host[4 * m + 2]; }
+  int zero_rows(int m) const { return info_host[FOCUSR_MESH_INFO_INTS * m + 2]; }
   // fp32 filter passes: local solves only (the peer-shared blocks of the row-partitioned solve are fp64)
-  bool lowp_available() const { return dist == nullptr && g_mixed_precision != 0 && g.weights_f != nullptr; }
+  bool lowp_available() const { return dist == nullptr && mixed && sell.entries != nullptr; }
 
   // fp32 view number `half` (0 or 1) of an fp64 block, indexed by global row like the block itself
   float* f32_view(double* blk, int half) const {
@@ -729,11 +756,8 @@ struct CudaBackend {
   void rotate_t() {
     constexpr int WS = (BB % 16 == 0) ? BB + 8 : BB;
     const size_t smem = sizeof(double) * ((size_t)BB * WS + 16 * BB);
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(k_rotate<BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      attr_set = true;
-    }
+    // the attribute is per device and per function: set on every call (cheap), never cached process-wide
+    fail(cudaFuncSetAttribute(k_rotate<BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in (rotate)");
     dim3 grid(chunks_max, M);
     // the fp32 residual block goes to the first half of Y (dead between filters), where filter_correction reads it
     k_rotate<BB><<<grid, GRAM_THREADS, smem, stream>>>(X, Xn, W, theta, g.degree_inv, g.mesh_off, partial_res, chunks_max,
@@ -787,13 +811,11 @@ struct CudaBackend {
     const bool wide = B > 32 || (B > 16 && M < 64);
     const int nt = wide ? 256 : 32;
     const size_t smem = sizeof(double) * ((size_t)3 * B * B + B + (B + 2) + nt) + sizeof(int) * (2 * B + 2);
-    static size_t attr_smem[2] = {0, 0};
-    if (smem > attr_smem[wide]) {
+    if (smem > 48 * 1024) {  // per device and per function: set on every call that needs it, never cached process-wide
       if (wide)
-        cudaFuncSetAttribute(k_rr_sym<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        fail(cudaFuncSetAttribute(k_rr_sym<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in (rr_sym)");
       else
-        cudaFuncSetAttribute(k_rr_sym<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      attr_smem[wide] = smem;
+        fail(cudaFuncSetAttribute(k_rr_sym<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in (rr_sym)");
     }
     const double* src = dist ? dist->small : partial;
     const int cm = dist ? 1 : chunks_max;
@@ -848,6 +870,12 @@ struct CudaBackend {
     memcpy(th, pin, bytes);
     memcpy(rs, pin + (size_t)M * B, bytes);
   }
+  // one fp32 filter step on the sliced-ELL copy of the matrix (sell.cu has the modes)
+  void lowp_step(int mode, const void* y, const float* x_prev, const float* r, void* out, float* y_copy, const void* al,
+                 const void* ga, int step, int n_steps, bool has_prev) {
+    launch_filter_sell(mode, B, sell, g.mesh_off, g.n_meshes, g.max_mesh_rows, y, x_prev, r, out, y_copy, al, ga, center,
+                       step, n_steps, has_prev, tune, stream);
+  }
   void filter(int deg, const double* al, const double* ga, const double* ce, bool lowp) {
     lowp = lowp && lowp_available() && deg >= 3;
     // tables are uploaded in chunks of table_cap steps; pinned staging holds every chunk of this
@@ -869,7 +897,7 @@ struct CudaBackend {
     // row_ptr), degree + 1/degree~, and three passes over the [rows][B] block
     const double rows = (double)(off_host[M] - off_host[0]);
     double nnz = 0.0;
-    for (int m = 0; m < M; ++m) nnz += info_host[4 * m];
+    for (int m = 0; m < M; ++m) nnz += info_host[FOCUSR_MESH_INFO_INTS * m];
     // fp32 passes read the fp32 copy of the matrix (4 + 4 bytes per entry, 8 bytes of (d, 1/d~) per row)
     const double step_bytes = lowp ? 8.0 * nnz + 4.0 * rows + 8.0 * rows + 12.0 * (double)B * rows
                                    : 12.0 * nnz + 4.0 * rows + 16.0 * rows + 24.0 * (double)B * rows;
@@ -891,22 +919,15 @@ struct CudaBackend {
       }
       fail(cudaMemcpyAsync(alpha, pa, sizeof(double) * (size_t)M * len, cudaMemcpyHostToDevice, stream), "H2D alpha");
       fail(cudaMemcpyAsync(gamma, pg, sizeof(double) * (size_t)M * len, cudaMemcpyHostToDevice, stream), "H2D gamma");
-      // L2 blocking: the three blocks + matrix of one mesh are ~7 MB at 15k vertices, so a group of
-      // meshes that fits the 126 MB L2 is taken through ALL steps of this table chunk before the next
-      // group starts; only the first step of a group streams from HBM.  (Every mesh of the batch runs
-      // the same number of steps, so the buffer rotation below is the same for every group.)
-      double per_mesh = 0.0;
-      for (int m = 0; m < M; ++m)
-        per_mesh = std::max(per_mesh, 12.0 * info_host[4 * m] + (20.0 + 24.0 * B) * (off_host[m + 1] - off_host[m]));
       if (lowp) {
         for (int s = 0; s < len; ++s) {
           const int gs = s0 + s;
           if (gs == 0) {  // X (fp64) -> f_cur, fp32 copy of X -> f_prev
-            launch_spmm_f32(1, B, g, X, nullptr, f_cur, f_prev, alpha, gamma, center, s, len, stream);
+            lowp_step(1, X, nullptr, nullptr, f_cur, f_prev, alpha, gamma, s, len, false);
           } else {
             const bool last = gs == deg - 1;
-            launch_spmm_f32(last ? 2 : 0, B, g, f_cur, f_prev, last ? (void*)X : (void*)f_next, nullptr, alpha, gamma,
-                            center, s, len, stream);
+            lowp_step(last ? 2 : 0, f_cur, f_prev, nullptr, last ? (void*)X : (void*)f_next, nullptr, alpha, gamma, s, len,
+                      true);
             float* t = f_prev;
             f_prev = f_cur;
             f_cur = f_next;
@@ -915,26 +936,9 @@ struct CudaBackend {
         }
         continue;
       }
-      int group = M;
-      if (g_l2_budget_mb > 0) group = std::max(1, (int)((double)g_l2_budget_mb * 1048576.0 / per_mesh));
-      if (group >= M || len < 2) {
-        group = M;
-      }
-      for (int m0 = 0; m0 < M; m0 += group) {
-        SpmmGraph gg = g;
-        gg.mesh_off = g.mesh_off + m0;
-        gg.n_meshes = std::min(group, M - m0);
-        double *c2 = cur, *p2 = prev, *n2 = next;
-        for (int s = 0; s < len; ++s) {
-          halo_exchange(c2);
-          spmm(0, gg, c2, p2, n2, alpha + (size_t)m0 * len, gamma + (size_t)m0 * len, center + m0, s, len);
-          double* t = p2;
-          p2 = c2;
-          c2 = n2;
-          n2 = t;
-        }
-      }
       for (int s = 0; s < len; ++s) {
+        halo_exchange(cur);
+        spmm(0, g, cur, prev, next, alpha, gamma, center, s, len);
         double* t = prev;
         prev = cur;
         cur = next;
@@ -954,51 +958,40 @@ struct CudaBackend {
   }
   // fp32 correction pass (chfsi_driver.hpp): X += z_deg, z_{k+1} = alpha_kj ((L - c) z_k + r_j) - gamma_kj z_{k-1}, z_0 = 0.
   // r (fp32) was left in the first half of Y by the last rotate_and_residual; the three z blocks live in the second
-  // half of Y and the two halves of Xn.  al / ga are per column: [M][deg][B].
-  void filter_correction(int deg, const double* al, const double* ga, const double* ce) {
-    const size_t total = (size_t)M * deg * B;
+  // half of Y and the two halves of Xn.  The per-column tables [M][len][B] (float) are built on the device from the
+  // Ritz values of that Rayleigh-Ritz step (k_corr_tables): the host hands over 2 M numbers.
+  void filter_correction(int deg, const double* a_m, const double* beta_m) {
     // the device tables (alpha, gamma: M * table_cap doubles each) hold M * cap_c * B floats
     const int cap_c = std::max(1, (int)((size_t)table_cap * 2 / B));
-    float* pin = (float*)g_pin_tables.get(sizeof(float) * 2 * total + sizeof(double) * M);
+    double* pin = (double*)g_pin_tables.get(sizeof(double) * 2 * (size_t)M);
     if (!pin) {
       fail(cudaErrorMemoryAllocation, "pinned tables");
       return;
     }
-    double* pc = reinterpret_cast<double*>(pin + 2 * total);
-    memcpy(pc, ce, sizeof(double) * M);
-    fail(cudaMemcpyAsync(center, pc, sizeof(double) * M, cudaMemcpyHostToDevice, stream), "H2D center");
+    memcpy(pin, a_m, sizeof(double) * M);
+    memcpy(pin + M, beta_m, sizeof(double) * M);
+    fail(cudaMemcpyAsync(corr_ab, pin, sizeof(double) * 2 * (size_t)M, cudaMemcpyHostToDevice, stream), "H2D filter edges");
     const float* r = f32_view(Y, 0);
     float* z_cur = f32_view(Y, 1);
     float* z_prev = f32_view(Xn, 0);
     float* z_next = f32_view(Xn, 1);
     const double rows = (double)(off_host[M] - off_host[0]);
     double nnz = 0.0;
-    for (int m = 0; m < M; ++m) nnz += info_host[4 * m];
+    for (int m = 0; m < M; ++m) nnz += info_host[FOCUSR_MESH_INFO_INTS * m];
     const double step_bytes = 8.0 * nnz + 4.0 * rows + 8.0 * rows + 16.0 * (double)B * rows;
-    g_filter_profile_corr.begin(stream);
-    fail(cudaMemsetAsync(z_cur + (size_t)off_host[0] * B, 0, sizeof(float) * (size_t)rows * B, stream), "zero z");
-    size_t pin_off = 0;
     float* d_al = reinterpret_cast<float*>(alpha);
     float* d_ga = reinterpret_cast<float*>(gamma);
+    // first chunk of tables before the timed bracket (its launches are the filter steps only)
+    launch_corr_tables(theta, corr_ab, M, B, deg, 0, std::min(cap_c, deg), d_al, d_ga, center, stream);
+    g_filter_profile_corr.begin(stream);
+    fail(cudaMemsetAsync(z_cur + (size_t)off_host[0] * B, 0, sizeof(float) * (size_t)rows * B, stream), "zero z");
     for (int s0 = 0; s0 < deg; s0 += cap_c) {
       const int len = std::min(cap_c, deg - s0);
-      float* pa = pin + pin_off;
-      float* pg = pa + (size_t)M * len * B;
-      pin_off += 2 * (size_t)M * len * B;
-#if defined(_OPENMP)
-#pragma omp parallel for schedule(static) if (M >= 8) num_threads(8)
-#endif
-      for (int m = 0; m < M; ++m)
-        for (size_t e = 0; e < (size_t)len * B; ++e) {
-          pa[(size_t)m * len * B + e] = (float)al[((size_t)m * deg + s0) * B + e];
-          pg[(size_t)m * len * B + e] = (float)ga[((size_t)m * deg + s0) * B + e];
-        }
-      fail(cudaMemcpyAsync(d_al, pa, sizeof(float) * (size_t)M * len * B, cudaMemcpyHostToDevice, stream), "H2D alpha (columns)");
-      fail(cudaMemcpyAsync(d_ga, pg, sizeof(float) * (size_t)M * len * B, cudaMemcpyHostToDevice, stream), "H2D gamma (columns)");
+      if (s0 > 0) launch_corr_tables(theta, corr_ab, M, B, deg, s0, len, d_al, d_ga, center, stream);
       for (int s = 0; s < len; ++s) {
         const int gs = s0 + s;
         const bool last = gs == deg - 1;
-        launch_spmm_corr(last, B, g, z_cur, z_prev, r, z_next, X, d_al, d_ga, center, s, len, gs > 0, stream);
+        lowp_step(last ? 4 : 3, z_cur, z_prev, r, last ? (void*)X : (void*)z_next, nullptr, d_al, d_ga, s, len, gs > 0);
         float* t = z_prev;
         z_prev = z_cur;
         z_cur = z_next;
@@ -1052,6 +1045,7 @@ static size_t eigs_ws_layout(int n_rows, int n_meshes, int max_mesh_rows, int B,
   double* alpha = cv.take<double>((size_t)n_meshes * table_cap);
   double* gamma = cv.take<double>((size_t)n_meshes * table_cap);
   double* center = cv.take<double>((size_t)n_meshes);
+  double* corr_ab = cv.take<double>((size_t)2 * n_meshes);
   long long* lo = cv.take<long long>((size_t)3 * n_meshes);
   long long* hi = cv.take<long long>((size_t)3 * n_meshes);
   int* flags = cv.take<int>((size_t)n_meshes);
@@ -1062,7 +1056,7 @@ static size_t eigs_ws_layout(int n_rows, int n_meshes, int max_mesh_rows, int B,
   if (be) {
     be->X = X; be->Y = Y; be->Xn = Xn; be->partial = partial; be->partial_res = partial_res;
     be->W = W; be->G = G; be->H = H; be->theta = theta; be->res = res; be->alpha = alpha;
-    be->gamma = gamma; be->center = center; be->lo = lo; be->hi = hi; be->flags = flags;
+    be->gamma = gamma; be->center = center; be->corr_ab = corr_ab; be->lo = lo; be->hi = hi; be->flags = flags;
     be->sel = sel; be->n_out = n_out; be->rr_info = rr_info; be->g.mesh_off = off;
     be->chunks_max = chunks_max; be->table_cap = table_cap;
   }
@@ -1103,15 +1097,42 @@ size_t focusr_eigs_workspace_bytes(int n_points, int n_meshes, int max_mesh_poin
   return eigs_ws_layout(n_points, n_meshes, max_mesh_points, block_size, nullptr, nullptr, 0);
 }
 
-// room for the fp32 copy of the matrix (weights: 4 bytes per stored entry; (degree, 1/degree~): 8 bytes per row) at the
-// end of the workspace; focusr_eigs_smallest runs its fp32 filter passes only if the workspace it is given has it
-static size_t eigs_f32_matrix_bytes(long long nnz, int n_points) {
-  return align_up(sizeof(float) * (size_t)nnz) + align_up(sizeof(float2) * (size_t)n_points) + 256;
+// room for the fp32 copy of the matrix at the end of the workspace: (degree, 1/degree~) per row and the SELL-64 packed
+// entries (8 bytes per padded entry) with their slice tables.  focusr_eigs_smallest runs its fp32 filter passes only if
+// the workspace it is given has this room.
+struct F32Layout {
+  float2* ddi;
+  int2* entries;
+  int *all_mesh_off, *mesh_slice_off, *slice_ptr, *slice_cnt, *scan_tmp;
+  size_t bytes;
+};
+static F32Layout f32_layout(long long sell_entries, int n_points, int n_meshes, void* base) {
+  Carver cv(base, (size_t)-1);
+  F32Layout l;
+  const size_t n_slices = (size_t)n_points / SELL_ROWS + (size_t)n_meshes + 1;
+  l.ddi = cv.take<float2>((size_t)n_points);
+  l.all_mesh_off = cv.take<int>((size_t)n_meshes + 1);  // device copy of every mesh offset (the SELL build spans the batch)
+  l.mesh_slice_off = cv.take<int>((size_t)n_meshes + 1);
+  l.slice_ptr = cv.take<int>(n_slices + 1);
+  l.slice_cnt = cv.take<int>(n_slices + 1);
+  l.scan_tmp = cv.take<int>(scan_tmp_ints((int)n_slices + 1));
+  l.entries = cv.take<int2>((size_t)std::max(sell_entries, 1LL));
+  l.bytes = cv.used + 512;
+  return l;
 }
 
-size_t focusr_eigs_workspace_bytes_mixed(int n_points, long long nnz, int n_meshes, int max_mesh_points, int block_size) {
+size_t focusr_eigs_workspace_bytes_mixed(int n_points, long long sell_entries_cap, int n_meshes, int max_mesh_points,
+                                         int block_size) {
   return eigs_ws_layout(n_points, n_meshes, max_mesh_points, block_size, nullptr, nullptr, 0) +
-         eigs_f32_matrix_bytes(nnz, n_points);
+         f32_layout(sell_entries_cap, n_points, n_meshes, nullptr).bytes;
+}
+
+void focusr_eigs_default_options(focusr_eigs_options* o) {
+  o->mixed_precision = 1;
+  o->filter_policy = 2;
+  o->filter_prefetch = 1;
+  o->filter_min_blocks = 8;
+  for (int& r : o->reserved) r = 0;
 }
 
 int focusr_eigs_block_size(int k, int n_k_needed, int k_buffer, int max_one_way, int max_zero_rows) {
@@ -1135,19 +1156,22 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
                          int block_size, double spectrum_upper_bound, double* eig_vals, double* eig_vecs,
                          int ldv, int* result_i_host,
                          double* result_d_host, void* workspace, size_t workspace_bytes,
-                         focusr_stream_t stream_) {
+                         const focusr_eigs_options* options, focusr_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  focusr_eigs_options opt;
+  focusr_eigs_default_options(&opt);
+  if (options) opt = *options;
   FB_REQUIRE(n_points > 0 && n_meshes > 0 && k >= 1 && n_k_needed >= 1 && ldv >= 1, "eigs: bad sizes");
   FB_REQUIRE(mesh_point_off_host[0] == 0 && mesh_point_off_host[n_meshes] == n_points,
              "eigs: mesh offsets must cover [0, n_points)");
   int max_oneway = 0, max_zero = 0, max_rows = 0;
   for (int m = 0; m < n_meshes; ++m) {
-    max_oneway = std::max(max_oneway, mesh_info_host[4 * m + 1]);
-    max_zero = std::max(max_zero, mesh_info_host[4 * m + 2]);
+    max_oneway = std::max(max_oneway, mesh_info_host[FOCUSR_MESH_INFO_INTS * m + 1]);
+    max_zero = std::max(max_zero, mesh_info_host[FOCUSR_MESH_INFO_INTS * m + 2]);
     max_rows = std::max(max_rows, mesh_point_off_host[m + 1] - mesh_point_off_host[m]);
-    FB_REQUIRE(mesh_info_host[4 * m + 3] == 0,
+    FB_REQUIRE(mesh_info_host[FOCUSR_MESH_INFO_INTS * m + 3] == 0,
                "eigs: mesh %d has %d non-finite edge weights (zero-length edges, graph.py:177-178)", m,
-               mesh_info_host[4 * m + 3]);
+               mesh_info_host[FOCUSR_MESH_INFO_INTS * m + 3]);
   }
   const int B = block_size > 0 ? block_size
                                : focusr_eigs_block_size(k, n_k_needed, k_buffer, max_oneway, max_zero);
@@ -1174,25 +1198,31 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
 
   // fp32 copy of the matrix for the fp32 filter passes, at the end of the workspace if it has the room
   // (focusr_eigs_workspace_bytes_mixed); without it every pass is fp64
-  float* wf = nullptr;
-  float2* ddi = nullptr;
+  F32Layout f32{};
+  bool have_f32 = false;
   size_t ws_main = workspace_bytes;
+  FilterTuning tune;
+  tune.policy = opt.filter_policy;
+  tune.prefetch = opt.filter_prefetch;
+  tune.min_blocks = opt.filter_min_blocks;
   {
-    long long nnz_total = 0;
     bool any_sym = false;
-    for (int m = 0; m < n_meshes; ++m) {
-      nnz_total += mesh_info_host[4 * m];
-      any_sym = any_sym || mesh_info_host[4 * m + 1] == 0;
-    }
-    const size_t extra = eigs_f32_matrix_bytes(nnz_total, n_points);
+    for (int m = 0; m < n_meshes; ++m) any_sym = any_sym || mesh_info_host[FOCUSR_MESH_INFO_INTS * m + 1] == 0;
+    const long long sell_cap = sell_entries_cap(mesh_point_off_host, mesh_info_host, n_meshes, 0);
+    const size_t extra = f32_layout(sell_cap, n_points, n_meshes, nullptr).bytes;
     const size_t base = eigs_ws_layout(n_points, n_meshes, max_rows, B, nullptr, nullptr, 0);
-    if (any_sym && g_mixed_precision != 0 && workspace_bytes >= base + extra) {
+    if (any_sym && opt.mixed_precision != 0 && workspace_bytes >= base + extra) {
       ws_main = workspace_bytes - extra;
       char* tail = reinterpret_cast<char*>(workspace) + ws_main;
       tail += (256 - (reinterpret_cast<uintptr_t>(tail) & 255)) & 255;
-      wf = reinterpret_cast<float*>(tail);
-      ddi = reinterpret_cast<float2*>(tail + align_up(sizeof(float) * (size_t)nnz_total));
-      launch_matrix_f32(weights, degree, degree_inv, nnz_total, n_points, wf, ddi, stream);
+      f32 = f32_layout(sell_cap, n_points, n_meshes, tail);
+      have_f32 = true;
+      FB_CUDA(cudaMemcpyAsync(f32.all_mesh_off, mesh_point_off_host, sizeof(int) * ((size_t)n_meshes + 1), cudaMemcpyHostToDevice,
+                              stream));
+      const int rc = sell_build_f32(row_ptr, cols, weights, degree, degree_inv, f32.all_mesh_off, mesh_point_off_host, n_meshes,
+                                    n_points, f32.mesh_slice_off, f32.slice_ptr, f32.entries, f32.ddi, f32.slice_cnt,
+                                    f32.scan_tmp, stream);
+      if (rc) return rc;
     }
   }
   // contiguous runs of meshes with the same symmetry class are solved as one batch
@@ -1200,14 +1230,20 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
   std::vector<MeshResult> results(n_meshes);
   int m0 = 0;
   while (m0 < n_meshes) {
-    const bool sym = mesh_info_host[4 * m0 + 1] == 0;
+    const bool sym = mesh_info_host[FOCUSR_MESH_INFO_INTS * m0 + 1] == 0;
     int m1 = m0 + 1;
-    while (m1 < n_meshes && (mesh_info_host[4 * m1 + 1] == 0) == sym) ++m1;
+    while (m1 < n_meshes && (mesh_info_host[FOCUSR_MESH_INFO_INTS * m1 + 1] == 0) == sym) ++m1;
     const int M = m1 - m0;
     CudaBackend be;
     be.g = SpmmGraph{row_ptr, cols, weights, degree, degree_inv, nullptr, M, 0};
-    be.g.weights_f = wf;
-    be.g.ddi_f = ddi;
+    be.mixed = opt.mixed_precision != 0;
+    be.tune = tune;
+    if (have_f32) {
+      be.sell.entries = f32.entries;
+      be.sell.slice_ptr = f32.slice_ptr;
+      be.sell.mesh_slice_off = f32.mesh_slice_off + m0;
+      be.sell.ddi = f32.ddi;
+    }
     int run_max = 0;
     for (int m = m0; m < m1; ++m)
       run_max = std::max(run_max, mesh_point_off_host[m + 1] - mesh_point_off_host[m]);
@@ -1225,7 +1261,7 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
     be.Xn -= shift;
     be.points = points;
     be.off_host = mesh_point_off_host + m0;
-    be.info_host = mesh_info_host + 4 * m0;
+    be.info_host = mesh_info_host + FOCUSR_MESH_INFO_INTS * m0;
     be.M = M;
     be.B = B;
     be.mesh_base = m0;
@@ -1439,7 +1475,7 @@ int focusr_eigs_smallest_dist(const int* row_ptr, const int* cols_local, const d
     return FB_ERR_WORKSPACE;
   }
   const int off_host[2] = {0, n_local};
-  const int info_host[4] = {(int)nnz_local, 0, n_zero_rows_global, 0};
+  const int info_host[FOCUSR_MESH_INFO_INTS] = {(int)nnz_local, 0, n_zero_rows_global, 0, 0, 0, 0, 0};
   const int fake[2] = {0, 1};
   be.points = points;
   be.off_host = off_host;

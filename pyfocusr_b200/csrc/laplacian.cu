@@ -168,40 +168,99 @@ __global__ void k_edge_fill(const int* __restrict__ tris, int n_edges, int n_poi
   raw_cols[slot] = p2;
 }
 
-// One thread per row: sort the row's raw columns (the fill order is non-deterministic, the
-// sorted order is not), collapse duplicates (assignment semantics of graph.py:178: a repeated
-// directed edge carries the identical weight), and take the degree as the sequential
-// ascending-column sum of the weights (= scipy's A.sum(axis=1) bit for bit).
-__global__ void k_row_sort_unique(const double* __restrict__ points, int pd, int n_points,
-                                  const int* __restrict__ start, int* __restrict__ raw_cols,
-                                  int* __restrict__ ucnt, double* __restrict__ degree,
-                                  double* __restrict__ degree_inv) {
+// One thread per row: sort the row's raw columns (the fill order is non-deterministic, the sorted order is
+// not), collapse duplicates (assignment semantics of graph.py:178: a repeated directed edge carries the identical
+// weight), compute every kept edge weight ONCE and the degree as the sequential ascending-column sum of the weights
+// (= scipy's A.sum(axis=1) bit for bit), and write the sorted row back in place.  Rows of up to 16 entries -- every
+// row of a triangle mesh in practice -- are sorted in registers by an odd-even transposition network; longer rows
+// fall back to an insertion sort in global memory.  The row keeps its slot [start[i], start[i+1]): when no row of
+// the batch had a duplicate (the common case: `dups` stays 0) that slot layout already IS the final CSR.
+template <int L>
+__device__ __forceinline__ void sort_network(int (&c)[L]) {
+#pragma unroll
+  for (int round = 0; round < L; ++round) {
+#pragma unroll
+    for (int a = (round & 1); a + 1 < L; a += 2) {
+      const int lo = min(c[a], c[a + 1]), hi = max(c[a], c[a + 1]);
+      c[a] = lo;
+      c[a + 1] = hi;
+    }
+  }
+}
+
+template <int L>
+__device__ __forceinline__ int row_finish_small(const double* __restrict__ points, int pd, int i, int* __restrict__ crow,
+                                                double* __restrict__ wrow, int len, double* deg_out) {
+  int c[L];
+#pragma unroll
+  for (int a = 0; a < L; ++a) c[a] = a < len ? crow[a] : 0x7fffffff;
+  sort_network<L>(c);
+  const double* pi = points + (size_t)pd * i;
+  int u = 0, last = -1;
+  double d = 0.0;
+#pragma unroll
+  for (int a = 0; a < L; ++a) {
+    const int v = c[a];
+    if (a < len && v != last) {
+      const double w = edge_weight(pi, points + (size_t)pd * v, pd);
+      crow[u] = v;
+      wrow[u] = w;
+      d = FB_ADD(d, w);
+      ++u;
+      last = v;
+    }
+  }
+  *deg_out = d;
+  return u;
+}
+
+__global__ void __launch_bounds__(256)
+k_row_finish(const double* __restrict__ points, int pd, int n_points, const int* __restrict__ start,
+             int* __restrict__ cols, double* __restrict__ weights, int* __restrict__ ucnt, double* __restrict__ degree,
+             double* __restrict__ degree_inv, int* __restrict__ dups) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_points) return;
-  const int s = start[i], e = start[i + 1];
-  int* c = raw_cols + s;
-  const int len = e - s;
-  for (int a = 1; a < len; ++a) {
-    const int v = c[a];
-    int b = a - 1;
-    while (b >= 0 && c[b] > v) {
-      c[b + 1] = c[b];
-      --b;
-    }
-    c[b + 1] = v;
-  }
-  int u = 0;
+  const int s = start[i], len = start[i + 1] - s;
+  int* c = cols + s;
+  double* wr = weights + s;
   double d = 0.0;
-  const double* pi = points + (size_t)pd * i;
-  for (int a = 0; a < len; ++a) {
-    const int v = c[a];
-    if (a > 0 && v == c[u - 1]) continue;
-    c[u++] = v;
-    d = FB_ADD(d, edge_weight(pi, points + (size_t)pd * v, pd));
+  int u;
+  if (len <= 8) {
+    u = row_finish_small<8>(points, pd, i, c, wr, len, &d);
+  } else if (len <= 16) {
+    u = row_finish_small<16>(points, pd, i, c, wr, len, &d);
+  } else {
+    for (int a = 1; a < len; ++a) {
+      const int v = c[a];
+      int b = a - 1;
+      while (b >= 0 && c[b] > v) {
+        c[b + 1] = c[b];
+        --b;
+      }
+      c[b + 1] = v;
+    }
+    u = 0;
+    const double* pi = points + (size_t)pd * i;
+    for (int a = 0; a < len; ++a) {
+      const int v = c[a];
+      if (a > 0 && v == c[u - 1]) continue;
+      const double w = edge_weight(pi, points + (size_t)pd * v, pd);
+      c[u] = v;
+      wr[u] = w;
+      d = FB_ADD(d, w);
+      ++u;
+    }
   }
   ucnt[i] = u;
   degree[i] = d;
   degree_inv[i] = degree_inverse(d);
+  if (u < len) atomicAdd(dups, len - u);
+}
+
+// duplicate directed edges exist (rare: inconsistent / non-manifold input): rows move left to their final offsets
+__global__ void k_copy_ints(const int* __restrict__ in, int* __restrict__ out, long long n) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = in[t];
 }
 
 __global__ void k_compact(const double* __restrict__ points, int pd, int n_points,
@@ -233,19 +292,20 @@ __device__ __forceinline__ int find_mesh(const int* __restrict__ off, int n_mesh
 
 // per-mesh structure facts the solver needs: one-way entries (A_ij without A_ji, which make L
 // non-normal: SURVEY.md section 7.3-1), zero-degree rows (exact null vectors), non-finite weights.
-__global__ void k_mesh_stats(const int* __restrict__ row_ptr, const int* __restrict__ cols,
+// Rows are read in the slot layout k_row_finish leaves: row i = [row_ptr[i], row_ptr[i] + ucnt[i]).
+__global__ void k_mesh_stats(const int* __restrict__ row_ptr, const int* __restrict__ ucnt, const int* __restrict__ cols,
                              const double* __restrict__ weights, int n_points,
                              const int* __restrict__ mesh_off, int n_meshes,
                              int* __restrict__ mesh_info) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_points) return;
   const int m = find_mesh(mesh_off, n_meshes, i);
-  const int s = row_ptr[i], e = row_ptr[i + 1];
+  const int s = row_ptr[i], e = s + ucnt[i];
   int oneway = 0, nonfinite = 0;
   for (int p = s; p < e; ++p) {
     const int j = cols[p];
     if (!isfinite(weights[p])) ++nonfinite;
-    int lo = row_ptr[j], hi = row_ptr[j + 1] - 1;
+    int lo = row_ptr[j], hi = lo + ucnt[j] - 1;
     bool found = false;
     while (lo <= hi) {
       const int mid = (lo + hi) >> 1;
@@ -261,10 +321,32 @@ __global__ void k_mesh_stats(const int* __restrict__ row_ptr, const int* __restr
     }
     oneway += !found;
   }
-  if (oneway) atomicAdd(&mesh_info[4 * m + 1], oneway);
-  if (e == s) atomicAdd(&mesh_info[4 * m + 2], 1);
-  if (nonfinite) atomicAdd(&mesh_info[4 * m + 3], nonfinite);
-  if (i == mesh_off[m]) mesh_info[4 * m + 0] = row_ptr[mesh_off[m + 1]] - row_ptr[mesh_off[m]];
+  constexpr int S = FOCUSR_MESH_INFO_INTS;
+  if (oneway) atomicAdd(&mesh_info[S * m + 1], oneway);
+  if (e == s) atomicAdd(&mesh_info[S * m + 2], 1);
+  if (nonfinite) atomicAdd(&mesh_info[S * m + 3], nonfinite);
+  // longest row and entry count of the mesh: one atomic per warp unless the warp straddles meshes
+  int len = e - s, total = e - s;
+  const unsigned act = __activemask();
+  bool warp_wide = false;
+  if (act == 0xffffffffu) {
+    const int m_lo = __shfl_sync(act, m, 0);
+    warp_wide = __all_sync(act, m == m_lo);
+  }
+  if (warp_wide) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+      total += __shfl_xor_sync(0xffffffffu, total, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMax(&mesh_info[S * m + 4], len);
+      atomicAdd(&mesh_info[S * m + 0], total);
+    }
+  } else {
+    atomicMax(&mesh_info[S * m + 4], len);
+    if (total) atomicAdd(&mesh_info[S * m + 0], total);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -369,31 +451,39 @@ int focusr_laplacian_build(const double* points, int point_dim, const int* tris,
   FB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)n_points + 1), stream));
   FB_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int) * ((size_t)n_points + 1), stream));
   FB_CUDA(cudaMemsetAsync(bad, 0, sizeof(int) * 4, stream));
-  FB_CUDA(cudaMemsetAsync(mesh_info, 0, sizeof(int) * 4 * (size_t)n_meshes, stream));
+  FB_CUDA(cudaMemsetAsync(mesh_info, 0, sizeof(int) * FOCUSR_MESH_INFO_INTS * (size_t)n_meshes, stream));
   if (n_edges > 0) {
     k_edge_count<<<div_up(n_edges, T), T, 0, stream>>>(tris, n_edges, n_points, cnt, bad);
     FB_COUNT_LAUNCH(1);
   }
-  int rc = exclusive_scan_i32(cnt, start, n_points, scan_tmp, stream);
+  // the slot of row i, [row_ptr[i], row_ptr[i+1]), holds its raw directed edges; it is final unless duplicates exist
+  int rc = exclusive_scan_i32(cnt, row_ptr, n_points, scan_tmp, stream);
   if (rc) return rc;
   if (n_edges > 0) {
-    k_edge_fill<<<div_up(n_edges, T), T, 0, stream>>>(tris, n_edges, n_points, start, cursor, raw_cols);
+    k_edge_fill<<<div_up(n_edges, T), T, 0, stream>>>(tris, n_edges, n_points, row_ptr, cursor, cols);
     FB_COUNT_LAUNCH(1);
   }
-  k_row_sort_unique<<<div_up(n_points, T), T, 0, stream>>>(points, point_dim, n_points, start, raw_cols, ucnt,
-                                                           degree, degree_inv);
-  FB_COUNT_LAUNCH(1);
-  rc = exclusive_scan_i32(ucnt, row_ptr, n_points, scan_tmp, stream);
-  if (rc) return rc;
-  k_compact<<<div_up(n_points, T), T, 0, stream>>>(points, point_dim, n_points, start, raw_cols, row_ptr, cols, weights);
-  k_mesh_stats<<<div_up(n_points, T), T, 0, stream>>>(row_ptr, cols, weights, n_points, mesh_point_off,
-                                                      n_meshes, mesh_info);
+  k_row_finish<<<div_up(n_points, T), T, 0, stream>>>(points, point_dim, n_points, row_ptr, cols, weights, ucnt, degree,
+                                                      degree_inv, bad + 1);
+  k_mesh_stats<<<div_up(n_points, T), T, 0, stream>>>(row_ptr, ucnt, cols, weights, n_points, mesh_point_off, n_meshes,
+                                                      mesh_info);
   FB_COUNT_LAUNCH(2);
   FB_LAUNCH_CHECK();
-  int bad_host = 0;
-  FB_CUDA(cudaMemcpyAsync(&bad_host, bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  int bad_host[2] = {0, 0};
+  FB_CUDA(cudaMemcpyAsync(bad_host, bad, sizeof(bad_host), cudaMemcpyDeviceToHost, stream));
   FB_CUDA(cudaStreamSynchronize(stream));
-  FB_REQUIRE(bad_host == 0, "laplacian_build: %d triangle corner(s) index outside [0, n_points)", bad_host);
+  FB_REQUIRE(bad_host[0] == 0, "laplacian_build: %d triangle corner(s) index outside [0, n_points)", bad_host[0]);
+  if (bad_host[1] > 0) {
+    // duplicates were collapsed: close the gaps (sorted unique columns -> raw_cols at the old offsets -> final offsets,
+    // weights recomputed: the same products as in k_row_finish)
+    FB_CUDA(cudaMemcpyAsync(start, row_ptr, sizeof(int) * ((size_t)n_points + 1), cudaMemcpyDeviceToDevice, stream));
+    k_copy_ints<<<div_up(n_edges, T), T, 0, stream>>>(cols, raw_cols, n_edges);
+    rc = exclusive_scan_i32(ucnt, row_ptr, n_points, scan_tmp, stream);
+    if (rc) return rc;
+    k_compact<<<div_up(n_points, T), T, 0, stream>>>(points, point_dim, n_points, start, raw_cols, row_ptr, cols, weights);
+    FB_COUNT_LAUNCH(2);
+    FB_LAUNCH_CHECK();
+  }
   return FB_OK;
 }
 

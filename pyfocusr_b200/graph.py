@@ -268,7 +268,8 @@ def recursive_eig(matrix, k, n_k_needed, k_buffer=1, sigma=1e-10, which="LM"):
     g.degree_inv = torch.ones(n, dtype=torch.float64, device=dev)
     empty_rows = int(np.sum((np.diff(lap.indptr) == 0)))
     # general matrix: force the Euclidean (non-symmetric) Rayleigh-Ritz path
-    g.mesh_info_host = np.array([[off.nnz, max(1, off.nnz), empty_rows, 0]], dtype=np.int32)
+    max_row = int(np.max(np.diff(off.indptr))) if n else 0
+    g.mesh_info_host = np.array([[off.nnz, max(1, off.nnz), empty_rows, 0, max_row, 0, 0, 0]], dtype=np.int32)
     g.nnz = off.nnz
     # start block from a 1-D embedding of the row index (no geometry available)
     t = np.linspace(-1.0, 1.0, n)

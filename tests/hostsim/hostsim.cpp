@@ -186,7 +186,17 @@ struct HostBackend {
   }
   // fp32 correction pass as k_spmm_corr runs it: X += z_deg, z_{k+1} = alpha_kj ((L - c) z_k + r_j) - gamma_kj z_{k-1}, z_0 = 0;
   // z, r, matrix entries and tables rounded to float, float arithmetic; tables are [mesh][step][column]
-  void filter_correction(int deg_m, const double* alpha, const double* gamma, const double* center) {
+  void filter_correction(int deg_m, const double* a_m, const double* beta_m) {
+    // the per-column tables, as k_corr_tables builds them on the GPU
+    std::vector<double> alpha((size_t)M * deg_m * B), gamma((size_t)M * deg_m * B), center(M);
+    for (int m = 0; m < M; ++m) {
+      center[m] = 0.5 * (beta_m[m] + a_m[m]);
+      for (int j = 0; j < B; ++j)
+        fb::corr_table_column(a_m[m], theta[(size_t)m * B + j], beta_m[m], deg_m, [&](int s, double al, double ga) {
+          alpha[((size_t)m * deg_m + s) * B + j] = al;
+          gamma[((size_t)m * deg_m + s) * B + j] = ga;
+        });
+    }
     std::vector<float> p(X.size(), 0.f), z(X.size(), 0.f), n(X.size()), acc(B), r(X.size());
     for (size_t t = 0; t < X.size(); ++t) r[t] = (float)R[t];
     for (int s = 0; s < deg_m; ++s) {

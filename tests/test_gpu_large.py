@@ -32,7 +32,7 @@ def test_icosphere_1m_k10():
     m = icosphere(316)
     assert m.points.shape[0] == 998562
     g = DeviceGraph([m.points], [m.tris])
-    assert g.mesh_info_host[0].tolist() == [3 * m.tris.shape[0], 0, 0, 0]
+    assert g.mesh_info_host[0].tolist() == [3 * m.tris.shape[0], 0, 0, 0, 6, 0, 0, 0]
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     vals, vecs, info = g.eigs_smallest(k=11, n_k_needed=10, k_buffer=1)

@@ -61,7 +61,8 @@ def test_laplacian_bit_exact(torch, shipped_meshes, synth, golden):
         assert np.array_equal(lv, lap.data), name + ": Laplacian values not bit-exact"
         pat = (a != 0).astype(np.int8)
         oneway = int((pat - pat.multiply(pat.T)).nnz)  # stored (i,j) whose mirror (j,i) is not stored
-        assert g.mesh_info_host[0].tolist() == [a.nnz, oneway, int(np.sum(deg == 0)), 0], name
+        longest = int(np.max(np.diff(a.indptr)))
+        assert g.mesh_info_host[0].tolist() == [a.nnz, oneway, int(np.sum(deg == 0)), 0, longest, 0, 0, 0], name
     # golden counts of the shipped 15k meshes
     for tag, nm in (("15k_t", "target_mesh_15k"), ("15k_s", "source_mesh_15k")):
         m = shipped_meshes[nm]
@@ -220,23 +221,23 @@ def test_eigs_synthetic_and_batch_consistency(torch, synth):
 
 @pytest.mark.parametrize("block", [16, 24, 32, 48])
 def test_eigs_mixed_precision_passes(torch, shipped_meshes, synth, block):
-    """By default the filter passes iterate in fp32 (k_spmm_f32 on fp32 blocks, then k_spmm_corr: the correction form
-    driven by the fp64 residual; float4 slices, 2 or 4 threads per row); focusr_set_tuning(3, 0) keeps fp64 throughout.
-    Both meet the fp64 tolerance and the oracle; the fp32 passes cost no extra filter degree."""
-    from pyfocusr_b200 import _lib
+    """By default the filter passes iterate in fp32 (k_filter_sell on the sliced-ELL fp32 copy of the matrix: plain fp32
+    blocks, then the correction form driven by the fp64 residual; float4 slices, 2 or 4 threads per row);
+    options.mixed_precision = 0 keeps fp64 throughout.  Both meet the fp64 tolerance and the oracle; the fp32 passes cost
+    no extra filter degree.  Every cache-policy / occupancy variant of the kernels gives bit-identical eigenvectors."""
     from pyfocusr_b200._device import DeviceGraph
 
     ms = [shipped_meshes["target_mesh"], synth["ell20a"], synth["ell39"]]
     g = DeviceGraph([m.points for m in ms], [m.tris for m in ms])
     out = {}
-    try:
-        for mixed in (1, 0):
-            _lib.call("focusr_set_tuning", 3, mixed)
-            vals, vecs, info = g.eigs_smallest(k=7, n_k_needed=6, block_size=block)
-            out[mixed] = (vals.cpu().numpy(), vecs.cpu().numpy(), info)
-    finally:
-        _lib.call("focusr_set_tuning", 3, 1)
+    for mixed in (1, 0):
+        vals, vecs, info = g.eigs_smallest(k=7, n_k_needed=6, block_size=block, options=dict(mixed_precision=mixed))
+        out[mixed] = (vals.cpu().numpy(), vecs.cpu().numpy(), info)
     (v1, x1, i1), (v0, x0, i0) = out[1], out[0]
+    for opt in (dict(filter_policy=0, filter_prefetch=0), dict(filter_policy=3), dict(filter_min_blocks=6)):
+        _, xv, iv = g.eigs_smallest(k=7, n_k_needed=6, block_size=block, options=opt)
+        assert np.array_equal(xv.cpu().numpy(), x1), opt
+        assert np.array_equal(iv["filter_degree"], i1["filter_degree"])
     assert i1["status"].tolist() == [0, 0, 0] and i0["status"].tolist() == [0, 0, 0]
     assert np.all(i0["fp32_filter_degree"] == 0)
     assert np.all(i1["fp32_filter_degree"] > 10) and np.all(i1["fp32_filter_degree"] <= 10 + i1["filter_degree"])
@@ -531,24 +532,11 @@ def test_batch_equals_oracle_and_single(torch, synth):
     n_s = [m.points.shape[0] for m in s]
     fin = out["final_idx"].cpu().numpy()
     wavg = out["weighted_avg_transformed_points"].cpu().numpy()
-    q0 = 0
+    from parity_checks import check_pair_against_oracle
+
     for p in range(2):
-        got = fin[q0:q0 + n_s[p]]
-        assert got.min() >= 0 and got.max() < t[p].points.shape[0]
-        # stages after the solver against the oracle fed OUR pre-sort eigenvectors (eigsort's costs
-        # depend on the arbitrary sign of the target eigenvectors)
-        o_t, o_s = off[p], off[2 + p]
-        vt = pre[o_t:o_t + t[p].points.shape[0], :nf[p]].copy()
-        vs = pre[o_s:o_s + n_s[p], :nf[2 + p]].copy()
-        srt = port.sort_eigenmaps(t[p].points, s[p].points, out["idx_t"][p], out["idx_s"][p], vals[p, :nf[p]],
-                                  vals[2 + p, :nf[2 + p]], vt, vs, 6, True)
-        assert np.max(np.abs(out["Q"][p] - srt["Q"]) / srt["Q"]) <= 1e-9
-        assert np.array_equal(post[o_s:o_s + n_s[p], :6], vs[:, :6])
-        w = port.spectral_weights(srt["Q"], vals[2 + p], vals[p], 3)
-        cs = port.correspondence_stage(dict(A=port.adjacency(t[p].points, t[p].tris)), dict(A=port.adjacency(s[p].points, s[p].tris)),
-                                       t[p].points, s[p].points, port.spectral_coords(vt, w, 3), port.spectral_coords(vs, w, 3), 30, 10)
-        assert np.mean(got == cs["final_idx"]) >= 0.999
-        q0 += n_s[p]
+        # stages after the solver against the oracle: indices EQUAL (tests/parity_checks.py has the chain of custody)
+        check_pair_against_oracle(port, out, p, 2, t[p].points, t[p].tris, s[p].points, s[p].tris, 6, 3, 30, 10)
     single = SpectralBatch(n_coords_spectral_ordering=2000, graph_smoothing_iterations=30, projection_smooth_iterations=10)
     o1 = single.run_meshes(t[:1], s[:1], idx_t=out["idx_t"][:1], idx_s=out["idx_s"][:1])
     assert np.array_equal(o1["final_idx"].cpu().numpy(), fin[: n_s[0]])
@@ -709,7 +697,7 @@ def test_error_behaviour_and_degenerate_inputs(torch):
         DeviceGraph([tiny.points], [tiny.tris]).eigs_smallest(k=7, n_k_needed=6)
     # a mesh without any triangle: every row has zero degree, the Laplacian is empty
     g0 = DeviceGraph([m.points], [np.zeros((0, 3), dtype=np.int32)])
-    assert g0.nnz == 0 and g0.mesh_info_host[0].tolist() == [0, 0, m.points.shape[0], 0]
+    assert g0.nnz == 0 and g0.mesh_info_host[0].tolist() == [0, 0, m.points.shape[0], 0, 0, 0, 0, 0]
     assert g0.laplacian_host()[0][-1] == 0
     # more neighbours requested than references exist: missing slots are -1 / inf
     refs = torch.from_numpy(np.random.RandomState(0).rand(2, 3)).cuda()
@@ -752,27 +740,29 @@ def test_hungarian_correspondence(torch, synth):
         pyfocusr.Focusr(t, s, icp_register_first=False, initial_correspondence_type="nearest")
 
 
-def test_cluster_smoothing_is_bit_identical(torch, shipped_meshes, synth):
-    """focusr_mean_filter_meshes (all passes of a mesh inside one thread-block cluster, distributed shared memory)
-    against the one-launch-per-pass kernel: bit-identical, for 1 and 3 columns, mixed mesh sizes, sub-ranges of the
-    batch, an isolated vertex, and odd / even / single iteration counts."""
+def test_smoothing_sub_ranges_and_columns(torch, shipped_meshes, synth):
+    """focusr_mean_filter on sub-ranges of a batch (mixed mesh sizes, an isolated vertex), 1 and 3 columns, odd / even /
+    single iteration counts: equal to the oracle's scipy product, bit for bit, mesh by mesh."""
+    from oracle import port
     from pyfocusr_b200._device import DeviceGraph
     from pyfocusr_b200.mesh import icosphere
 
     small = icosphere(3)
     pts = np.concatenate([small.points, [[9.0, 9.0, 9.0]]])                    # unreferenced vertex: empty row
     ms = [shipped_meshes["source_mesh_15k"], synth["ell20a"], shipped_meshes["target_mesh"], synth["ell39"]]
-    g = DeviceGraph([m.points for m in ms] + [pts], [m.tris for m in ms] + [small.tris])
+    all_pts, all_tris = [m.points for m in ms] + [pts], [m.tris for m in ms] + [small.tris]
+    g = DeviceGraph(all_pts, all_tris)
     off = g.mesh_off_host
+    adj = [port.adjacency(p, t) for p, t in zip(all_pts, all_tris)]
     rng = np.random.RandomState(0)
     for c in (3, 1):
-        x = torch.from_numpy(rng.standard_normal((g.n_points, c))).cuda()
+        x_h = rng.standard_normal((g.n_points, c))
+        x = torch.from_numpy(x_h).cuda()
         for iters, (mb, me) in ((1, (0, 5)), (2, (1, 3)), (7, (0, 5)), (40, (2, 5)), (301, (3, 4))):
             r0, r1 = int(off[mb]), int(off[me])
-            a = g.mean_filter(x, iters, r0, r1, cluster=True)
-            b = g.mean_filter(x, iters, r0, r1, cluster=False)
-            assert torch.equal(a[r0:r1], b[r0:r1]), (c, iters, mb, me)
-    # a range that is not made of whole meshes silently takes the per-pass path
-    a = g.mean_filter(x, 3, 10, 5000, cluster=True)
-    b = g.mean_filter(x, 3, 10, 5000, cluster=False)
-    assert torch.equal(a[10:5000], b[10:5000])
+            got = g.mean_filter(x, iters, r0, r1).cpu().numpy()
+            for m in range(mb, me):
+                ref = port.mean_filter(adj[m], x_h[off[m]:off[m + 1]], iters)
+                assert np.array_equal(got[off[m]:off[m + 1]], ref), (c, iters, m)
+    with pytest.raises(ValueError):
+        g.mean_filter(x, 3, 10, 5000)   # not whole meshes

@@ -23,11 +23,11 @@ ms = [fmesh.PolyData(base.points, t), fmesh.perturbed_ellipsoid(7, 1), fmesh.per
 g = DeviceGraph([m.points for m in ms], [m.tris for m in ms])
 for block in (0, 24, 32):
     vals, vecs, info = g.eigs_smallest(k=5, n_k_needed=4, block_size=block)
+    for opt in (dict(filter_policy=3), dict(filter_policy=0, filter_prefetch=0), dict(filter_min_blocks=6)):
+        g.eigs_smallest(k=5, n_k_needed=4, block_size=block, options=opt)
     print("block", block, "status", info["status"].tolist(), "fp32 steps", info["fp32_filter_degree"].tolist(),
           "degree", info["filter_degree"].tolist(), "residual %.1e" % info["max_residual"].max())
-_lib.call("focusr_set_tuning", 3, 0)
-vals, vecs, info = g.eigs_smallest(k=5, n_k_needed=4)
-_lib.call("focusr_set_tuning", 3, 1)
+vals, vecs, info = g.eigs_smallest(k=5, n_k_needed=4, options=dict(mixed_precision=0))
 print("fp64 only: status", info["status"].tolist(), "fp32 steps", info["fp32_filter_degree"].tolist())
 sb = SpectralBatch(n_coords_spectral_ordering=200, graph_smoothing_iterations=5, projection_smooth_iterations=3)
 jobs = [sb.pack_meshes([ms[1]], [ms[2]]), sb.pack_meshes([ms[2], ms[3]], [ms[1], ms[1]])]
