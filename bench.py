@@ -65,10 +65,12 @@ def cpu_pair(args):
 
 
 def config_dict(pairs_per_gpu, nu, n):
+    """The workload, in the same words for both arms (how each arm steps through it is in the line's `run` key)."""
     return {"workload": "configs[2]: synthetic perturbed-ellipsoid pairs, nu=%d (%d vertices/mesh), Focusr defaults "
                         "(k=7, 5000 samples, smoothing 300/40), CPD=identity" % (nu, n),
-            "pairs_per_gpu_per_step": pairs_per_gpu, "vertices_per_mesh": n,
-            "l2": "working set >> L2 (batched CSR + blocks ~ %.1f GB per GPU): no flush needed" % (pairs_per_gpu * 2 * 12e6 / 1e9)}
+            "workload_pairs_per_gpu": pairs_per_gpu, "vertices_per_mesh": n,
+            "l2": "GPU arm: working set >> L2 (batched CSR + blocks ~ %.1f GB per GPU), no flush needed; CPU arm: n/a"
+                  % (pairs_per_gpu * 2 * 12e6 / 1e9)}
 
 
 def run_reference(a):
@@ -84,19 +86,20 @@ def run_reference(a):
     pairs_per_step = cores
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
-        for w in range(a.warmup):
-            pool.map(cpu_pair, [(w * pairs_per_step + j, a.nu) for j in range(min(2, pairs_per_step))])
+        for w in range(a.warmup):  # full steps: every worker imports scipy and touches its pages before the clock starts
+            pool.map(cpu_pair, [(w * pairs_per_step + j, a.nu) for j in range(pairs_per_step)])
         t0 = time.perf_counter()
         for s in range(a.steps):
             pool.map(cpu_pair, [(1000 + s * pairs_per_step + j, a.nu) for j in range(pairs_per_step)])
         dt = time.perf_counter() - t0
     value = a.steps * pairs_per_step / dt
-    sample = "%d pairs per step, one pair per process on %d host cores (scipy eigs/cKDTree are single-threaded)" % (
-        pairs_per_step, cores)
+    sample = ("bounded sample of the workload: %d pairs per step (not the %d of the GPU arm's step), one pair per process on "
+              "%d host cores (scipy eigs/cKDTree are single-threaded)" % (pairs_per_step, a.pairs_per_gpu, cores))
     line = {"impl": "reference", "metric": "spectral-embed pairs/sec @15k verts", "value": value, "unit": "pairs/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(a.pairs_per_gpu, a.nu, n),
+            "run": {"pairs_per_step": pairs_per_step, "processes": cores},
             "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -173,68 +176,104 @@ def run_ours(a):
     for ids in groups:
         pts, tris, off, n, f, _ = make_pairs(ids, a.nu)
         pts_pin = torch.from_numpy(pts).pin_memory()
-        tris_dev = torch.from_numpy(tris).cuda()
+        tris_pin = torch.from_numpy(tris).pin_memory()
         sizes = np.diff(off)
         p_sub = len(ids)
         idx_t, idx_s = sb.sample_indices(sizes[:p_sub], rng), sb.sample_indices(sizes[p_sub:], rng)
-        common = dict(tris=tris_dev, mesh_off_host=off, n_pairs=p_sub, idx_t=idx_t, idx_s=idx_s)
-        jobs.append(dict(points=pts_pin.cuda(), **common))
-        jobs_e2e.append(dict(points=pts_pin, **common))   # H2D of the vertices inside the timed region
-        h2d += pts_pin.numel() * 8
+        common = dict(mesh_off_host=off, n_pairs=p_sub, idx_t=idx_t, idx_s=idx_s)
+        jobs.append(dict(points=pts_pin.cuda(), tris=tris_pin.cuda(), **common))
+        # e2e: the whole mesh (vertices AND triangles) goes host -> device inside the timed region, as a real call does
+        jobs_e2e.append(dict(points=pts_pin, tris=tris_pin, **common))
+        h2d += pts_pin.numel() * 8 + tris_pin.numel() * 4
     lib = _lib.load()
 
     barrier = fdist.barrier
+    D = max(1, a.in_flight)
+    last = {}
 
-    def step_resident():
-        return sb.run_concurrent(jobs)
+    def certify(infos):
+        """The timed run's own outputs: every mesh of the step converged (status 0) with its fp64 residual
+        ||L v - theta v|| <= 1e-10 ||v||.  Raises otherwise: a throughput number from a step that did not solve its
+        problems is not a number."""
+        worst, fp32_steps, steps = 0.0, 0, 0
+        for info in infos:
+            if not (np.all(info["status"] == 0) and np.all(info["n_found"] >= sb.n)):
+                raise RuntimeError("bench: a mesh of the timed step did not converge: status %s" % info["status"].tolist())
+            worst = max(worst, float(info["max_residual"].max()))
+            fp32_steps = max(fp32_steps, int(info["fp32_filter_degree"].max()))
+            steps = max(steps, int(info["filter_degree"].max()))
+        if not worst <= 1e-10:
+            raise RuntimeError("bench: max residual %.3e of the timed step exceeds the tolerance 1e-10" % worst)
+        return worst, fp32_steps, steps
 
     d2h = [0]
 
-    def step_e2e():
-        outs = sb.run_concurrent(jobs_e2e)
-        # correspondences + weighted positions -> pinned host memory
-        d2h[0] = sum(v.nbytes for k, o in enumerate(outs) for v in sb.fetch(o, slot=k).values())
-        return outs
+    def keep_info(out, k):      # resident run: nothing is read back but the solver's per-mesh report (host arrays)
+        return out["eigs_info"]
+
+    def fetch_results(out, k):  # e2e run: correspondences + weighted positions -> pinned host memory, per step
+        d2h[0] = S * sum(v.nbytes for v in sb.fetch(out, slot=None).values())
+        return out["eigs_info"]
+
+    def run_steps(steps, e2e):
+        """`steps` steps of the hot path over this rank's pairs.  A step is either ONE batch of all P pairs (S = 1) with
+        up to D steps in flight (SpectralBatch.run_pipelined: kernels keep their full size, the tail of a step hides under
+        the filter of the next), or S sub-batches of P / S pairs run concurrently (SpectralBatch.run_concurrent)."""
+        js, consume = (jobs_e2e if e2e else jobs), (fetch_results if e2e else keep_info)
+        if S == 1:
+            infos = sb.run_pipelined([js[0]] * steps, depth=D, consume=consume)
+            last["infos"] = infos[-1:]
+        else:
+            for _ in range(steps):
+                outs = sb.run_concurrent(js)
+                last["infos"] = [consume(o, k) for k, o in enumerate(outs)]
 
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            fn()
+        fn(steps)
         e1.record()
         barrier()
         return fdist.all_reduce_max(e0.elapsed_time(e1))  # device time, slowest rank
 
-    for _ in range(a.warmup):
-        step_resident()
+    run_steps(max(a.warmup, D), False)
     sampler = ClockSampler(local) if rank == 0 else None
     lib.focusr_profile_reset()
     l0 = _lib.launch_count()
-    ms = timed(step_resident, a.steps)
+    ms = timed(lambda k: run_steps(k, False), a.steps)
     launches = _lib.launch_count() - l0
-    ms_kernels, kernel_pass = ms, "the timed region"
-    if S > 1 or sb.overlap_smoothing:
-        # with several streams in flight (sub-batches, the smoothing side stream) launches interleave and a kernel's
-        # duration is not defined; the per-kernel numbers (roofline) come from the same K steps run again right away,
-        # still under the clock sampler, one stream only: sub-batches one after the other, smoothing in line -- same
-        # launches, same sizes, nothing else on the GPU
-        lib.focusr_profile_reset()
-        ov, sb.overlap_smoothing = sb.overlap_smoothing, False
-        [sb.run(**job) for job in jobs]   # warm-up of this form (the caching allocator keeps a pool per stream)
-        lib.focusr_profile_reset()
-        ms_kernels = timed(lambda: [sb.run(**job) for job in jobs], a.steps)
-        sb.overlap_smoothing = ov
-        kernel_pass = "a second pass of the same %d steps on one stream (sub-batches one after the other, smoothing in line: %.1f ms per step)" % (
-            a.steps, ms_kernels / a.steps)
+    max_residual, fp32_steps, filter_steps = certify(last["infos"])
+    max_residual = fdist.all_reduce_max(max_residual)
+    # With several streams in flight (steps, sub-batches, the smoothing side stream) launches interleave and a kernel's
+    # duration is not defined; the per-kernel numbers (roofline) come from the same K steps run again right away, still
+    # under the clock sampler, on ONE stream: steps / sub-batches one after the other, smoothing in line -- same launches,
+    # same sizes, nothing else on the GPU.
+    lib.focusr_profile_reset()
+    ov, sb.overlap_smoothing = sb.overlap_smoothing, False
+    [sb.run(**job) for job in jobs]   # warm-up of this form (the caching allocator keeps a pool per stream)
+    lib.focusr_profile_reset()
+    ms_kernels = timed(lambda k: [sb.run(**job) for _ in range(k) for job in jobs], a.steps)
+    sb.overlap_smoothing = ov
+    kernel_pass = "a second pass of the same %d steps on one stream (%d pairs per launch, smoothing in line: %.1f ms per step)" % (
+        a.steps, P // S, ms_kernels / a.steps)
     prof = np.zeros(4)
     lib.focusr_profile_get(prof.ctypes.data)
     prof32, profc = np.zeros(4), np.zeros(4)
     lib.focusr_profile_get_kind(1, prof32.ctypes.data)  # filter passes on fp32 blocks (k_spmm_f32)
     lib.focusr_profile_get_kind(2, profc.ctypes.data)   # filter passes in fp32 correction form (k_spmm_corr)
     clocks = sampler.stop() if sampler else None
-    step_e2e()
-    ms_e2e = timed(step_e2e, a.steps)
+    run_steps(D, True)
+    ms_e2e = timed(lambda k: run_steps(k, True), a.steps)
+    certify(last["infos"])
+    # the same steps with every filter pass in fp64 (options.mixed_precision = 0): what the fp32 inner iterations buy
+    opts = dict(sb.eigs_options or {})
+    sb.eigs_options = dict(opts, mixed_precision=0)
+    run_steps(D, False)
+    k64 = min(a.steps, 6)
+    ms_fp64 = timed(lambda k: run_steps(k, False), k64) * a.steps / k64
+    res_fp64, _, steps_fp64 = certify(last["infos"])
+    sb.eigs_options = opts or None
     # per-stage breakdown (one extra, untimed step on one stream: sub-batches one after the other, smoothing in line;
     # times summed)
     stages = {}
@@ -256,12 +295,13 @@ def run_ours(a):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
-    # The Chebyshev filter step exists in three forms: fp64 (k_spmm), fp32 blocks (k_spmm_f32) and
-    # the fp32 correction form (k_spmm_corr).  Each is timed live by the library (CUDA events around every filter
-    # application, on the launching stream); the roofline line is the one that holds the largest share of the step.
+    # The Chebyshev filter step exists in three forms: fp64 on CSR (k_spmm), and fp32 blocks / the
+    # fp32 correction form on the sliced-ELL fp32 copy of the matrix (k_filter_sell modes 0 and 3).  Each is timed live by
+    # the library (CUDA events around every filter application, on the launching stream); the roofline line is the one
+    # that holds the largest share of the step.
     kinds = [("fp64", "k_spmm<16,8,0> (Chebyshev filter step: CSR SpMM + three-term update, fp64 blocks)", prof),
-             ("fp32", "k_spmm_f32<16,4,0> (same step on fp32 blocks: spectrum probe + first pass)", prof32),
-             ("fp32_correction", "k_spmm_corr<16,4,0> (same step in fp32 correction form: z = p(L)x - x driven by the fp64 "
+             ("fp32", "k_filter_sell<16,4,0> (same step on fp32 blocks, sliced-ELL matrix: spectrum probe + first pass)", prof32),
+             ("fp32_correction", "k_filter_sell<16,4,3> (same step in fp32 correction form: z = p(L)x - x driven by the fp64 "
                                  "residual; the pass that reaches the tolerance)", profc)]
     tpath = os.path.join(ROOT, "profiles", "filter_traffic.json")
     traffic = json.load(open(tpath)) if os.path.exists(tpath) else {}
@@ -313,13 +353,21 @@ def run_ours(a):
         cpu = {"value": len(times) / sum(times), "unit": "pairs/s", "cores": 1, "kind": "port",
                "sample": "%d pairs of the same workload, oracle/port.py (reference algorithm: scipy eigs shift-invert, "
                          "cKDTree, sparse smoothing) in one process, %.1f s" % (len(times), time.perf_counter() - t0)}
+    secondary["value_fp64_only"] = {"value": world * P * a.steps / (ms_fp64 / 1e3), "unit": "pairs/s",
+                                    "ms_per_step": ms_fp64 / a.steps, "filter_steps": steps_fp64, "max_residual": res_fp64,
+                                    "note": "same step with options.mixed_precision = 0: every filter pass in fp64"}
     line = {"metric": "spectral-embed pairs/sec @15k verts", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 (fp32 inner filter)", "data": "synthetic",
+            "max_residual": max_residual,
+            "certified": "every mesh of the last timed step: status 0 and ||L v - theta v|| <= 1e-10 ||v|| in fp64 "
+                         "(%d of its %d filter steps iterate in fp32)" % (fp32_steps, filter_steps),
             "precision": "results fp64 (every returned eigenpair meets ||Lv - theta v|| <= 1e-10 ||v|| in fp64; Laplacian, smoothing, "
                          "KNN, positions fp64 bit-exact); inside the eigensolver the filter passes iterate in fp32 (see "
                          "secondary_metrics.filter_step_forms), Rayleigh-Ritz and residuals in fp64",
-            "config": dict(config_dict(P, a.nu, n), sub_batches_in_flight=S), "clocks": clocks,
+            "config": config_dict(P, a.nu, n),
+            "run": {"pairs_per_step": P, "steps_in_flight": D if S == 1 else 1, "sub_batches_in_flight": S,
+                    "pairs_per_launch": P // S}, "clocks": clocks,
             "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h[0] * world,
                     "ms_per_step": ms_e2e / a.steps},
             "gpu_launches": int(total_launches), "roofline": roofline, "cpu_baseline": cpu, "stage_ms": stages, "secondary_metrics": secondary}
@@ -381,7 +429,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs-per-gpu", type=int, default=128)
-    ap.add_argument("--sub-batches", type=int, default=2, help="sub-batches of a GPU's pairs in flight at once")
+    ap.add_argument("--in-flight", type=int, default=2, help="steps in flight at once (whole batches, one stream each)")
+    ap.add_argument("--sub-batches", type=int, default=1,
+                    help="> 1: split a step's pairs into sub-batches run concurrently instead of pipelining whole steps")
     ap.add_argument("--nu", type=int, default=NU)
     ap.add_argument("--cpu-pairs", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -114,11 +114,13 @@ size_t focusr_eigs_workspace_bytes_mixed(int n_points, long long sell_entries_ca
  * the fp32 filter steps and exist for A/B measurements (csrc/sell.cu has the record). */
 typedef struct focusr_eigs_options {
   int mixed_precision;   /* 1 (default): fp32 filter passes for symmetric adjacencies; 0: every pass fp64 */
-  int filter_policy;     /* fp32 filter steps: bit 1 (default) = no L1 allocation + L2 evict_first on the single-use
-                            streams, bit 0 = L2 evict_last on the gathered block */
+  int filter_policy;     /* fp32 filter steps: bit 1 = no L1 allocation + L2 evict_first on the single-use streams,
+                            bit 0 = L2 evict_last on the gathered block; default 3 = both */
   int filter_prefetch;   /* 1 (default): the CTA asks L2 early for the lines it will stream */
   int filter_min_blocks; /* resident CTAs per SM the b = 16 kernels are compiled for: 8 (default), 6 or 5 */
-  int reserved[12];
+  int filter_pdl;        /* 2 (default): steps chained by programmatic dependent launch, constant streams prefetched
+                            before the dependency wait; 1: the same, prefetch after the wait; 0: plain launches */
+  int reserved[11];
 } focusr_eigs_options;
 void focusr_eigs_default_options(focusr_eigs_options* options);
 int focusr_eigs_block_size(int k, int n_k_needed, int k_buffer, int max_one_way, int max_zero_rows);

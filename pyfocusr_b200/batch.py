@@ -245,6 +245,56 @@ class SpectralBatch:
         return results
 
     # ------------------------------------------------------------------------------------------
+    def run_pipelined(self, jobs, depth=2, consume=None, **kw):
+        """A stream of independent batches with at most ``depth`` of them in flight, one host thread and one CUDA stream
+        each: ``jobs`` is an iterable of dicts of ``run`` keyword arguments (successive steps of a production queue).
+        Unlike ``run_concurrent`` the launches keep their full size -- every kernel works on a whole batch -- while the
+        FP64-ALU / latency-bound tail of one batch (eigsort, KNN, host visits) hides under the HBM-bound filter steps of
+        the next.  ``consume(out, k)`` runs in the worker thread right after batch k has been enqueued, with its stream
+        current (read results back there, keep what is needed); what it returns is collected in order.  Default: the
+        whole result dict is kept (its tensors are handed over to the caller's stream)."""
+        from concurrent.futures import ThreadPoolExecutor
+
+        torch = _lib.require_cuda()
+        jobs = [dict(j) for j in jobs]
+        depth = max(1, min(int(depth), len(jobs)))
+        main = torch.cuda.current_stream()
+        device = torch.cuda.current_device()
+        if depth == 1:
+            return [consume(self.run(**j, **kw), k) if consume else self.run(**j, **kw) for k, j in enumerate(jobs)]
+        if self._pool is None or self._pool._max_workers < depth:
+            self._pool = ThreadPoolExecutor(max_workers=depth)  # kept: workers own pinned pools and streams
+        streams = set()
+        lock = threading.Lock()
+
+        def work(item):
+            k, job = item
+            with torch.cuda.device(device):
+                if getattr(self._tls, "stream", None) is None:
+                    self._tls.stream = torch.cuda.Stream(device=device)
+                st = self._tls.stream
+                with lock:
+                    streams.add(st)
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    out = self.run(**job, **kw)
+                    if consume is not None:
+                        return consume(out, k)
+                    for obj in (out, out.get("graph")):
+                        if obj is None:
+                            continue
+                        for v in (obj.values() if isinstance(obj, dict) else vars(obj).values()):
+                            if isinstance(v, torch.Tensor) and v.is_cuda:
+                                v.record_stream(main)
+                    return out
+
+        # ThreadPoolExecutor hands items to idle workers in order: at most `depth` batches are in flight
+        results = list(self._pool.map(work, list(enumerate(jobs))))
+        for st in streams:
+            main.wait_stream(st)
+        return results
+
+    # ------------------------------------------------------------------------------------------
     def _register_pairs(self, coords, off, P, sizes):
         """focusr.py:537-543 per pair: affine on fresh random subsets, transform all target coordinates, then
         deformable on fresh subsets, transform again.  Returns the index draws [(s_aff, t_aff, s_def, t_def)].
@@ -315,8 +365,11 @@ class SpectralBatch:
     def fetch(self, out, keys=("final_idx", "weighted_avg_transformed_points"), slot=0):
         """Device -> host read-back of the per-vertex results into reusable pinned buffers (one
         asynchronous copy each, then a single synchronisation).  Returns numpy views that stay valid
-        until the next ``fetch`` with the same ``slot`` (one slot per sub-batch of ``run_concurrent``)."""
+        until the next ``fetch`` with the same ``slot`` (one slot per sub-batch of ``run_concurrent``; ``slot=None`` =
+        one slot per calling thread, for the workers of ``run_pipelined``)."""
         torch = _lib.require_cuda()
+        if slot is None:
+            slot = ("thread", threading.get_ident())
         if not hasattr(self, "_pinned"):
             self._pinned = {}
         res = {}

@@ -1129,9 +1129,10 @@ size_t focusr_eigs_workspace_bytes_mixed(int n_points, long long sell_entries_ca
 
 void focusr_eigs_default_options(focusr_eigs_options* o) {
   o->mixed_precision = 1;
-  o->filter_policy = 2;
+  o->filter_policy = 3;
   o->filter_prefetch = 1;
   o->filter_min_blocks = 8;
+  o->filter_pdl = 2;
   for (int& r : o->reserved) r = 0;
 }
 
@@ -1205,6 +1206,7 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
   tune.policy = opt.filter_policy;
   tune.prefetch = opt.filter_prefetch;
   tune.min_blocks = opt.filter_min_blocks;
+  tune.pdl = opt.filter_pdl;
   {
     bool any_sym = false;
     for (int m = 0; m < n_meshes; ++m) any_sym = any_sym || mesh_info_host[FOCUSR_MESH_INFO_INTS * m + 1] == 0;

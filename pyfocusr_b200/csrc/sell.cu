@@ -11,8 +11,11 @@
 //     Measured on B200, 128 pairs per launch (tools/kernel_ab.py, gpurun_out/r2_ab1.log): correction step 0.2494 ms (CSR)
 //     -> 0.2793 (SELL, default cache policy) -> 0.2277 ms (SELL + stream policy) = 5.40 TB/s = 82.7% of the measured HBM
 //     peak by algorithmic bytes; plain fp32 step 0.2024 -> 0.2003 ms (75%).  evict_last on the gathered block instead:
-//     0.2430 / 0.2374 ms (worse for the plain step); both: 0.2298 / 0.1985.  6 or 5 resident CTAs per SM (40 / 46
-//     registers): 0.2537 / 0.2593 ms; without the L2 prefetch of the CTA's streams: 0.2696 ms.  The CSR kernels are gone.
+//     0.2430 / 0.2374 ms (worse for the plain step); both (the default): 0.2298 / 0.1985.  6 or 5 resident CTAs per SM
+//     (40 / 46 registers): 0.2537 / 0.2593 ms; without the L2 prefetch of the CTA's streams: 0.2696 ms.  The absolute
+//     numbers move by +-8% from one B200 of the pool to the next (r2_ab1..3.log); the order of the variants does not,
+//     except that stream policy alone vs both is a toss-up for the correction step and both is never worse for the
+//     plain step (0.1855 vs 0.2210, 0.1864 vs 0.1886, 0.1985 vs 0.2003 ms on three boxes).  The CSR kernels are gone.
 // (2) Programmatic dependent launch: every step of a chain is launched with programmaticStreamSerialization; a CTA
 //     first asks L2 for the data of its rows that the previous step does not write (matrix slice, r, z_prev), then
 //     executes griddepcontrol.wait, then griddepcontrol.launch_dependents.  The next step's CTAs therefore become
@@ -21,7 +24,9 @@
 //     diagonal in at its sorted position -- scipy's accumulation order, bit for bit.  A sliced-ELL form of the smoothing
 //     matrix (entries pre-multiplied, padded [n][4] iterates fetched with one 256-bit load) was measured at 18.6 / 17.95 ms
 //     against 17.8 ms for 300 passes over 128 meshes and removed: the pass is bound by its 6.4-wave launches, not by
-//     the row walk.
+//     the row walk (programmatic dependent launch: 17.8 -> 17.0 ms).  Marking the matrix stream evict_first in L2, which
+//     pays in the filter steps, costs here (18.3 -> 20.0 ms): the 140 MB matrix of 128 targets is partly L2-resident
+//     from one pass to the next.
 #include <vector>
 
 #include "common.cuh"
@@ -231,7 +236,7 @@ k_filter_sell(const int2* __restrict__ entries, const int* __restrict__ slice_pt
               const float2* __restrict__ ddi, const int* __restrict__ mesh_off, const void* __restrict__ y_,
               const float* __restrict__ x_prev, const float* __restrict__ r, void* __restrict__ out_, float* __restrict__ y_copy,
               const void* __restrict__ alpha_, const void* __restrict__ gamma_, const double* __restrict__ center, int step,
-              int n_steps, int has_prev, int prefetch) {
+              int n_steps, int has_prev, int prefetch, int early) {
   constexpr int VPT = B / (4 * TPR);
   static_assert(VPT * 4 * TPR == B, "block size must be a multiple of 4*TPR");
   constexpr bool CORR = MODE >= 3;
@@ -249,6 +254,10 @@ k_filter_sell(const int2* __restrict__ entries, const int* __restrict__ slice_pt
   // this launch only after ITS wait returned).  After it: the rows of y this CTA owns.
   const int pr = r0 + (int)threadIdx.x;
   constexpr int LINES = (B * 4 + 127) / 128;  // 128-byte lines per fp32 row
+  if (!early) {
+    pdl_wait();
+    pdl_launch_dependents();
+  }
   if (prefetch && MODE != 1) {
     if (pr < r1) {
 #pragma unroll
@@ -261,8 +270,10 @@ k_filter_sell(const int2* __restrict__ entries, const int* __restrict__ slice_pt
     const int q0 = slice_ptr[slice0], q1 = slice_ptr[slice0 + ns];
     for (int q = q0 + 16 * (int)threadIdx.x; q < q1; q += 16 * FS_THREADS) prefetch_l2_line(entries + q);
   }
-  pdl_wait();
-  pdl_launch_dependents();
+  if (early) {
+    pdl_wait();
+    pdl_launch_dependents();
+  }
   if (prefetch && MODE != 1 && pr < r1) {
 #pragma unroll
     for (int l = 0; l < LINES; ++l) prefetch_l2_line(yf + (size_t)pr * B + 32 * l);
@@ -376,10 +387,16 @@ k_filter_sell(const int2* __restrict__ entries, const int* __restrict__ slice_pt
 template <int B, int TPR, int MODE, int MINB>
 static void launch_fs_pol(int pol, dim3 grid, cudaStream_t stream, const SellF32& m, const int* mesh_off, const void* y,
                           const float* x_prev, const float* r, void* out, float* y_copy, const void* alpha, const void* gamma,
-                          const double* center, int step, int n_steps, int has_prev, int prefetch) {
-#define FB_FS_GO(P)                                                                                                     \
-  launch_pdl(k_filter_sell<B, TPR, MODE, P, MINB>, grid, dim3(FS_THREADS), stream, m.entries, m.slice_ptr, m.mesh_slice_off, \
-             m.ddi, mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, center, step, n_steps, has_prev, prefetch)
+                          const double* center, int step, int n_steps, int has_prev, int prefetch, int pdl) {
+#define FB_FS_GO(P)                                                                                                        \
+  if (pdl)                                                                                                                 \
+    launch_pdl(k_filter_sell<B, TPR, MODE, P, MINB>, grid, dim3(FS_THREADS), stream, m.entries, m.slice_ptr,               \
+               m.mesh_slice_off, m.ddi, mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, center, step, n_steps, has_prev, \
+               prefetch, pdl == 2 ? 1 : 0);                                                                                \
+  else                                                                                                                     \
+    k_filter_sell<B, TPR, MODE, P, MINB><<<grid, FS_THREADS, 0, stream>>>(m.entries, m.slice_ptr, m.mesh_slice_off, m.ddi,  \
+                                                                          mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, \
+                                                                          center, step, n_steps, has_prev, prefetch, 0)
   switch (pol & 3) {
     case 0: FB_FS_GO(0); break;
     case 1: FB_FS_GO(1); break;
@@ -399,14 +416,14 @@ static int launch_fs_b(int mode, const SellF32& m, const int* mesh_off, int n_me
   constexpr int MB = VPT == 1 ? 8 : (VPT == 2 ? 6 : 3);
   const int hp = has_prev ? 1 : 0, pf = tune.prefetch ? 1 : 0;
 #define FB_FS_MODE(MODE_, MINB_) \
-  launch_fs_pol<B, TPR, MODE_, MINB_>(tune.policy, grid, stream, m, mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, center, step, n_steps, hp, pf)
+  launch_fs_pol<B, TPR, MODE_, MINB_>(tune.policy, grid, stream, m, mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, center, step, n_steps, hp, pf, tune.pdl)
   // the occupancy A/B (6 or 5 resident CTAs instead of 8) exists for the two steady-state b = 16 kernels only
   if (B == 16 && (mode == 0 || mode == 3) && (tune.min_blocks == 6 || tune.min_blocks == 5)) {
     constexpr int BB = B == 16 ? B : 16, TT = B == 16 ? TPR : 4;
-    if (mode == 0 && tune.min_blocks == 6) launch_fs_pol<BB, TT, 0, 6>(tune.policy, grid, stream, m, mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, center, step, n_steps, hp, pf);
-    else if (mode == 0) launch_fs_pol<BB, TT, 0, 5>(tune.policy, grid, stream, m, mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, center, step, n_steps, hp, pf);
-    else if (tune.min_blocks == 6) launch_fs_pol<BB, TT, 3, 6>(tune.policy, grid, stream, m, mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, center, step, n_steps, hp, pf);
-    else launch_fs_pol<BB, TT, 3, 5>(tune.policy, grid, stream, m, mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, center, step, n_steps, hp, pf);
+    if (mode == 0 && tune.min_blocks == 6) launch_fs_pol<BB, TT, 0, 6>(tune.policy, grid, stream, m, mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, center, step, n_steps, hp, pf, tune.pdl);
+    else if (mode == 0) launch_fs_pol<BB, TT, 0, 5>(tune.policy, grid, stream, m, mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, center, step, n_steps, hp, pf, tune.pdl);
+    else if (tune.min_blocks == 6) launch_fs_pol<BB, TT, 3, 6>(tune.policy, grid, stream, m, mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, center, step, n_steps, hp, pf, tune.pdl);
+    else launch_fs_pol<BB, TT, 3, 5>(tune.policy, grid, stream, m, mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, center, step, n_steps, hp, pf, tune.pdl);
   } else {
     switch (mode) {
       case 0: FB_FS_MODE(0, MB); break;
@@ -481,6 +498,7 @@ k_mean_filter(const int* __restrict__ row_ptr, const int* __restrict__ cols, con
   bool diag_done = false;
   for (int p = p1 - 1; p >= p0; --p) {
     const int j = cols[p];
+    const double wp = weights[p];
     if (!diag_done && j < i) {
       const double* xi = x + (size_t)i * nc;
 #pragma unroll
@@ -490,10 +508,10 @@ k_mean_filter(const int* __restrict__ row_ptr, const int* __restrict__ cols, con
     }
     double val;
     if (j == i) {
-      val = FB_MUL(dsm, FB_ADD(weights[p], 1.0));
+      val = FB_MUL(dsm, FB_ADD(wp, 1.0));
       diag_done = true;
     } else {
-      val = FB_MUL(dsm, weights[p]);
+      val = FB_MUL(dsm, wp);
     }
     const double* xj = x + (size_t)j * nc;
 #pragma unroll

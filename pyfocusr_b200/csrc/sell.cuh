@@ -33,10 +33,12 @@ int sell_build_f32(const int* row_ptr, const int* cols, const double* weights, c
 
 // per-call tuning of the filter-step kernels (focusr_eigs_options in the C ABI)
 struct FilterTuning {
-  int policy = 2;    // bit 1 (default) = no L1 allocation + L2 evict_first on the single-use streams (entries, z_prev,
-                     // r, stores); bit 0 = L2 evict_last on the gathered block
+  int policy = 3;    // bit 1 = no L1 allocation + L2 evict_first on the single-use streams (entries, z_prev, r, stores);
+                     // bit 0 = L2 evict_last on the gathered block; default both
   int prefetch = 1;  // ask L2 early for the CTA's streams
   int min_blocks = 8;  // resident CTAs per SM the b = 16 kernels are compiled for (8, 6 or 5)
+  int pdl = 2;       // 0 = plain launches, 1 = programmatic dependent launch, 2 = + the prefetch of the streams the previous
+                     // step does not write is issued before the dependency wait
 };
 
 // One Chebyshev filter step on the SELL copy.  mode: 0 plain fp32 step (y, x_prev, out fp32), 1 first step of a pass (y
