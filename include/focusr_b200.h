@@ -153,7 +153,16 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
  * caller, focusr_dist_shared_open) and the kernel gathers a remote column straight from the owning
  * rank's HBM over NVLink (ghost g lives at row ghost_row[g] of rank ghost_peer[g]); no pack / send /
  * receive, no ghost copies, and the steps are ordered by a flag barrier in peer memory instead of a
- * collective.  `rows_cap` = the largest n_local of any rank (identical layout on every rank).
+ * collective.  `rows_cap` = rows of a block in the shared region (identical layout on every rank).
+ * In P2P mode the filter passes take the fp32 forms of the single-GPU solver (plain fp32 blocks, then the correction
+ * form) on fp32 views of the shared blocks, and ALL steps of a pass run in ONE persistent cooperative kernel per GPU
+ * (k_filter_persist): every fp32 view carries ghost rows from row `ghost_base` on (= the largest n_local of any rank;
+ * `rows_cap` >= ghost_base + the largest n_ghost), a rank PUSHES the rows its peers gather into their ghost rows with
+ * posted NVLink stores as soon as it has written them (`push_row` [n_push] sorted local rows, `push_dst` [n_push] =
+ * (peer << 24) | ghost slot on that peer), and the steps are separated by an in-kernel barrier (local arrival counter +
+ * one flag line per peer) -- no launch, no collective and no host involvement per step.  `max_row_entries` = longest
+ * local row (sizes the sliced-ELL copy).  result_i_host = {status, n_found, k_final, outer_iterations, total_filter_degree, block_size,
+ * filter steps that ran in fp32, world}.
  * ------------------------------------------------------------------------------------------- */
 size_t focusr_dist_shared_bytes(int rows_cap, int block_size, int world);
 int focusr_dist_shared_alloc(size_t bytes, char* handle64_host);
@@ -162,25 +171,29 @@ int focusr_dist_shared_free(void);
 int focusr_dist_unique_id(char* out128_host);
 int focusr_dist_init(const char* id128_host, int rank, int world);
 int focusr_dist_finalize(void);
-size_t focusr_eigs_dist_workspace_bytes(int n_local, int n_ghost, int n_send, int block_size, int world);
+size_t focusr_eigs_dist_workspace_bytes(int n_local, int n_ghost, int n_send, int max_row_entries,
+                                        int block_size, int world);
 int focusr_eigs_smallest_dist(const int* row_ptr, const int* cols_local, const double* weights,
                               const double* degree, const double* degree_inv, const double* points,
                               int n_local, int n_ghost, long long row_begin_global, long long nnz_local,
                               const int* send_idx, int n_send, const int* send_counts_host,
                               const int* recv_counts_host, const int* ghost_peer, const int* ghost_row,
-                              int use_p2p, int rows_cap, int n_zero_rows_global, int k,
-                              int n_k_needed, int k_buffer, double min_eig_val, double tol,
+                              int ghost_base, const int* push_row, const int* push_dst, int n_push,
+                              int use_p2p, int rows_cap, int n_zero_rows_global, int max_row_entries,
+                              int k, int n_k_needed, int k_buffer, double min_eig_val, double tol,
                               int max_outer, int block_size, double spectrum_upper_bound,
                               double* eig_vals, double* eig_vecs, int ldv, int* result_i_host,
                               double* result_d_host, void* workspace, size_t workspace_bytes,
-                              focusr_stream_t stream);
+                              const focusr_eigs_options* options, focusr_stream_t stream);
 
 /* Live profile of the dominant kernel, the Chebyshev SpMM filter step (CUDA events on the launching
  * stream around every filter application since the last reset): out4_host = {milliseconds,
  * launches, algorithmic bytes (12 nnz + 20 N + 24 b N per launch), 0}.  bench.py's roofline line.
  * focusr_profile_get counts the fp64 steps (k_spmm); focusr_profile_get_kind(kind, ...) the steps of one kind:
  * 0 = fp64, 1 = fp32 (k_spmm_f32: 8 nnz + 12 N + 12 b N per launch), 2 = fp32 correction form (k_spmm_corr:
- * 8 nnz + 12 N + 16 b N per launch); reset clears all three. */
+ * 8 nnz + 12 N + 16 b N per launch); reset clears all three.  kind 3 = the persistent filter kernels of the last
+ * row-partitioned solve of this process: {nanoseconds CTA 0 spent at the in-kernel barriers, nanoseconds it spent
+ * working, steps, 0}. */
 void focusr_profile_reset(void);
 void focusr_profile_get(double* out4_host);
 void focusr_profile_get_kind(int kind, double* out4_host);

@@ -40,14 +40,14 @@ SIGNATURES = {
     "focusr_dist_unique_id": (_i, [_vp]),
     "focusr_dist_init": (_i, [_vp, _i, _i]),
     "focusr_dist_finalize": (_i, []),
-    "focusr_eigs_dist_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "focusr_eigs_dist_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "focusr_dist_shared_bytes": (_sz, [_i, _i, _i]),
     "focusr_dist_shared_alloc": (_i, [_sz, _vp]),
     "focusr_dist_shared_open": (_i, [_vp, _i, _i]),
     "focusr_dist_shared_free": (_i, []),
     "focusr_eigs_smallest_dist": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, C.c_longlong, C.c_longlong, _vp, _i, _vp,
-                                       _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _d, _d, _i, _i, _d, _vp, _vp, _i, _vp,
-                                       _vp, _vp, _sz, _vp]),
+                                       _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _d, _d, _i, _i, _d,
+                                       _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp, _vp]),
     "focusr_profile_reset": (None, []),
     "focusr_profile_get": (None, [_vp]),
     "focusr_profile_get_kind": (None, [_i, _vp]),

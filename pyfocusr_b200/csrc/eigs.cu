@@ -498,7 +498,18 @@ struct DistCtx {
   const int* ghost_row = nullptr;        // device [n_ghost]
   int* dev_err = nullptr;                // device flag raised by a barrier time-out
   unsigned long long epoch = 0;
+  // --- fp32 filter passes as ONE persistent cooperative kernel per pass (sell.cu: k_filter_persist) ---
+  bool lowp = false;                     // P2P mode + SELL copy of the local rows built
+  int rows_cap = 0;                      // rows of a block in the shared region (identical on every rank)
+  int ghost_base = 0;                    // first ghost row of an fp32 view (= largest n_local of any rank)
+  const int* push_row = nullptr;         // device [n_push], sorted: local rows some peer gathers
+  const int* push_dst = nullptr;         // device [n_push]: (peer << 24) | ghost slot on that peer
+  int n_push = 0;
+  const float* const* peer_views = nullptr;  // device [6][world]: fp32 view 2 * block + half of rank p
+  unsigned* counter = nullptr;           // arrivals of this GPU's CTAs at the in-kernel barrier
+  unsigned long long* timing = nullptr;  // {ns at barriers, ns working, steps} of CTA 0 of the persistent kernels
 };
+static double g_persist_timing[4] = {0.0, 0.0, 0.0, 0.0};  // last row-partitioned solve of this process (profile kind 3)
 static ncclComm_t g_dist_comm = nullptr;
 static int g_dist_rank = 0, g_dist_world = 1;
 
@@ -676,10 +687,12 @@ struct CudaBackend {
   bool symmetric() const { return sym; }
   int zero_rows(int m) const { return info_host[FOCUSR_MESH_INFO_INTS * m + 2]; }
   // fp32 filter passes: local solves only (the peer-shared blocks of the row-partitioned solve are fp64)
-  bool lowp_available() const { return dist == nullptr && mixed && sell.entries != nullptr; }
+  // fp32 filter passes: batches on one GPU, and the row-partitioned solve in P2P mode (fp32 views of the peer-shared blocks)
+  bool lowp_available() const { return (dist == nullptr || dist->lowp) && mixed && sell.entries != nullptr; }
 
   // fp32 view number `half` (0 or 1) of an fp64 block, indexed by global row like the block itself
   float* f32_view(double* blk, int half) const {
+    if (dist) return reinterpret_cast<float*>(blk) + (size_t)half * dist->rows_cap * B;  // same offset on every rank
     const size_t shift = (size_t)off_host[0] * B;
     const size_t rows = (size_t)(off_host[M] - off_host[0]);
     return reinterpret_cast<float*>(blk + shift) + (size_t)half * rows * B - shift;
@@ -727,6 +740,50 @@ struct CudaBackend {
     nccl_check(api.GroupEnd(), "group end");
   }
   int block_index(const double* ptr) const { return (int)((ptr - dist->blocks) / (ptrdiff_t)dist->block_stride); }
+  int view_id(const double* blk, int half) const { return 2 * block_index(blk) + half; }
+  // one chunk of steps [s0, s0 + len) of a `deg`-step pass as one persistent kernel; views rotate by len afterwards
+  void persist_chunk(bool corr, int s0, int len, int deg, int (&v)[3], const void* al, const void* ga) {
+    fail(cudaMemsetAsync(dist->counter, 0, sizeof(unsigned), stream), "zero barrier counter");
+    PersistArgs a{};
+    a.entries = sell.entries;
+    a.slice_ptr = sell.slice_ptr;
+    a.ddi = sell.ddi;
+    a.n_loc = dist->n_loc;
+    a.ghost_base = dist->ghost_base;
+    a.push_row = dist->push_row;
+    a.push_dst = dist->push_dst;
+    a.n_push = dist->n_push;
+    a.push_first = (!corr && s0 == 0) ? 1 : 0;   // plain pass: the fp32 copy of X still lacks its ghost rows
+    a.peer_views = dist->peer_views;
+    a.world = dist->world;
+    a.rank = dist->rank;
+    a.v_prev = v[0];
+    a.v_cur = v[1];
+    a.v_next = v[2];
+    a.r = f32_view(Y, 0);
+    a.x = X;
+    a.alpha = al;
+    a.gamma = ga;
+    a.center = center;
+    a.s0 = s0;
+    a.len = len;
+    a.deg = deg;
+    a.prefetch = tune.prefetch;
+    a.counter = dist->counter;
+    a.my_flags = dist->flags;
+    a.peer_flags = dist->peer_flags;
+    a.epoch0 = dist->epoch;
+    a.err = dist->dev_err;
+    a.timing = dist->timing;
+    if (launch_filter_persist(corr, B, a, stream) != FB_OK && err == FB_OK) err = FB_ERR_CUDA;
+    dist->epoch += (unsigned long long)len;
+    for (int i = 0; i < len % 3; ++i) {
+      const int t = v[0];
+      v[0] = v[1];
+      v[1] = v[2];
+      v[2] = t;
+    }
+  }
   void spmm(int mode, const SpmmGraph& gg, const double* y, const double* x_prev, double* out, const double* al,
             const double* ga, const double* ce, int step, int n_steps) {
     if (dist && dist->p2p && dist->world > 1)
@@ -908,6 +965,7 @@ struct CudaBackend {
     float* f_cur = f32_view(Y, 0);
     float* f_prev = f32_view(Y, 1);
     float* f_next = f32_view(Xn, 0);
+    int dist_views[3] = {0, 0, 0};
     for (int s0 = 0; s0 < deg; s0 += table_cap) {
       const int len = std::min(table_cap, deg - s0);
       double* pa = pin + pin_off;
@@ -919,6 +977,17 @@ struct CudaBackend {
       }
       fail(cudaMemcpyAsync(alpha, pa, sizeof(double) * (size_t)M * len, cudaMemcpyHostToDevice, stream), "H2D alpha");
       fail(cudaMemcpyAsync(gamma, pg, sizeof(double) * (size_t)M * len, cudaMemcpyHostToDevice, stream), "H2D gamma");
+      if (lowp && dist) {
+        // row-partitioned: the fp32 copy of X goes to view (Y,1) first, then every step has the same form
+        if (s0 == 0) {
+          block_to_f32(X, f32_view(Y, 1), (long long)dist->n_loc * B, stream);
+          dist_views[0] = view_id(Xn, 0);
+          dist_views[1] = view_id(Y, 1);
+          dist_views[2] = view_id(Y, 0);
+        }
+        persist_chunk(false, s0, len, deg, dist_views, alpha, gamma);
+        continue;
+      }
       if (lowp) {
         for (int s = 0; s < len; ++s) {
           const int gs = s0 + s;
@@ -984,10 +1053,22 @@ struct CudaBackend {
     // first chunk of tables before the timed bracket (its launches are the filter steps only)
     launch_corr_tables(theta, corr_ab, M, B, deg, 0, std::min(cap_c, deg), d_al, d_ga, center, stream);
     g_filter_profile_corr.begin(stream);
-    fail(cudaMemsetAsync(z_cur + (size_t)off_host[0] * B, 0, sizeof(float) * (size_t)rows * B, stream), "zero z");
+    // (row-partitioned: the ghost rows of the view are zeroed too)
+    fail(cudaMemsetAsync(z_cur + (size_t)off_host[0] * B, 0, sizeof(float) * (size_t)(dist ? dist->rows_cap : rows) * B, stream),
+         "zero z");
+    int dist_views[3] = {0, 0, 0};
+    if (dist) {
+      dist_views[0] = view_id(Xn, 0);
+      dist_views[1] = view_id(Y, 1);
+      dist_views[2] = view_id(Xn, 1);
+    }
     for (int s0 = 0; s0 < deg; s0 += cap_c) {
       const int len = std::min(cap_c, deg - s0);
       if (s0 > 0) launch_corr_tables(theta, corr_ab, M, B, deg, s0, len, d_al, d_ga, center, stream);
+      if (dist) {
+        persist_chunk(true, s0, len, deg, dist_views, d_al, d_ga);
+        continue;
+      }
       for (int s = 0; s < len; ++s) {
         const int gs = s0 + s;
         const bool last = gs == deg - 1;
@@ -1080,6 +1161,10 @@ void focusr_profile_reset(void) {
 }
 
 void focusr_profile_get_kind(int kind, double* out4_host) {
+  if (kind == 3) {  // persistent filter kernels of the last row-partitioned solve: CTA 0's {ns at barriers, ns working, steps}
+    for (int i = 0; i < 4; ++i) out4_host[i] = g_persist_timing[i];
+    return;
+  }
   g_filter_profile.collect();
   g_filter_profile_lowp.collect();
   g_filter_profile_corr.collect();
@@ -1404,21 +1489,32 @@ static size_t dist_extra_layout(int n_send, int B, int world, DistCtx* d, Carver
   const double** peer_blocks = cv.take<const double*>((size_t)3 * world);
   unsigned long long** peer_flags = cv.take<unsigned long long*>((size_t)world);
   int* dev_err = cv.take<int>(2);
+  const float** peer_views = cv.take<const float*>((size_t)6 * world);
+  unsigned* counter = cv.take<unsigned>(4);
+  unsigned long long* timing = cv.take<unsigned long long>(4);
   if (d) {
+    d->timing = timing;
     d->sendbuf = sendbuf;
     d->small = small;
     d->fake_off = fake_off;
     d->peer_blocks = peer_blocks;
     d->peer_flags = peer_flags;
     d->dev_err = dev_err;
+    d->peer_views = peer_views;
+    d->counter = counter;
   }
   return cv.used + 256;
 }
 
-size_t focusr_eigs_dist_workspace_bytes(int n_local, int n_ghost, int n_send, int block_size, int world) {
+static long long dist_sell_cap(int n_local, int max_row_entries) {
+  return (long long)div_up(n_local, SELL_ROWS) * SELL_ROWS * (long long)std::max(max_row_entries, 1);
+}
+
+size_t focusr_eigs_dist_workspace_bytes(int n_local, int n_ghost, int n_send, int max_row_entries, int block_size, int world) {
   const size_t base = eigs_ws_layout(n_local + n_ghost, 1, n_local, block_size, nullptr, nullptr, 0);
   Carver cv(nullptr, 0);
-  return align_up(base) + dist_extra_layout(n_send, block_size, world, nullptr, cv) + 1024;
+  return align_up(base) + align_up(dist_extra_layout(n_send, block_size, world, nullptr, cv)) +
+         f32_layout(dist_sell_cap(n_local, max_row_entries), n_local, 1, nullptr).bytes + 1024;
 }
 
 int focusr_eigs_smallest_dist(const int* row_ptr, const int* cols_local, const double* weights,
@@ -1426,12 +1522,16 @@ int focusr_eigs_smallest_dist(const int* row_ptr, const int* cols_local, const d
                               int n_local, int n_ghost, long long row_begin_global, long long nnz_local,
                               const int* send_idx, int n_send, const int* send_counts_host,
                               const int* recv_counts_host, const int* ghost_peer, const int* ghost_row,
-                              int use_p2p, int rows_cap, int n_zero_rows_global, int k, int n_k_needed,
-                              int k_buffer, double min_eig_val, double tol, int max_outer, int block_size,
-                              double spectrum_upper_bound, double* eig_vals, double* eig_vecs, int ldv,
-                              int* result_i_host, double* result_d_host, void* workspace,
-                              size_t workspace_bytes, focusr_stream_t stream_) {
+                              int ghost_base, const int* push_row, const int* push_dst, int n_push,
+                              int use_p2p, int rows_cap, int n_zero_rows_global, int max_row_entries, int k,
+                              int n_k_needed, int k_buffer, double min_eig_val, double tol, int max_outer,
+                              int block_size, double spectrum_upper_bound, double* eig_vals, double* eig_vecs,
+                              int ldv, int* result_i_host, double* result_d_host, void* workspace,
+                              size_t workspace_bytes, const focusr_eigs_options* options, focusr_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  focusr_eigs_options opt;
+  focusr_eigs_default_options(&opt);
+  if (options) opt = *options;
   FB_REQUIRE(n_local > 0 && k >= 1 && n_k_needed >= 1 && ldv >= 1, "eigs_dist: bad sizes");
   FB_REQUIRE(g_dist_world == 1 || g_dist_comm != nullptr, "eigs_dist: call focusr_dist_init first");
   const int world = g_dist_world;
@@ -1471,11 +1571,14 @@ int focusr_eigs_smallest_dist(const int* row_ptr, const int* cols_local, const d
   be.g = SpmmGraph{row_ptr, cols_local, weights, degree, degree_inv, nullptr, 1, n_local};
   const size_t base = eigs_ws_layout(n_local + n_ghost, 1, n_local, B, &be, workspace, workspace_bytes);
   Carver cv((char*)workspace + align_up(base), workspace_bytes > align_up(base) ? workspace_bytes - align_up(base) : 0);
-  const size_t extra = dist_extra_layout(n_send, B, world, &d, cv);
-  if (align_up(base) + extra > workspace_bytes) {
-    set_error("eigs_dist: workspace too small (%zu < %zu)", workspace_bytes, align_up(base) + extra);
+  const size_t extra = align_up(dist_extra_layout(n_send, B, world, &d, cv));
+  const long long sell_cap = dist_sell_cap(n_local, max_row_entries);
+  const size_t f32_bytes = f32_layout(sell_cap, n_local, 1, nullptr).bytes;
+  if (align_up(base) + extra + f32_bytes > workspace_bytes) {
+    set_error("eigs_dist: workspace too small (%zu < %zu)", workspace_bytes, align_up(base) + extra + f32_bytes);
     return FB_ERR_WORKSPACE;
   }
+  const F32Layout f32 = f32_layout(sell_cap, n_local, 1, (char*)workspace + align_up(base) + extra);
   const int off_host[2] = {0, n_local};
   const int info_host[FOCUSR_MESH_INFO_INTS] = {(int)nnz_local, 0, n_zero_rows_global, 0, 0, 0, 0, 0};
   const int fake[2] = {0, 1};
@@ -1492,12 +1595,15 @@ int focusr_eigs_smallest_dist(const int* row_ptr, const int* cols_local, const d
   be.ldv = ldv;
   be.dist = &d;
   std::vector<const double*> pb_host;
+  std::vector<const float*> pv_host;
   std::vector<unsigned long long*> pf_host;
   if (use_p2p && world > 1) {
     FB_REQUIRE(g_shared.base != nullptr && g_shared.world == world && (int)g_shared.peer.size() == world,
                "eigs_dist: P2P mode needs focusr_dist_shared_alloc/open first");
-    FB_REQUIRE(rows_cap >= n_local && focusr_dist_shared_bytes(rows_cap, B, world) <= g_shared.bytes,
-               "eigs_dist: shared region too small for rows_cap=%d block=%d", rows_cap, B);
+    FB_REQUIRE(ghost_base >= n_local && rows_cap >= ghost_base + n_ghost &&
+                   focusr_dist_shared_bytes(rows_cap, B, world) <= g_shared.bytes,
+               "eigs_dist: shared region too small for rows_cap=%d (ghost rows from %d, %d of them) block=%d", rows_cap,
+               ghost_base, n_ghost, B);
     const size_t stride = align_up(sizeof(double) * (size_t)rows_cap * B) / sizeof(double);
     d.p2p = true;
     d.block_stride = stride;
@@ -1519,9 +1625,20 @@ int focusr_eigs_smallest_dist(const int* row_ptr, const int* cols_local, const d
     FB_CUDA(cudaMemcpyAsync(const_cast<unsigned long long**>(d.peer_flags), pf_host.data(), sizeof(void*) * world,
                             cudaMemcpyHostToDevice, stream));
     FB_CUDA(cudaMemsetAsync(d.dev_err, 0, sizeof(int) * 2, stream));
+    FB_CUDA(cudaMemsetAsync(d.timing, 0, sizeof(unsigned long long) * 4, stream));
     be.X = d.blocks;
     be.Y = d.blocks + stride;
     be.Xn = d.blocks + 2 * stride;
+    // fp32 views of the shared blocks: view 2 * block + half of rank p starts half * rows_cap * B floats into block `block`
+    d.rows_cap = rows_cap;
+    pv_host.resize((size_t)6 * world);
+    for (int p = 0; p < world; ++p)
+      for (int kb = 0; kb < 3; ++kb)
+        for (int half = 0; half < 2; ++half)
+          pv_host[(size_t)(2 * kb + half) * world + p] =
+              reinterpret_cast<const float*>(pb_host[(size_t)kb * world + p]) + (size_t)half * rows_cap * B;
+    FB_CUDA(cudaMemcpyAsync(const_cast<const float**>(d.peer_views), pv_host.data(), sizeof(float*) * 6 * world,
+                            cudaMemcpyHostToDevice, stream));
   }
   FB_CUDA(cudaMemcpyAsync(const_cast<int*>(be.g.mesh_off), off_host, sizeof(off_host), cudaMemcpyHostToDevice, stream));
   FB_CUDA(cudaMemcpyAsync(d.fake_off, fake, sizeof(fake), cudaMemcpyHostToDevice, stream));
@@ -1530,6 +1647,31 @@ int focusr_eigs_smallest_dist(const int* row_ptr, const int* cols_local, const d
   FB_CUDA(cudaMemsetAsync(be.X, 0, sizeof(double) * ext_rows * B, stream));
   FB_CUDA(cudaMemsetAsync(be.Y, 0, sizeof(double) * ext_rows * B, stream));
   FB_CUDA(cudaMemsetAsync(be.Xn, 0, sizeof(double) * ext_rows * B, stream));
+  // fp32 filter passes: SELL copy of the local rows, remote columns encoded for the in-kernel peer gather.  P2P mode
+  // only (the fp32 views live in the peer-shared blocks); the ncclSend/ncclRecv path keeps the fp64 steps.
+  be.mixed = opt.mixed_precision != 0;
+  be.tune.policy = opt.filter_policy;
+  be.tune.prefetch = opt.filter_prefetch;
+  be.tune.min_blocks = opt.filter_min_blocks;
+  be.tune.pdl = opt.filter_pdl;
+  if (d.p2p && be.mixed && max_row_entries > 0 && rows_cap < (1 << 24) && world <= 128) {
+    const int rcs = sell_build_f32(row_ptr, cols_local, weights, degree, degree_inv, be.g.mesh_off, off_host, 1, n_local,
+                                   f32.mesh_slice_off, f32.slice_ptr, f32.entries, f32.ddi, f32.slice_cnt, f32.scan_tmp,
+                                   stream);
+    if (rcs) return rcs;
+    const int rcg = sell_remap_ghosts(f32.entries, sell_cap, f32.slice_ptr, div_up(n_local, SELL_ROWS), n_local, ghost_base,
+                                      stream);
+    if (rcg) return rcg;
+    be.sell.entries = f32.entries;
+    be.sell.slice_ptr = f32.slice_ptr;
+    be.sell.mesh_slice_off = f32.mesh_slice_off;
+    be.sell.ddi = f32.ddi;
+    d.lowp = true;
+    d.ghost_base = ghost_base;
+    d.push_row = push_row;
+    d.push_dst = push_dst;
+    d.n_push = n_push;
+  }
   FB_CUDA(cudaStreamSynchronize(stream));  // off_host / fake live on this stack frame
   MeshResult r;
   const int rc = chfsi_solve(be, p, &r);
@@ -1538,8 +1680,11 @@ int focusr_eigs_smallest_dist(const int* row_ptr, const int* cols_local, const d
     be.halo_exchange(be.X);
     g_peer_epoch = d.epoch;
     int herr[2] = {0, 0};
+    unsigned long long tim[4] = {0, 0, 0, 0};
     cudaMemcpyAsync(herr, d.dev_err, sizeof(herr), cudaMemcpyDeviceToHost, stream);
+    cudaMemcpyAsync(tim, d.timing, sizeof(tim), cudaMemcpyDeviceToHost, stream);
     cudaStreamSynchronize(stream);
+    for (int i = 0; i < 4; ++i) g_persist_timing[i] = (double)tim[i];
     if (herr[0] != 0) {
       set_error("eigs_dist: a peer did not reach the inter-GPU barrier (time-out)");
       return FB_ERR_CUDA;
@@ -1548,13 +1693,15 @@ int focusr_eigs_smallest_dist(const int* row_ptr, const int* cols_local, const d
   if (be.err != FB_OK) return be.err;
   FB_CUDA(cudaStreamSynchronize(stream));
   g_filter_profile.collect();
+  g_filter_profile_lowp.collect();
+  g_filter_profile_corr.collect();
   result_i_host[0] = r.status;
   result_i_host[1] = r.n_out;
   result_i_host[2] = r.k_final;
   result_i_host[3] = r.outer_iters;
   result_i_host[4] = r.total_degree;
   result_i_host[5] = B;
-  result_i_host[6] = 1;
+  result_i_host[6] = r.lowp_degree;  // filter steps that ran in fp32 (0: every step fp64)
   result_i_host[7] = world;
   result_d_host[0] = r.max_residual;
   result_d_host[1] = r.beta;

@@ -70,12 +70,14 @@ __device__ __forceinline__ unsigned long long policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
+// (the loads below are of data that no thread writes during the launch: plain `asm`, not `asm volatile`, so that the
+// compiler is free to batch several of them before the first use)
 // gathered (re-used) data
 template <int HINT>
 __device__ __forceinline__ float4 ld_keep(const float4* p, unsigned long long pol) {
   if (HINT) {
     float4 v;
-    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                  : "l"(p), "l"(pol));
     return v;
@@ -86,7 +88,7 @@ template <int HINT>
 __device__ __forceinline__ double2 ld_keep(const double2* p, unsigned long long pol) {
   if (HINT) {
     double2 v;
-    asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    asm("ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
     return v;
   }
   return __ldg(p);
@@ -96,7 +98,7 @@ template <int HINT>
 __device__ __forceinline__ float4 ld_stream(const float4* p, unsigned long long pol) {
   if (HINT) {
     float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                  : "l"(p), "l"(pol));
     return v;
@@ -107,7 +109,7 @@ template <int HINT>
 __device__ __forceinline__ int2 ld_stream(const int2* p, unsigned long long pol) {
   if (HINT) {
     int2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.s32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.s32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
     return v;
   }
   return __ldg(p);
@@ -314,8 +316,34 @@ k_filter_sell(const int2* __restrict__ entries, const int* __restrict__ slice_pt
     float4 acc[VPT];
 #pragma unroll
     for (int v = 0; v < VPT; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
-    for (int k = 0; k < w; ++k) {
+    // two entries, then their two gathers, then the arithmetic: two independent gathers in flight per thread
+    int k = 0;
+#pragma unroll 1
+    for (; k + 1 < w; k += 2) {
+      const int2 e0v = ld_stream<STRM>(ep + (size_t)k * SELL_ROWS, pol_strm);
+      const int2 e1v = ld_stream<STRM>(ep + (size_t)(k + 1) * SELL_ROWS, pol_strm);
+      float4 g0[VPT], g1[VPT];
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) g0[v] = load_y(e0v.x, t + v * TPR);
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) g1[v] = load_y(e1v.x, t + v * TPR);
+      const float w0 = __int_as_float(e0v.y), w1 = __int_as_float(e1v.y);
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) {
+        acc[v].x = fmaf(w0, g0[v].x, acc[v].x);
+        acc[v].y = fmaf(w0, g0[v].y, acc[v].y);
+        acc[v].z = fmaf(w0, g0[v].z, acc[v].z);
+        acc[v].w = fmaf(w0, g0[v].w, acc[v].w);
+      }
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) {
+        acc[v].x = fmaf(w1, g1[v].x, acc[v].x);
+        acc[v].y = fmaf(w1, g1[v].y, acc[v].y);
+        acc[v].z = fmaf(w1, g1[v].z, acc[v].z);
+        acc[v].w = fmaf(w1, g1[v].w, acc[v].w);
+      }
+    }
+    if (k < w) {
       const int2 e = ld_stream<STRM>(ep + (size_t)k * SELL_ROWS, pol_strm);
       const float wt = __int_as_float(e.y);
 #pragma unroll
@@ -460,6 +488,419 @@ int launch_filter_sell(int mode, int b, const SellF32& m, const int* mesh_off, i
     FB_CASE(96, 4)
     default:
       set_error("filter (SELL): unsupported block size %d (multiples of 8 up to 96)", b);
+      return FB_ERR_UNSUPPORTED;
+  }
+#undef FB_CASE
+}
+
+// ===============================================================================================================
+// Row-partitioned solve (one mesh over several GPUs, one process per GPU): ALL steps of a filter pass in ONE
+// persistent cooperative kernel per GPU.  Round 1 launched one fp64 SpMM plus one flag-barrier kernel per step and was
+// bound by that latency (49 us per step against ~21 us of memory time at 8 GPUs).  Here every rank keeps its three
+// vector blocks in a region shared through CUDA IPC; the fp32 forms of the step run on fp32 views of those blocks; a
+// rows of the neighbours that a rank gathers are PUSHED into its ghost rows over NVLink by their owners as soon as they
+// are written (posted stores, see k_filter_persist); and the steps are separated by a barrier INSIDE the kernel
+// (step_barrier below).  No launch, no host involvement, no collective per step.
+// ===============================================================================================================
+constexpr int PEER_ROW_BITS = 24;
+
+// ghost column n_loc + g of the local numbering -> row ghost_base + g of the fp32 views (their ghost rows)
+__global__ void k_sell_remap_ghosts(int2* __restrict__ entries, const int* __restrict__ slice_ptr, int n_slices, int n_loc,
+                                    int ghost_base) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= slice_ptr[n_slices]) return;  // slots past the scanned total were never written
+  const int c = entries[t].x;
+  if (c >= n_loc) entries[t].x = ghost_base + (c - n_loc);
+}
+
+int sell_remap_ghosts(int2* entries, long long n_entries_cap, const int* slice_ptr, int n_slices, int n_loc, int ghost_base,
+                      cudaStream_t stream) {
+  // padded slots hold column r0 of their slice (< n_loc) and are left alone
+  k_sell_remap_ghosts<<<div_up(n_entries_cap, 256), 256, 0, stream>>>(entries, slice_ptr, n_slices, n_loc, ghost_base);
+  FB_COUNT_LAUNCH(1);
+  FB_LAUNCH_CHECK();
+  return FB_OK;
+}
+
+__global__ void k_block_to_f32(const double* __restrict__ x, float* __restrict__ out, long long n) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = (float)x[t];
+}
+
+int block_to_f32(const double* x, float* out, long long n, cudaStream_t stream) {
+  k_block_to_f32<<<div_up(n, 256), 256, 0, stream>>>(x, out, n);
+  FB_COUNT_LAUNCH(1);
+  FB_LAUNCH_CHECK();
+  return FB_OK;
+}
+
+// The vector blocks change inside the persistent kernel: ordinary C++ loads (ld.global, coherent at the fences of
+// step_barrier; never .nc), which the compiler may batch between two barriers but not move across one.
+__device__ __forceinline__ float4 ld_plain(const float4* p) { return *p; }
+
+// Barrier between two steps, across the CTAs of this GPU and across the GPUs.  System-scope operations are expensive
+// (a fence.sys by each of ~1000 CTAs per step cost 30-45 us per step in the first version), so exactly ONE thread per
+// GPU and step executes them: every CTA releases its rows at GPU scope and arrives on a local counter; the last one to
+// arrive publishes the step number to every peer (fence.sys + st.release.sys over NVLink), waits until every peer has
+// published it (ld.acquire.sys on LOCAL flag lines), and then opens a local gate at GPU scope on which all other CTAs
+// wait.  Causality is transitive across the scopes (rows -> fence.gpu -> counter -> last CTA -> fence.sys -> flag ->
+// peer's last CTA -> gate -> peer's CTAs), and the acquiring fence.gpu of every CTA also drops its SM's L1 lines, so
+// the plain loads that follow see the rows the other SMs and the other GPUs wrote in the previous step.
+// Fences are spelled out: __threadfence() / st.release compile to MEMBAR.SC.* or one MEMBAR.ALL.SYS per store, the
+// patterns below ("fence.acq_rel; relaxed store" to release, "relaxed load; fence.acq_rel" to acquire) to one MEMBAR.ALL
+// per side.  Measured at 2 GPUs on a problem small enough to expose the barrier (18 000 rows per rank): 14.9 us per step
+// with __threadfence / st.release.sys per peer, see profiles/r2_scaling.md for the current figure.
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+
+__device__ __forceinline__ void step_barrier(const PersistArgs& a, unsigned target, unsigned long long epoch, bool pushed) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned old;
+    // release: this CTA's stores of the step, ordered before by the bar.sync -- GPU scope, or system scope when the CTA
+    // has posted rows into peer memory (the fence then waits for their acknowledgement)
+    if (pushed) fence_sys();
+    else fence_gpu();
+    asm volatile("atom.relaxed.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(a.counter) : "memory");
+    unsigned long long* gate = a.my_flags + (size_t)a.rank * 16;  // this rank's own line doubles as the local gate
+    const long long t0 = clock64();
+    if (old + 1u == target) {  // last CTA of this GPU: every local row of the step is written
+      if (a.world > 1) {
+        fence_sys();           // acquires the other CTAs' arrivals, releases to the peers
+        for (int p = 0; p < a.world; ++p)
+          if (p != a.rank) {
+            unsigned long long* dst = a.peer_flags[p] + (size_t)a.rank * 16;
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(epoch) : "memory");
+          }
+        for (int p = 0; p < a.world; ++p) {
+          if (p == a.rank) continue;
+          const unsigned long long* src = a.my_flags + (size_t)p * 16;
+          for (;;) {   // acquire loads: no fence (which would wait for the acknowledgement of the flag stores above)
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+            if (v >= epoch) break;
+            if (clock64() - t0 > 20000000000LL) {  // ~10 s: a lost peer becomes an error, not a hang
+              atomicExch(a.err, 1);
+              break;
+            }
+          }
+        }
+      }
+      fence_gpu();   // (cumulative) releases what was acquired, local rows and the peers' pushed rows, to the local CTAs
+      asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(gate), "l"(epoch) : "memory");
+    } else {
+      for (;;) {
+        unsigned long long v;
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(gate) : "memory");
+        if (v >= epoch) break;
+        if (clock64() - t0 > 24000000000LL) {
+          atomicExch(a.err, 1);
+          break;
+        }
+      }
+    }
+    fence_gpu();  // acquire side (GPU scope); a fence of scope >= cluster also drops the SM's L1 lines (CCTL.IVALL)
+  }
+  __syncthreads();
+}
+
+// Halo by PUSH: a remote column is never loaded over NVLink inside the step (a peer load costs 1-2 us, three of them in
+// a row's dependent chain made the boundary CTAs the critical path of every step: 12.6 us per step at 18 000 rows per
+// rank, 25 us at 125 000).  Instead every fp32 view carries ghost rows behind the owned rows, and a CTA that has just
+// written rows its peers gather copies them into the peers' ghost slots with posted stores before it arrives at the
+// barrier (its arrival fence is then system-scoped, so the stores are acknowledged before the flag can be seen).  After
+// the barrier every gather is local.  Tried and dropped: caching the CTA's matrix slice in shared memory and issuing the
+// epilogue operands before the gathers (shorter dependent chain, but 80-128 registers: 33.9 against 25.1 us per step).
+template <int B, int TPR, bool CORR>
+__global__ void __launch_bounds__(FS_THREADS, (B / (4 * TPR) == 1) ? 6 : ((B / (4 * TPR) == 2) ? 4 : 3))
+k_filter_persist(const PersistArgs a) {
+  constexpr int VPT = B / (4 * TPR);
+  constexpr int RP = FS_THREADS / TPR, SPP = RP / SELL_ROWS;
+  const int g = threadIdx.x / TPR, t = threadIdx.x % TPR;
+  const int gs_ = g / SELL_ROWS, rl = g % SELL_ROWS;
+  const float cc = (float)a.center[0];
+  const int u0 = blockIdx.x * a.units_per_cta, u1 = min(a.n_units, u0 + a.units_per_cta);
+  const int n_slices = (a.n_loc + SELL_ROWS - 1) / SELL_ROWS;
+  // this CTA's share of the push list (sorted by row): items [i0, i1)
+  int i0 = 0, i1 = 0;
+  if (a.n_push > 0) {
+    auto lower = [&](int row) {
+      int lo = 0, hi = a.n_push;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a.push_row[mid] < row) lo = mid + 1;
+        else hi = mid;
+      }
+      return lo;
+    };
+    i0 = lower(u0 * RP);
+    i1 = lower(u1 * RP);
+  }
+  const bool pusher = i1 > i0;
+  // Units holding rows that peers gather are processed FIRST in every step and pushed right away: the posted stores are
+  // acknowledged while the CTA works on its other units, so the system-scope fence of its arrival does not wait for an
+  // NVLink round trip (measured at 2 GPUs, 18 000 rows per rank: that wait alone was 2.8 us of a 9.4 us barrier).
+  constexpr int ORDER_CAP = 64;
+  __shared__ int s_order[ORDER_CAP];
+  __shared__ int s_first;
+  const int nu = max(u1 - u0, 0);
+  const bool reorder = pusher && nu <= ORDER_CAP;
+  if (reorder && threadIdx.x == 0) {
+    int nf = 0, nl = nu;
+    for (int j = 0; j < nu; ++j) {   // stable: boundary units in order, then the others in order
+      bool has = false;
+      for (int i = i0; i < i1 && !has; ++i) has = a.push_row[i] / RP == u0 + j;
+      if (has) s_order[nf++] = u0 + j;
+    }
+    for (int j = nu - 1; j >= 0; --j) {
+      bool has = false;
+      for (int i = 0; i < nf && !has; ++i) has = s_order[i] == u0 + j;
+      if (!has) s_order[--nl] = u0 + j;
+    }
+    s_first = nf;
+  }
+  __syncthreads();
+  const int n_first = reorder ? s_first : nu;   // the push follows unit number n_first - 1 of the CTA's order
+  // rows [i0, i1) of a view this rank owns -> the ghost slots of the peers that gather them (posted stores)
+  auto push_rows = [&](int view, const float* mine) {
+    constexpr int Q = B / 4;
+    const float* const* dst_of = a.peer_views + (size_t)view * a.world;
+    for (int i = threadIdx.x; i < (i1 - i0) * Q; i += FS_THREADS) {
+      const int item = i0 + i / Q, q = i % Q;
+      const int dst = a.push_dst[item];
+      const float4 v = reinterpret_cast<const float4*>(mine + (size_t)a.push_row[item] * B)[q];
+      float* base = const_cast<float*>(dst_of[dst >> PEER_ROW_BITS]);
+      reinterpret_cast<float4*>(base + ((size_t)a.ghost_base + (size_t)(dst & ((1 << PEER_ROW_BITS) - 1))) * B)[q] = v;
+    }
+  };
+  if (a.push_first && pusher) push_rows(a.v_cur, a.peer_views[(size_t)a.v_cur * a.world + a.rank]);
+  // live profile (CTA 0, thread 0): nanoseconds spent waiting at the barriers / working, per launch
+  const bool timer = a.timing != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  unsigned long long t_wait = 0, t_work = 0, t_mark = 0;
+  auto now = [] {
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    return v;
+  };
+  if (timer) t_mark = now();
+  for (int s = 0; s < a.len; ++s) {
+    step_barrier(a, (unsigned)(s + 1) * gridDim.x, a.epoch0 + 1ull + (unsigned long long)s, pusher);
+    if (timer) {
+      const unsigned long long t = now();
+      t_wait += t - t_mark;
+      t_mark = t;
+    }
+    const int gstep = a.s0 + s;
+    const bool last = gstep == a.deg - 1;
+    // views rotate: (prev, cur, next) <- (cur, next, prev)
+    const int rot = s % 3;
+    const int v_prev = rot == 0 ? a.v_prev : (rot == 1 ? a.v_cur : a.v_next);
+    const int v_cur = rot == 0 ? a.v_cur : (rot == 1 ? a.v_next : a.v_prev);
+    const int v_next = rot == 0 ? a.v_next : (rot == 1 ? a.v_prev : a.v_cur);
+    const float* cur = a.peer_views[(size_t)v_cur * a.world + a.rank];
+    const float* prev = a.peer_views[(size_t)v_prev * a.world + a.rank];
+    float* next = const_cast<float*>(a.peer_views[(size_t)v_next * a.world + a.rank]);
+    float al_s = 0.f, ga_s = 0.f;
+    const float4* al_p = nullptr;
+    const float4* ga_p = nullptr;
+    if (CORR) {
+      al_p = reinterpret_cast<const float4*>(static_cast<const float*>(a.alpha) + (size_t)s * B);
+      ga_p = reinterpret_cast<const float4*>(static_cast<const float*>(a.gamma) + (size_t)s * B);
+    } else {
+      al_s = (float)static_cast<const double*>(a.alpha)[s];
+      ga_s = (float)static_cast<const double*>(a.gamma)[s];
+    }
+    const bool has_prev = CORR ? gstep > 0 : ga_s != 0.f;
+    // L2 prefetch of a unit's streams (what the batch kernel does at CTA start): entries, r, prev and own cur rows
+    auto prefetch_unit = [&](int u, const float* pv, const float* cu, bool want_prev) {
+      const int rb0 = u * RP;
+      if (rb0 >= a.n_loc) return;
+      const int rows = min(RP, a.n_loc - rb0);
+      constexpr int LINES = (B * 4 + 127) / 128;
+      for (int i = threadIdx.x; i < rows * LINES; i += FS_THREADS) {
+        const size_t o = (size_t)(rb0 + i / LINES) * B + 32 * (i % LINES);
+        if (cu) prefetch_l2_line(cu + o);
+        if (want_prev) prefetch_l2_line(pv + o);
+        if (CORR) prefetch_l2_line(a.r + o);
+      }
+      const int s_lo = u * SPP, s_hi = min(s_lo + SPP, n_slices);
+      const int q0 = a.slice_ptr[s_lo], q1 = a.slice_ptr[s_hi];
+      for (int q = q0 + 16 * (int)threadIdx.x; q < q1; q += 16 * FS_THREADS) prefetch_l2_line(a.entries + q);
+    };
+    for (int j = 0; j < nu; ++j) {
+      const int u = reorder ? s_order[j] : u0 + j;
+      if (j == n_first && pusher && !last && n_first < nu) {   // boundary units done: push them, then the other units
+        __syncthreads();
+        push_rows(v_next, next);
+      }
+      if (a.prefetch) {
+        if (j + 1 < nu) prefetch_unit(reorder ? s_order[j + 1] : u + 1, prev, cur, has_prev);
+        else if (!last) prefetch_unit(reorder ? s_order[0] : u0, cur, nullptr, true);   // first unit of the next step: its prev is this cur
+      }
+      const int slice = u * SPP + gs_;
+      const int rb = slice * SELL_ROWS;
+      if (rb >= a.n_loc) continue;
+      const int row = rb + rl;
+      const int e0 = a.slice_ptr[slice];
+      const int w = (a.slice_ptr[slice + 1] - e0) / SELL_ROWS;
+      const int2* ep = a.entries + (size_t)e0 + rl;
+      float4 acc[VPT];
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      int k = 0;
+#pragma unroll 1
+      for (; k + 1 < w; k += 2) {   // two entries, their two gathers, then the arithmetic
+        const int2 e0v = __ldg(ep + (size_t)k * SELL_ROWS);   // the matrix is constant during the kernel
+        const int2 e1v = __ldg(ep + (size_t)(k + 1) * SELL_ROWS);
+        const float4* s0 = reinterpret_cast<const float4*>(cur + (size_t)e0v.x * B);
+        const float4* s1 = reinterpret_cast<const float4*>(cur + (size_t)e1v.x * B);
+        float4 g0[VPT], g1[VPT];
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) g0[v] = ld_plain(s0 + t + v * TPR);
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) g1[v] = ld_plain(s1 + t + v * TPR);
+        const float w0 = __int_as_float(e0v.y), w1 = __int_as_float(e1v.y);
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+          acc[v].x = fmaf(w0, g0[v].x, acc[v].x);
+          acc[v].y = fmaf(w0, g0[v].y, acc[v].y);
+          acc[v].z = fmaf(w0, g0[v].z, acc[v].z);
+          acc[v].w = fmaf(w0, g0[v].w, acc[v].w);
+        }
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+          acc[v].x = fmaf(w1, g1[v].x, acc[v].x);
+          acc[v].y = fmaf(w1, g1[v].y, acc[v].y);
+          acc[v].z = fmaf(w1, g1[v].z, acc[v].z);
+          acc[v].w = fmaf(w1, g1[v].w, acc[v].w);
+        }
+      }
+      if (k < w) {
+        const int2 e = __ldg(ep + (size_t)k * SELL_ROWS);
+        const float wt = __int_as_float(e.y);
+        const float4* s0 = reinterpret_cast<const float4*>(cur + (size_t)e.x * B);
+#pragma unroll
+        for (int v = 0; v < VPT; ++v) {
+          const float4 x4 = ld_plain(s0 + t + v * TPR);
+          acc[v].x = fmaf(wt, x4.x, acc[v].x);
+          acc[v].y = fmaf(wt, x4.y, acc[v].y);
+          acc[v].z = fmaf(wt, x4.z, acc[v].z);
+          acc[v].w = fmaf(wt, x4.w, acc[v].w);
+        }
+      }
+      if (row >= a.n_loc) continue;
+      const float2 dd = a.ddi[row];
+      const float d = dd.x, di = dd.y;
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) {
+        const int sl = t + v * TPR;
+        const float4 yv = ld_plain(reinterpret_cast<const float4*>(cur + (size_t)row * B) + sl);
+        float4 o;
+        if (CORR) {
+          const float4 rv = __ldg(reinterpret_cast<const float4*>(a.r + (size_t)row * B) + sl);  // constant during the pass
+          const float4 al = __ldg(al_p + sl);
+          o.x = al.x * ((di * (d * yv.x - acc[v].x) - cc * yv.x) + rv.x);
+          o.y = al.y * ((di * (d * yv.y - acc[v].y) - cc * yv.y) + rv.y);
+          o.z = al.z * ((di * (d * yv.z - acc[v].z) - cc * yv.z) + rv.z);
+          o.w = al.w * ((di * (d * yv.w - acc[v].w) - cc * yv.w) + rv.w);
+          if (has_prev) {
+            const float4 ga = __ldg(ga_p + sl);
+            const float4 pv = ld_plain(reinterpret_cast<const float4*>(prev + (size_t)row * B) + sl);
+            o.x -= ga.x * pv.x;
+            o.y -= ga.y * pv.y;
+            o.z -= ga.z * pv.z;
+            o.w -= ga.w * pv.w;
+          }
+        } else {
+          o.x = al_s * (di * (d * yv.x - acc[v].x) - cc * yv.x);
+          o.y = al_s * (di * (d * yv.y - acc[v].y) - cc * yv.y);
+          o.z = al_s * (di * (d * yv.z - acc[v].z) - cc * yv.z);
+          o.w = al_s * (di * (d * yv.w - acc[v].w) - cc * yv.w);
+          if (has_prev) {
+            const float4 pv = ld_plain(reinterpret_cast<const float4*>(prev + (size_t)row * B) + sl);
+            o.x -= ga_s * pv.x;
+            o.y -= ga_s * pv.y;
+            o.z -= ga_s * pv.z;
+            o.w -= ga_s * pv.w;
+          }
+        }
+        if (last) {
+          double2* xo = reinterpret_cast<double2*>(a.x + (size_t)row * B) + 2 * sl;
+          if (CORR) {
+            double2 p0 = xo[0], p1 = xo[1];
+            p0.x += (double)o.x;
+            p0.y += (double)o.y;
+            p1.x += (double)o.z;
+            p1.y += (double)o.w;
+            xo[0] = p0;
+            xo[1] = p1;
+          } else {
+            xo[0] = make_double2((double)o.x, (double)o.y);
+            xo[1] = make_double2((double)o.z, (double)o.w);
+          }
+        } else {
+          reinterpret_cast<float4*>(next + (size_t)row * B)[sl] = o;
+        }
+      }
+    }
+    if (pusher && !last && n_first >= nu) {   // every unit of the CTA is a boundary unit: push at the end
+      __syncthreads();
+      push_rows(v_next, next);
+    }
+    if (timer) {
+      const unsigned long long t = now();
+      t_work += t - t_mark;
+      t_mark = t;
+    }
+  }
+  if (timer) {
+    atomicAdd(a.timing, t_wait);
+    atomicAdd(a.timing + 1, t_work);
+    atomicAdd(a.timing + 2, (unsigned long long)a.len);
+  }
+}
+
+template <int B, int TPR>
+static int launch_persist_b(bool corr, PersistArgs a, cudaStream_t stream) {
+  constexpr int RP = FS_THREADS / TPR;
+  a.n_units = div_up(a.n_loc, RP);
+  int dev = 0, sms = 0, per_sm = 0;
+  FB_CUDA(cudaGetDevice(&dev));
+  FB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const void* fn = corr ? (const void*)k_filter_persist<B, TPR, true> : (const void*)k_filter_persist<B, TPR, false>;
+  if (corr)
+    FB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_filter_persist<B, TPR, true>, FS_THREADS, 0));
+  else
+    FB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_filter_persist<B, TPR, false>, FS_THREADS, 0));
+  const int g_max = std::max(1, sms * per_sm);
+  // balanced: every CTA gets the same number of row units (the grid shrinks rather than leaving a ragged last pass)
+  a.units_per_cta = div_up(a.n_units, g_max);
+  const int grid = div_up(a.n_units, a.units_per_cta);
+  void* args[] = {&a};
+  FB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(FS_THREADS), args, 0, stream));
+  FB_COUNT_LAUNCH(1);
+  return FB_OK;
+}
+
+int launch_filter_persist(bool corr, int b, const PersistArgs& a, cudaStream_t stream) {
+#define FB_CASE(BB, TT) \
+  case BB:              \
+    return launch_persist_b<BB, TT>(corr, a, stream);
+  switch (b) {
+    FB_CASE(8, 2)
+    FB_CASE(16, 4)
+    FB_CASE(24, 2)
+    FB_CASE(32, 4)
+    FB_CASE(40, 2)
+    FB_CASE(48, 4)
+    FB_CASE(56, 2)
+    FB_CASE(64, 4)
+    FB_CASE(72, 2)
+    FB_CASE(80, 4)
+    FB_CASE(88, 2)
+    FB_CASE(96, 4)
+    default:
+      set_error("filter (persistent): unsupported block size %d (multiples of 8 up to 96)", b);
       return FB_ERR_UNSUPPORTED;
   }
 #undef FB_CASE

@@ -50,4 +50,38 @@ int launch_filter_sell(int mode, int b, const SellF32& m, const int* mesh_off, i
                        const void* alpha, const void* gamma, const double* center, int step, int n_steps, bool has_prev,
                        const FilterTuning& tune, cudaStream_t stream);
 
+// ---- row-partitioned solve: all steps of a filter pass in one persistent cooperative kernel per GPU (sell.cu) ----
+struct PersistArgs {
+  const int2* entries;       // SELL copy of the LOCAL rows; ghost columns point at the views' ghost rows (sell_remap_ghosts)
+  const int* slice_ptr;
+  const float2* ddi;
+  int n_loc;
+  int n_units, units_per_cta;              // filled by the launcher (units = CTA passes of 256 / TPR rows)
+  int ghost_base;                          // first ghost row of a view (same on every rank)
+  const int* push_row;                     // push list, sorted by row: local rows some peer gathers ...
+  const int* push_dst;                     // ... and where they go: (peer << 24) | ghost slot on that peer
+  int n_push;
+  int push_first;                          // the view gathered by the first step still needs its ghost rows filled
+  const float* const* peer_views;          // device [6][world]: fp32 view v (= 2 * block + half) of rank p's blocks
+  int world, rank;
+  int v_prev, v_cur, v_next;               // views at the first step of this launch
+  const float* r;                          // correction form: the fp32 residual block (local)
+  double* x;                               // fp64 block the last step writes (plain) or updates (correction)
+  const void* alpha;                       // this launch's tables: double [len] (plain) or float [len][B] (correction)
+  const void* gamma;
+  const double* center;
+  int s0, len, deg;                        // first step, steps of this launch, steps of the pass
+  int prefetch;                            // L2 prefetch of the next unit's streams (pays when the rank's rows exceed L2)
+  unsigned* counter;                       // zeroed before the launch: arrivals of this GPU's CTAs
+  unsigned long long* my_flags;            // one 128-byte line per rank
+  unsigned long long* const* peer_flags;   // device [world]
+  unsigned long long epoch0;               // step s of the launch publishes epoch0 + 1 + s
+  int* err;
+  unsigned long long* timing;              // nullable: {ns at barriers, ns working, steps} of CTA 0 are added here
+};
+int launch_filter_persist(bool corr, int b, const PersistArgs& a, cudaStream_t stream);
+int sell_remap_ghosts(int2* entries, long long n_entries_cap, const int* slice_ptr, int n_slices, int n_loc, int ghost_base,
+                      cudaStream_t stream);
+int block_to_f32(const double* x, float* out, long long n, cudaStream_t stream);
+
 }  // namespace fb

@@ -2,12 +2,18 @@
 (BASELINE.json configs[3]: "synthetic 1M-vertex icosphere ... row-partitioned ... NCCL halo over
 NVLink").
 
-Rank r owns a contiguous block of rows of the adjacency.  The host-side partition logic below is
-pure numpy (tested on CPU, world sizes 1..8, by emulating the exchange); the solve itself is
-``focusr_eigs_smallest_dist``: the same Chebyshev-filtered subspace iteration as the single-GPU
-path, with one grouped ncclSend/ncclRecv of boundary rows before every SpMM and small all-reduces
-for the Gram blocks, residuals and norms.  ``torch.distributed`` is used only to agree on the NCCL
-unique id and to exchange the ghost lists once.
+The vertices are first ordered along the 3-D Morton (Z-order) curve of their positions, so that a
+contiguous block of rows is a compact patch of the surface whatever order the file listed them in;
+rank r owns one such block.  A rank never holds the whole graph: it keeps the triangles that touch
+its rows, numbers their vertices [own rows | ghosts sorted by global id] and assembles only that
+sub-mesh on its GPU with the same K1 kernels (``focusr_laplacian_build``) -- the rows of its own
+vertices come out complete, with the columns already in the local numbering the solver wants.
+The host-side partition logic below is pure numpy (tested on CPU for world sizes 1..8); the solve is
+``focusr_eigs_smallest_dist``: the Chebyshev-filtered subspace iteration of the single-GPU path with
+the halo fused into the kernels over NVLink peer memory (default) or exchanged by grouped
+ncclSend/ncclRecv, and small all-reduces for the Gram blocks, residuals and norms.
+``torch.distributed`` is used only to agree on the NCCL unique id / IPC handles and to exchange the
+ghost lists once.
 """
 from __future__ import annotations
 
@@ -18,7 +24,8 @@ import numpy as np
 from . import _lib
 from . import dist as fdist
 
-__all__ = ["row_bounds", "local_partition", "send_lists", "RowPartitionedSolver"]
+__all__ = ["row_bounds", "morton_order", "partition_mesh", "local_partition", "send_lists", "push_lists",
+           "RowPartitionedSolver"]
 
 
 def row_bounds(n_rows, world):
@@ -29,8 +36,65 @@ def row_bounds(n_rows, world):
     return np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
 
 
+def _spread_bits_21(v):
+    """Bits of a 21-bit integer moved to every third position (the classic magic-number interleave)."""
+    v = v.astype(np.uint64) & np.uint64(0x1FFFFF)
+    v = (v | (v << np.uint64(32))) & np.uint64(0x1F00000000FFFF)
+    v = (v | (v << np.uint64(16))) & np.uint64(0x1F0000FF0000FF)
+    v = (v | (v << np.uint64(8))) & np.uint64(0x100F00F00F00F00F)
+    v = (v | (v << np.uint64(4))) & np.uint64(0x10C30C30C30C30C3)
+    v = (v | (v << np.uint64(2))) & np.uint64(0x1249249249249249)
+    return v
+
+
+def morton_order(points):
+    """Permutation ``order`` (new index -> old index) that sorts the vertices along the Morton curve of their
+    positions, quantised to 21 bits per axis over the bounding box (ties keep the input order)."""
+    p = np.asarray(points, dtype=np.float64)
+    lo, hi = p.min(axis=0), p.max(axis=0)
+    span = np.where(hi > lo, hi - lo, 1.0)
+    q = np.minimum(((p - lo) / span * 2097151.0).astype(np.uint64), np.uint64(2097151))
+    key = _spread_bits_21(q[:, 0]) | (_spread_bits_21(q[:, 1]) << np.uint64(1)) | (_spread_bits_21(q[:, 2]) << np.uint64(2))
+    return np.argsort(key, kind="stable").astype(np.int64)
+
+
+def partition_mesh(points, tris, world, rank, reorder="morton"):
+    """What ``rank`` of ``world`` keeps of the mesh.  Returns a dict:
+    ``order`` (new -> old vertex id), ``bounds`` (row blocks in the new order), ``n_local``, ``row_begin``,
+    ``ghosts`` (sorted new global ids of the foreign vertices its triangles touch, hence grouped by owner),
+    ``points_local`` [n_local + n_ghost][3] and ``tris_local`` (the triangles touching its rows, in the local numbering
+    [own rows | ghosts]), ``recv_counts`` [world]."""
+    points = np.asarray(points, dtype=np.float64)
+    tris = np.asarray(tris, dtype=np.int64).reshape(-1, 3)
+    n = points.shape[0]
+    if reorder == "morton":
+        order = morton_order(points)
+    elif reorder in (None, "none"):
+        order = np.arange(n, dtype=np.int64)
+    else:
+        raise ValueError("reorder must be 'morton' or None")
+    inv = np.empty(n, dtype=np.int64)
+    inv[order] = np.arange(n, dtype=np.int64)
+    t_new = inv[tris]
+    bounds = row_bounds(n, world)
+    r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+    n_loc = r1 - r0
+    mine = ((t_new >= r0) & (t_new < r1)).any(axis=1)
+    t_sel = t_new[mine]
+    verts = np.unique(t_sel)
+    ghosts = verts[(verts < r0) | (verts >= r1)]
+    is_own = (t_sel >= r0) & (t_sel < r1)
+    t_loc = np.where(is_own, t_sel - r0, n_loc + np.searchsorted(ghosts, t_sel)).astype(np.int32)
+    owner = np.searchsorted(bounds[1:], ghosts, side="right")
+    recv_counts = np.bincount(owner, minlength=world).astype(np.int32)
+    pts_loc = np.ascontiguousarray(np.concatenate([points[order[r0:r1]], points[order[ghosts]]]))
+    return dict(order=order, bounds=bounds, n_local=n_loc, row_begin=r0, ghosts=ghosts, points_local=pts_loc,
+                tris_local=np.ascontiguousarray(t_loc), recv_counts=recv_counts)
+
+
 def local_partition(indptr, indices, bounds, rank):
-    """Local CSR of rank's rows with columns remapped to [local | ghosts] numbering.
+    """Local CSR of rank's rows cut out of a GLOBAL CSR, columns remapped to [local | ghosts] numbering (the form the
+    solver takes; ``partition_mesh`` + the device build produce the same thing without the global matrix).
 
     Returns dict(row_ptr, cols_local, entry_slice, ghosts (sorted global ids, hence grouped by owner),
     recv_counts [world])."""
@@ -62,10 +126,34 @@ def send_lists(all_ghosts, bounds, rank):
     return np.concatenate(idx).astype(np.int32), np.asarray(counts, dtype=np.int32)
 
 
-class RowPartitionedSolver:
-    """All ranks construct it with the same mesh, then call :meth:`eigs_smallest` collectively."""
+def push_lists(send_idx, send_counts, recv_counts_all, rank):
+    """The halo as a PUSH: which of ``rank``'s rows go where.  ``send_idx`` / ``send_counts`` are ``send_lists`` of this
+    rank, ``recv_counts_all[q]`` the ``recv_counts`` of rank q.  Rank q's ghost list is sorted by global id, so this rank's
+    rows sit in it contiguously, in the order of its own send list, after the ghosts q gets from lower ranks.  Returns
+    (rows int64, dst int64) sorted by row: local row ``rows[i]`` is copied to ghost slot ``dst[i] & 0xffffff`` of peer
+    ``dst[i] >> 24``."""
+    rows, dsts, so = [], [], 0
+    for q in range(len(send_counts)):
+        cnt = int(send_counts[q])
+        if cnt:
+            first_slot = int(np.sum(np.asarray(recv_counts_all[q])[:rank]))
+            rows.append(np.asarray(send_idx[so:so + cnt], dtype=np.int64))
+            dsts.append((q << 24) | (first_slot + np.arange(cnt, dtype=np.int64)))
+        so += cnt
+    if not rows:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    rows, dsts = np.concatenate(rows), np.concatenate(dsts)
+    o = np.argsort(rows, kind="stable")
+    return rows[o], dsts[o]
 
-    def __init__(self, points, tris):
+
+class RowPartitionedSolver:
+    """All ranks construct it with the same mesh, then call :meth:`eigs_smallest` collectively.
+
+    ``order`` maps the solver's row numbering back to the caller's vertex ids: row ``row_begin + i`` of this rank is
+    vertex ``order[row_begin + i]``; :meth:`gather_vectors` returns the full eigenvectors in the caller's order."""
+
+    def __init__(self, points, tris, reorder="morton"):
         torch = _lib.require_cuda()
         from ._device import DeviceGraph
 
@@ -79,43 +167,58 @@ class RowPartitionedSolver:
         uid_all = (C.c_char * 128).from_buffer_copy(ids[0])
         if self.world > 1:
             _lib.call("focusr_dist_init", C.cast(uid_all, C.c_void_p), self.rank, self.world)
-        # every rank assembles the whole adjacency on its own GPU (K1 is cheap) and keeps its rows
-        full = DeviceGraph([points], [tris])
-        info = full.mesh_info_host[0]
-        if info[1] != 0:
-            raise NotImplementedError("the row-partitioned solve needs a symmetric adjacency (closed, oriented mesh)")
-        self.n_global = full.n_points
-        self.n_zero_rows = int(info[2])
-        indptr, indices, weights = full.adjacency_host()
-        self.bounds = row_bounds(self.n_global, self.world)
-        part = local_partition(indptr, indices, self.bounds, self.rank)
-        all_ghosts = fdist.gather_objects(part["ghosts"])
-        send_idx, send_counts = send_lists(all_ghosts, self.bounds, self.rank)
-        r0, n_loc = part["row_begin"], part["n_local"]
-        e0, e1 = part["entry_slice"]
-        dev = full.device
+        part = partition_mesh(points, tris, self.world, self.rank, reorder)
+        self.order, self.bounds = part["order"], part["bounds"]
+        self.n_global = int(self.bounds[-1])
+        n_loc, ghosts = part["n_local"], part["ghosts"]
+        n_tot = n_loc + int(ghosts.size)
+        # K1 on the rank's sub-mesh: "mesh" 0 = its own rows (complete), "mesh" 1 = the ghost vertices (rows incomplete,
+        # dropped); the per-mesh facts of mesh 0 are this rank's share of the global ones
+        off = np.array([0, n_loc, n_tot] if ghosts.size else [0, n_loc], dtype=np.int32)
+        sub = DeviceGraph.from_device(torch.from_numpy(part["points_local"]), torch.from_numpy(part["tris_local"]), off)
+        own = sub.mesh_info_host[0]
+        one_way = int(round(fdist.all_reduce_sum(int(own[1]))))
+        if int(round(fdist.all_reduce_sum(int(own[3])))) != 0:
+            raise ValueError("the mesh has zero-length edges (non-finite weights, reference graph.py:177-178)")
+        if one_way != 0:
+            raise NotImplementedError("the row-partitioned solve needs a symmetric adjacency (closed, oriented mesh); "
+                                      "%d one-way entries" % one_way)
+        self.n_zero_rows = int(round(fdist.all_reduce_sum(int(own[2]))))
+        self.max_row_entries = int(own[4])
+        self.nnz_local = int(own[0])
+        dev = sub.device
         self.device = dev
-        self.n_local, self.n_ghost, self.row_begin = n_loc, int(part["ghosts"].size), r0
-        self.nnz_local = e1 - e0
-        self.row_ptr = torch.from_numpy(part["row_ptr"]).to(dev)
-        self.cols_local = torch.from_numpy(part["cols_local"]).to(dev)
-        self.weights = full.weights[e0:e1].clone()
-        self.degree = full.degree[r0 : r0 + n_loc].clone()
-        self.degree_inv = full.degree_inv[r0 : r0 + n_loc].clone()
-        self.points = full.points[r0 : r0 + n_loc].clone()
+        self.n_local, self.n_ghost, self.row_begin = n_loc, int(ghosts.size), part["row_begin"]
+        self.row_ptr = sub.row_ptr[: n_loc + 1].clone()
+        self.cols_local = sub.cols[: max(self.nnz_local, 1)].clone()
+        self.weights = sub.weights[: max(self.nnz_local, 1)].clone()
+        self.degree = sub.degree[:n_loc].clone()
+        self.degree_inv = sub.degree_inv[:n_loc].clone()
+        self.points = sub.points[:n_loc].clone()
+        del sub
+        # NCCL send/receive mode: what this rank ships to whom
+        all_ghosts = fdist.gather_objects(ghosts)
+        send_idx, send_counts = send_lists(all_ghosts, self.bounds, self.rank)
         self.send_idx = torch.from_numpy(send_idx if send_idx.size else np.zeros(1, np.int32)).to(dev)
         self.n_send = int(send_idx.size)
         self.send_counts = np.ascontiguousarray(send_counts, dtype=np.int32)
         self.recv_counts = np.ascontiguousarray(part["recv_counts"], dtype=np.int32)
         # P2P mode: where every ghost row lives (owner rank, row inside the owner's block)
-        ghosts = part["ghosts"]
         owner = np.searchsorted(self.bounds[1:], ghosts, side="right").astype(np.int32)
         g_row = (ghosts - self.bounds[owner]).astype(np.int32)
         self.ghost_peer = torch.from_numpy(owner if owner.size else np.zeros(1, np.int32)).to(dev)
         self.ghost_row = torch.from_numpy(g_row if g_row.size else np.zeros(1, np.int32)).to(dev)
-        self.rows_cap = int(np.max(np.diff(self.bounds)))
+        # persistent-kernel halo: the fp32 views carry ghost rows behind the owned rows (same layout on every rank), and
+        # every rank pushes the rows its peers gather into their ghost slots.  Rank q's ghost list is sorted by global id,
+        # so this rank's rows sit in it contiguously, in the order of its own send list, after the ghosts q gets from
+        # lower ranks.
+        self.ghost_base = int(np.max(np.diff(self.bounds)))
+        self.rows_cap = self.ghost_base + max(int(gh.size) for gh in all_ghosts)
+        rows, dsts = push_lists(send_idx, send_counts, fdist.gather_objects(self.recv_counts), self.rank)
+        self.n_push = int(rows.size)
+        self.push_row = torch.from_numpy((rows if rows.size else np.zeros(1)).astype(np.int32)).to(dev)
+        self.push_dst = torch.from_numpy((dsts if dsts.size else np.zeros(1)).astype(np.int32)).to(dev)
         self._shared_for_block = None
-        del full
         self._lib = lib
 
     def _ensure_shared(self, block):
@@ -133,33 +236,58 @@ class RowPartitionedSolver:
         self._shared_for_block = block
 
     def eigs_smallest(self, k, n_k_needed, k_buffer=1, min_eig_val=1e-10, tol=1e-10, max_outer=60, block_size=0,
-                      p2p=True):
-        """``p2p=True`` (default when world > 1): halo fused into the SpMM over NVLink peer memory;
-        ``p2p=False``: packed boundary rows exchanged with grouped ncclSend/ncclRecv."""
+                      p2p=True, options=None):
+        """``p2p=True`` (default when world > 1): halo fused into the kernels over NVLink peer memory, filter passes in
+        the fp32 forms with all steps of a pass in one persistent kernel per GPU; ``p2p=False``: fp64 steps with the
+        packed boundary rows exchanged by grouped ncclSend/ncclRecv.  Returns ``(vals, vecs, info)``: the eigenvalues
+        (identical on every rank) and this rank's rows of the eigenvectors."""
         torch = _lib.require_cuda()
         lib = self._lib
         b = int(block_size) if block_size else int(lib.focusr_eigs_block_size(k, n_k_needed, k_buffer, 0, self.n_zero_rows))
         use_p2p = bool(p2p) and self.world > 1
         if use_p2p:
             self._ensure_shared(b)
+        if isinstance(options, dict):
+            options = _lib.EigsOptions(**options)
+        opt_ptr = C.byref(options) if options is not None else None
         ldv = b
         vals = torch.zeros(ldv, dtype=torch.float64, device=self.device)
         vecs = torch.zeros((self.n_local, ldv), dtype=torch.float64, device=self.device)
-        ws_bytes = int(lib.focusr_eigs_dist_workspace_bytes(self.n_local, self.n_ghost, self.n_send, b, self.world))
+        ws_bytes = int(lib.focusr_eigs_dist_workspace_bytes(self.n_local, self.n_ghost, self.n_send, self.max_row_entries,
+                                                            b, self.world))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
         res_i, res_d = np.zeros(8, dtype=np.int32), np.zeros(2)
         _lib.call("focusr_eigs_smallest_dist", _lib.ptr(self.row_ptr), _lib.ptr(self.cols_local), _lib.ptr(self.weights),
                   _lib.ptr(self.degree), _lib.ptr(self.degree_inv), _lib.ptr(self.points), self.n_local, self.n_ghost,
                   self.row_begin, self.nnz_local, _lib.ptr(self.send_idx), self.n_send, _lib.ptr(self.send_counts),
-                  _lib.ptr(self.recv_counts), _lib.ptr(self.ghost_peer), _lib.ptr(self.ghost_row), int(use_p2p),
-                  self.rows_cap, self.n_zero_rows, int(k), int(n_k_needed), int(k_buffer),
+                  _lib.ptr(self.recv_counts), _lib.ptr(self.ghost_peer), _lib.ptr(self.ghost_row), self.ghost_base,
+                  _lib.ptr(self.push_row), _lib.ptr(self.push_dst), self.n_push, int(use_p2p),
+                  self.rows_cap, self.n_zero_rows, self.max_row_entries, int(k), int(n_k_needed), int(k_buffer),
                   float(min_eig_val), float(tol), int(max_outer), b, 0.0, _lib.ptr(vals), _lib.ptr(vecs), ldv,
-                  _lib.ptr(res_i), _lib.ptr(res_d), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
+                  _lib.ptr(res_i), _lib.ptr(res_d), _lib.ptr(ws), ws_bytes, opt_ptr, _lib.stream_ptr())
         m = int(res_i[1])
         info = dict(status=int(res_i[0]), n_found=m, k_final=int(res_i[2]), outer_iterations=int(res_i[3]),
-                    filter_degree=int(res_i[4]), block_size=b, world=int(res_i[7]), max_residual=float(res_d[0]), spectrum_bound=float(res_d[1]),
+                    filter_degree=int(res_i[4]), block_size=b, fp32_filter_degree=int(res_i[6]), world=int(res_i[7]),
+                    max_residual=float(res_d[0]), spectrum_bound=float(res_d[1]),
                     n_local=self.n_local, n_ghost=self.n_ghost, n_send=self.n_send, p2p=use_p2p)
         return vals[:m], vecs[:, :m], info
+
+    def gather_vectors(self, vecs):
+        """Every rank's rows -> the full eigenvectors [n_global][m] in the CALLER's vertex order, on every rank (a
+        check / export helper, not part of the solve)."""
+        torch = _lib.require_cuda()
+        if self.world > 1:
+            import torch.distributed as dist
+
+            sizes = [int(b1 - b0) for b0, b1 in zip(self.bounds[:-1], self.bounds[1:])]
+            parts = [torch.zeros((s, vecs.shape[1]), dtype=vecs.dtype, device=vecs.device) for s in sizes]
+            dist.all_gather(parts, vecs.contiguous())
+            new = torch.cat(parts)
+        else:
+            new = vecs
+        out = torch.empty_like(new)
+        out[torch.from_numpy(self.order).to(new.device)] = new
+        return out
 
     def close(self):
         if self.world > 1:

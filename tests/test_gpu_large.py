@@ -93,6 +93,7 @@ def test_row_partitioned_path_world1_matches_batched_solver():
     s = RowPartitionedSolver(m.points, m.tris)
     vals, vecs, info = s.eigs_smallest(k=7, n_k_needed=6)
     assert info["status"] == 0 and info["n_found"] == 6 and info["n_ghost"] == 0
+    vecs = s.gather_vectors(vecs)      # the solver works in Morton order; back to the caller's vertex order
     g = DeviceGraph([m.points], [m.tris])
     v2, x2, _ = g.eigs_smallest(k=7, n_k_needed=6)
     assert torch.allclose(vals, v2[0, :6], rtol=1e-9, atol=0)
@@ -113,12 +114,15 @@ def test_row_partitioned_multi_gpu_under_torchrun():
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 2)),
-                          "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.join(root, "tools", "rowpart_solve.py"),
-                          "60", "11"], capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stderr[-2000:]
-    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
-    assert line["status"] == 0 and line["n_found"] == 10 and line["max_residual_global"] <= 1e-9
+    for extra in (["p2p"], ["p2p", "shuffle"], ["nccl"]):
+        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 2)),
+                              "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.join(root, "tools", "rowpart_solve.py"),
+                              "60", "11"] + extra, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+        assert line["status"] == 0 and line["n_found"] == 10 and line["max_residual_global"] <= 1e-9
+        assert line["max_halo_fraction"] < 0.06
+        assert (line["fp32_filter_degree"] > 0) == (extra[0] == "p2p")   # fp32 forms in the persistent kernel, P2P mode only
 
 
 def test_batch_pipeline_full_size_properties():
