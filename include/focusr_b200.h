@@ -232,7 +232,7 @@ int focusr_spectral_coords(const double* vecs, int n_points, int ld, const int* 
  * c_hist / c_hist_f (1-D Wasserstein distance of log(v + 0.5 + eps), source flipped for _f) and
  * c_spatial / c_spatial_f (RMS difference at xyz nearest neighbours / n_samp_t); nn_idx
  * [n_pairs][n_samp_t] is the nearest sampled source point of each sampled target point.
- * c_lambda, min/compare, the n x n assignment and the flip list stay on the host.
+ * c_lambda, min/compare, the n x n assignment and the flip list: focusr_eigsort_decide (device) or the host classes.
  * ------------------------------------------------------------------------------------------- */
 size_t focusr_eigsort_workspace_bytes(int n_pairs, int n_samp_t, int n_samp_s, int n_features);
 int focusr_eigsort_costs(const double* vecs, int ld, const double* points,
@@ -241,6 +241,23 @@ int focusr_eigsort_costs(const double* vecs, int ld, const double* points,
                          int n_samp_s, int n_features, double* c_hist, double* c_hist_f,
                          double* c_spatial, double* c_spatial_f, long long* nn_idx, void* workspace,
                          size_t workspace_bytes, focusr_stream_t stream);
+
+/* C2, C5, D1  the n x n decisions of eigsort for every pair, on the device (eigsort.py:66-122, 142-160; focusr.py:
+ * 459-490): c_lambda from the eigenvalues (`eig_vals` [n_meshes][ldv], `n_found` [n_meshes] = how many each mesh
+ * returned: the gap averages over all of them), Q = min(c, c_f) with c = c_spatial * c_lambda * c_hist, the assignment
+ * (scipy.optimize.linear_sum_assignment's algorithm with its scan order and tie rules; of Q, or Q^T when the source is
+ * the reference), the flip list and the spectral weights.  Outputs: q_out [n_pairs][n] (cost of each matched pair, in
+ * the order of the reference's match list); dst / src / sign [n_meshes][n] = the column moves of
+ * focusr_flip_permute_columns for BOTH meshes of every pair (identity for the reference graph); weights
+ * [n_meshes][ns] for focusr_spectral_coords (ones when !weighted); *status (device int) = 1 if an assignment was
+ * infeasible (non-finite costs).  One thread per pair; n <= 96.  Meshes not named by t_mesh / s_mesh are not written. */
+size_t focusr_eigsort_decide_workspace_bytes(int n_pairs, int n_features);
+int focusr_eigsort_decide(const double* eig_vals, int ldv, const int* n_found, const int* t_mesh,
+                          const int* s_mesh, int n_pairs, const double* c_hist, const double* c_hist_f,
+                          const double* c_spatial, const double* c_spatial_f, int n_features, int ns,
+                          int target_as_reference, int weighted, double* q_out, int* dst, int* src,
+                          int* sign, double* weights, int* status, void* workspace,
+                          size_t workspace_bytes, focusr_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K4  exact k-nearest neighbours (scipy KDTree(refs).query(queries, k), p=2: focusr.py:351-353,

@@ -180,17 +180,26 @@ class DeviceGraph:
                   self.n_meshes, _lib.ptr(n_cols_dev), _lib.stream_ptr())
 
     def flip_permute(self, vecs, dst, src, sign):
-        """dst/src/sign: host int arrays [n_meshes][n_moves]."""
-        dst = np.ascontiguousarray(dst, dtype=np.int32).reshape(self.n_meshes, -1)
-        n_moves = dst.shape[1]
-        d, s, g = _dev_i32(dst), _dev_i32(np.asarray(src).reshape(self.n_meshes, -1)), _dev_i32(np.asarray(sign).reshape(self.n_meshes, -1))
+        """dst/src/sign: int arrays [n_meshes][n_moves], host (numpy) or device (torch int32, e.g. from
+        ``eigsort_decide``)."""
+        torch = _torch()
+        if isinstance(dst, torch.Tensor):
+            d, s, g = dst, src, sign
+            n_moves = int(d.shape[1])
+        else:
+            dst = np.ascontiguousarray(dst, dtype=np.int32).reshape(self.n_meshes, -1)
+            n_moves = dst.shape[1]
+            d, s, g = _dev_i32(dst), _dev_i32(np.asarray(src).reshape(self.n_meshes, -1)), _dev_i32(np.asarray(sign).reshape(self.n_meshes, -1))
         _lib.call("focusr_flip_permute_columns", _lib.ptr(vecs), self.n_points, int(vecs.shape[1]), _lib.ptr(self.mesh_off),
                   self.n_meshes, self.max_mesh_points, _lib.ptr(d), _lib.ptr(s), _lib.ptr(g), n_moves, _lib.stream_ptr())
 
     def spectral_coords(self, vecs, weights, ns):
-        """weights: host [n_meshes][ns] -> device [n_points][ns]."""
+        """weights: [n_meshes][ns], host (numpy) or device (torch float64) -> device [n_points][ns]."""
         torch = _torch()
-        w = torch.from_numpy(np.ascontiguousarray(weights, dtype=np.float64).reshape(self.n_meshes, ns)).to(self.device)
+        if isinstance(weights, torch.Tensor):
+            w = weights
+        else:
+            w = torch.from_numpy(np.ascontiguousarray(weights, dtype=np.float64).reshape(self.n_meshes, ns)).to(self.device)
         out = torch.empty((self.n_points, ns), dtype=torch.float64, device=self.device)
         _lib.call("focusr_spectral_coords", _lib.ptr(vecs), self.n_points, int(vecs.shape[1]), _lib.ptr(self.mesh_off),
                   self.n_meshes, self.max_mesh_points, _lib.ptr(w), int(ns), _lib.ptr(out), _lib.stream_ptr())
@@ -306,6 +315,33 @@ def curvatures(points, tris):
     _lib.call("focusr_curvatures", _lib.ptr(pts), _lib.ptr(tr), n, f, _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2]),
               _lib.ptr(out[3]), _lib.ptr(ws), nbytes, _lib.stream_ptr())
     return dict(gauss=out[0], mean=out[1], minimum=out[2], maximum=out[3])
+
+
+def eigsort_decide(graph, vals, n_found, t_mesh, s_mesh, costs, n_features, ns, target_as_reference=True, weighted=True):
+    """The n x n decisions of eigsort for every pair on the device (``focusr_eigsort_decide``): no host visit.
+    ``vals`` device [n_meshes][ldv]; ``n_found`` host ints [n_meshes]; ``costs`` = (c_hist, c_hist_f, c_spatial,
+    c_spatial_f) device tensors [n_pairs][n][n].  Returns device tensors: Q [n_pairs][n], dst / src / sign int32
+    [n_meshes][n], weights [n_meshes][ns], status int32 [1] (non-zero: an assignment was infeasible)."""
+    torch = _torch()
+    lib = _lib.load()
+    dev = graph.device
+    n, m = int(n_features), graph.n_meshes
+    tm, sm, nf = _dev_i32(t_mesh), _dev_i32(s_mesh), _dev_i32(n_found)
+    n_pairs = int(tm.shape[0])
+    q = torch.empty((n_pairs, n), dtype=torch.float64, device=dev)
+    ident = torch.arange(n, dtype=torch.int32, device=dev).repeat(m, 1)
+    dst, src = ident.clone(), ident
+    sign = torch.ones((m, n), dtype=torch.int32, device=dev)
+    w = torch.ones((m, int(ns)), dtype=torch.float64, device=dev)
+    status = torch.empty(1, dtype=torch.int32, device=dev)
+    ws_bytes = int(lib.focusr_eigsort_decide_workspace_bytes(n_pairs, n))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    ch, chf, cs, csf = costs
+    _lib.call("focusr_eigsort_decide", _lib.ptr(vals), int(vals.shape[1]), _lib.ptr(nf), _lib.ptr(tm), _lib.ptr(sm), n_pairs,
+              _lib.ptr(ch), _lib.ptr(chf), _lib.ptr(cs), _lib.ptr(csf), n, int(ns), int(bool(target_as_reference)),
+              int(bool(weighted)), _lib.ptr(q), _lib.ptr(dst), _lib.ptr(src), _lib.ptr(sign), _lib.ptr(w), _lib.ptr(status),
+              _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
+    return q, dst, src, sign, w, status
 
 
 def eigsort_costs(graph, vecs, t_mesh, s_mesh, idx_t, idx_s, n_features):

@@ -58,6 +58,9 @@ SIGNATURES = {
     "focusr_eigsort_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "focusr_eigsort_costs": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp,
                                   _vp, _sz, _vp]),
+    "focusr_eigsort_decide_workspace_bytes": (_sz, [_i, _i]),
+    "focusr_eigsort_decide": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp,
+                                   _vp, _sz, _vp]),
     "focusr_knn_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "focusr_knn": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "focusr_cdist": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp]),

@@ -4,9 +4,9 @@ This is the throughput path of BASELINE.json config 3 ("batch of 1024 synthetic 
 pairs sharded across 1/2/4/8 B200").  It is the same sequence ``Focusr.__init__`` +
 ``Focusr.align_maps`` run for one pair (reference focusr.py:134-169, 514-562, CPD = identity as
 in BASELINE.md section 3), but every kernel works on the block-diagonal graph of all 2P meshes, so
-one SpMM launch streams gigabytes instead of 1.3 MB and nothing but the n x n eigsort decisions
-(P x 36 numbers) visits the host between the upload of the vertices and the download of the
-correspondences.
+one SpMM launch streams gigabytes instead of 1.3 MB and nothing visits the host between the upload
+of the vertices and the download of the correspondences except the eigensolver's convergence test
+(a few hundred Ritz values and residuals per outer iteration).
 
 Mesh order inside the batch graph: targets 0..P-1, then sources 0..P-1.
 """
@@ -19,7 +19,6 @@ import numpy as np
 
 from . import _device, _lib
 from ._device import DeviceGraph
-from .eigsort import decide_batch
 
 __all__ = ["SpectralBatch"]
 
@@ -129,28 +128,11 @@ class SpectralBatch:
         t_mesh = np.arange(P, dtype=np.int32)
         s_mesh = np.arange(P, 2 * P, dtype=np.int32)
         ch, chf, cs, csf, _ = _device.eigsort_costs(g, vecs, t_mesh, s_mesh, idx_t, idx_s, n)
-        costs = torch.stack([ch, chf, cs, csf]).cpu().numpy()  # [4][P][n][n]
-        vals_h = vals.cpu().numpy()
-        # host: n x n decisions per pair (eigsort.py:66-105, focusr.py:459-490)
-        dst = np.tile(np.arange(n, dtype=np.int32), (2 * P, 1))
-        src = dst.copy()
-        sign = np.ones((2 * P, n), dtype=np.int32)
-        weights = np.ones((2 * P, ns))
-        # eigenvalue gap of every mesh over ALL its returned eigenvalues (graph.py:263-264)
-        if int(n_found.min()) == int(n_found.max()):
-            gaps = np.mean(np.diff(vals_h[:, : int(n_found[0])], axis=1), axis=1)
-        else:
-            gaps = np.array([np.mean(np.diff(vals_h[m, : n_found[m]])) for m in range(2 * P)])
-        gap = (gaps[:P] + gaps[P:]) / 2
-        vt, vs = vals_h[:P, :n], vals_h[P:, :n]
-        cl = np.exp((vt[:, :, None] - vs[:, None, :]) ** 2 / (2 * gap[:, None, None] ** 2))   # eigsort.py:155-160
-        Q, d, s, sg = decide_batch(cl, costs[0], costs[1], costs[2], costs[3], self.target_as_reference)
-        rows = slice(P, 2 * P) if self.target_as_reference else slice(0, P)
-        dst[rows], src[rows], sign[rows] = d, s, sg
-        if self.weighted:  # focusr.py:481-490
-            w = Q[:, :ns] * np.maximum(vs[:, :ns], vt[:, :ns])
-            w = np.exp(-(w**2) / (2 * np.mean(w, axis=1, keepdims=True) ** 2))
-            weights[:P] = weights[P:] = w
+        # n x n decisions per pair (eigsort.py:66-122, 142-160; focusr.py:459-490) on the device: c_lambda, min(c, c_f),
+        # the assignment (scipy's algorithm and tie rules), flips, column moves and spectral weights -- no host visit
+        Q, dst, src, sign, weights, decide_status = _device.eigsort_decide(
+            g, vals, n_found, t_mesh, s_mesh, (ch, chf, cs, csf), n, ns, self.target_as_reference, self.weighted)
+        costs = (ch, chf, cs, csf)
         presort = vecs.clone() if keep_presort else None
         g.flip_permute(vecs, dst, src, sign)
         coords = g.spectral_coords(vecs, weights, ns)
@@ -190,6 +172,7 @@ class SpectralBatch:
             torch.cuda.synchronize()
             self.timings = {ev[i][0]: ev[i - 1][1].elapsed_time(ev[i][1]) for i in range(1, len(ev))}
         return dict(graph=g, eig_vals=vals, eig_vecs=vecs, eigs_info=info, Q=Q, spectral_weights=weights[:P],
+                    eigsort_status=decide_status,
                     coords=coords, initial_idx=idx0[:, 0], smoothed_target_coords=smoothed_t[:nt_total],
                     source_projected_on_target=src_proj[nt_total:], final_idx=idx1[:, 0], knn3_idx=idx3,
                     knn3_dist=dist3, weighted_avg_transformed_points=weighted,

@@ -330,11 +330,12 @@ int chfsi_solve(BE& be, const SolveParams& p, MeshResult* out) {
       be.rr_sym();
     } else {
       be.get_GH(gh.data(), gh.data() + (size_t)M * B * B);
-      // the meshes' small eigenproblems are independent: one host thread each (OpenMP when compiled in) -- from 8
-      // meshes up only: for a single pair the team start-up costs more than it saves (Focusr() 38 -> 79 ms measured)
+      // the meshes' small eigenproblems are independent: a small OpenMP team (8 threads at most: one process per GPU
+      // times the steps in flight must not oversubscribe the host) -- from 8 meshes up only: for a single pair the team
+      // start-up costs more than it saves (Focusr() 38 -> 79 ms measured)
       std::vector<int> rr_rc(M, 0);
 #if defined(_OPENMP)
-#pragma omp parallel for schedule(dynamic) if (M >= 8) num_threads(M < 64 ? M : 64)
+#pragma omp parallel for schedule(dynamic) if (M >= 8) num_threads(8)
 #endif
       for (int m = 0; m < M; ++m) {
         const double cut = a_prev[m] < 0.0 ? 0.5 * p.beta : 2.0 * a_prev[m];
@@ -467,7 +468,7 @@ int chfsi_solve(BE& be, const SolveParams& p, MeshResult* out) {
     if (kind == PASS_FP32_CORR) {
       // y_k = x + z_k with the polynomial of column j normalised to 1 at theta_j: z_{k+1} = alpha_kj ((L - c) z_k + r_j) -
       // gamma_kj z_{k-1}, z_0 = 0, r = L x - theta x from the Rayleigh-Ritz step (fp64).  The M * B per-column tables
-      // (corr_table_column below) are built by the backend from the Ritz values it already holds -- a kernel on the
+      // (corr_table_column above) are built by the backend from the Ritz values it already holds -- a kernel on the
       // GPU, so that nothing N- or degree-sized is computed or uploaded by the host between two filter passes.
       be.filter_correction(deg, last_a.data(), beta_m.data());
     } else {

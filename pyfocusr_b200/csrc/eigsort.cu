@@ -12,6 +12,7 @@
 #include <float.h>
 
 #include "common.cuh"
+#include "eigsort_decide.h"
 #include "knn.cuh"
 #include "rowops.h"
 
@@ -315,6 +316,38 @@ int focusr_spectral_coords(const double* vecs, int n_points, int ld, const int* 
   return FB_OK;
 }
 
+// C2, C5, D1 on the device: one thread per pair runs eigsort_decide_pair (eigsort_decide.h) and writes the column moves
+// of BOTH meshes of the pair (identity for the reference graph) and their spectral weights.
+__global__ void __launch_bounds__(64)
+k_eigsort_decide(const double* __restrict__ eig_vals, int ldv, const int* __restrict__ n_found, const int* __restrict__ t_mesh,
+                 const int* __restrict__ s_mesh, int n_pairs, const double* __restrict__ c_hist,
+                 const double* __restrict__ c_hist_f, const double* __restrict__ c_spatial,
+                 const double* __restrict__ c_spatial_f, int n, int ns, int target_as_reference, int weighted,
+                 double* __restrict__ q_out, int* __restrict__ dst, int* __restrict__ src, int* __restrict__ sign,
+                 double* __restrict__ weights, double* __restrict__ scratch, int* __restrict__ status) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  const int mt = t_mesh[p], ms = s_mesh[p];
+  const size_t nn = (size_t)n * n;
+  int d[LSAP_MAX], s[LSAP_MAX], g[LSAP_MAX];
+  double w[LSAP_MAX];
+  const int rc = eigsort_decide_pair(eig_vals + (size_t)mt * ldv, n_found[mt], eig_vals + (size_t)ms * ldv, n_found[ms],
+                                     c_hist + p * nn, c_hist_f + p * nn, c_spatial + p * nn, c_spatial_f + p * nn, n, ns,
+                                     target_as_reference != 0, weighted != 0, q_out + (size_t)p * n, d, s, g, w,
+                                     scratch + (size_t)p * 2 * nn);
+  if (rc != 0) atomicExch(status, 1);
+  const int moved = target_as_reference ? ms : mt, fixed = target_as_reference ? mt : ms;
+  for (int k = 0; k < n; ++k) {
+    dst[(size_t)moved * n + k] = rc == 0 ? d[k] : k;
+    src[(size_t)moved * n + k] = rc == 0 ? s[k] : k;
+    sign[(size_t)moved * n + k] = rc == 0 ? g[k] : 1;
+    dst[(size_t)fixed * n + k] = k;
+    src[(size_t)fixed * n + k] = k;
+    sign[(size_t)fixed * n + k] = 1;
+  }
+  for (int k = 0; k < ns; ++k) weights[(size_t)mt * ns + k] = weights[(size_t)ms * ns + k] = rc == 0 ? w[k] : 1.0;
+}
+
 static int next_pow2(int v) {
   int p = 1;
   while (p < v) p <<= 1;
@@ -383,6 +416,28 @@ int focusr_eigsort_costs(const double* vecs, int ld, const double* points, const
   k_spatial<<<dim3(n * n, n_pairs), 128, 0, stream>>>(vecs, ld, mesh_point_off, t_mesh, s_mesh, idx_t, idx_s, nn_idx,
                                                       n_samp_t, n_samp_s, n, c_spatial, c_spatial_f);
   FB_COUNT_LAUNCH(3);
+  FB_LAUNCH_CHECK();
+  return FB_OK;
+}
+
+size_t focusr_eigsort_decide_workspace_bytes(int n_pairs, int n_features) {
+  return sizeof(double) * 2 * (size_t)n_pairs * n_features * n_features + 256;
+}
+
+int focusr_eigsort_decide(const double* eig_vals, int ldv, const int* n_found, const int* t_mesh, const int* s_mesh,
+                          int n_pairs, const double* c_hist, const double* c_hist_f, const double* c_spatial,
+                          const double* c_spatial_f, int n_features, int ns, int target_as_reference, int weighted,
+                          double* q_out, int* dst, int* src, int* sign, double* weights, int* status, void* workspace,
+                          size_t workspace_bytes, focusr_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  FB_REQUIRE(n_pairs > 0 && n_features >= 1 && n_features <= LSAP_MAX && ns >= 1 && ns <= n_features && n_features <= ldv,
+             "eigsort_decide: need 1 <= ns <= n_features <= %d", LSAP_MAX);
+  FB_REQUIRE(workspace_bytes >= focusr_eigsort_decide_workspace_bytes(n_pairs, n_features), "eigsort_decide: workspace too small");
+  FB_CUDA(cudaMemsetAsync(status, 0, sizeof(int), stream));
+  k_eigsort_decide<<<div_up(n_pairs, 64), 64, 0, stream>>>(eig_vals, ldv, n_found, t_mesh, s_mesh, n_pairs, c_hist, c_hist_f,
+                                                           c_spatial, c_spatial_f, n_features, ns, target_as_reference, weighted,
+                                                           q_out, dst, src, sign, weights, static_cast<double*>(workspace), status);
+  FB_COUNT_LAUNCH(1);
   FB_LAUNCH_CHECK();
   return FB_OK;
 }

@@ -39,7 +39,7 @@ def hostsim():
     so = os.path.join(d, "libhostsim.so")
     src_m = max(os.path.getmtime(os.path.join(d, "hostsim.cpp")),
                 *(os.path.getmtime(os.path.join(ROOT, "pyfocusr_b200", "csrc", f))
-                  for f in ("chfsi_driver.hpp", "dense_small.h", "nonsym_host.hpp", "rowops.h")))
+                  for f in ("chfsi_driver.hpp", "dense_small.h", "nonsym_host.hpp", "rowops.h", "eigsort_decide.h")))
     if not os.path.exists(so) or os.path.getmtime(so) < src_m:
         subprocess.check_call(["sh", os.path.join(d, "build.sh")])
     lib = C.CDLL(so)
@@ -54,4 +54,7 @@ def hostsim():
     lib.hostsim_eig_general.argtypes = [dp, C.c_int, dp, dp]
     lib.hostsim_edge_weight.argtypes = [dp, dp, C.c_int]
     lib.hostsim_edge_weight.restype = C.c_double
+    lib.hostsim_lsap.argtypes = [dp, C.c_int, ip]
+    lib.hostsim_eigsort_decide.argtypes = [dp, C.c_int, dp, C.c_int, dp, dp, dp, dp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           dp, ip, ip, ip, dp]
     return lib

@@ -12,6 +12,7 @@
 
 #include "../../pyfocusr_b200/csrc/cpd_host.hpp"
 #include "../../pyfocusr_b200/csrc/chfsi_driver.hpp"
+#include "../../pyfocusr_b200/csrc/eigsort_decide.h"
 #include "../../pyfocusr_b200/csrc/rowops.h"
 
 namespace {
@@ -335,4 +336,15 @@ int hostsim_eig_general(const double* a, int n, double* evals_ri, double* evecs_
 }
 
 double hostsim_edge_weight(const double* p1, const double* p2, int dim) { return fb::edge_weight(p1, p2, dim); }
+
+// the device-side decisions of eigsort (csrc/eigsort_decide.h), compiled for the host
+int hostsim_lsap(const double* cost, int n, int* col4row) { return fb::lsap_square(cost, n, col4row); }
+
+int hostsim_eigsort_decide(const double* vals_t, int nf_t, const double* vals_s, int nf_s, const double* c_hist,
+                           const double* c_hist_f, const double* c_spatial, const double* c_spatial_f, int n, int ns,
+                           int target_as_reference, int weighted, double* q, int* dst, int* src, int* sign, double* w) {
+  std::vector<double> scratch((size_t)2 * n * n);
+  return fb::eigsort_decide_pair(vals_t, nf_t, vals_s, nf_s, c_hist, c_hist_f, c_spatial, c_spatial_f, n, ns,
+                                 target_as_reference != 0, weighted != 0, q, dst, src, sign, w, scratch.data());
+}
 }

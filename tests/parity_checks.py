@@ -27,7 +27,8 @@ def check_pair_against_oracle(port, out, p, n_pairs, pts_t, tris_t, pts_s, tris_
     srt = port.sort_eigenmaps(pts_t, pts_s, out["idx_t"][p], out["idx_s"][p], vals[p, :nf[p]],
                               vals[n_pairs + p, :nf[n_pairs + p]], vt, vs, n_features, True)
     # (a)
-    assert np.max(np.abs(out["Q"][p] - srt["Q"]) / srt["Q"]) <= 1e-9
+    assert np.max(np.abs(out["Q"][p].cpu().numpy() - srt["Q"]) / srt["Q"]) <= 1e-9
+    assert int(out["eigsort_status"].item()) == 0
     post = out["eig_vecs"][o_s:o_s + n_s, :n_features].cpu().numpy()
     assert np.array_equal(post, vs[:, :n_features])
     # (b)

@@ -184,6 +184,14 @@ def test_batch_pipeline_full_size_properties():
     for p in range(0, P, 9):
         lo, hi = pts[off[p]:off[p + 1]].min(0), pts[off[p]:off[p + 1]].max(0)
         assert np.all(w[p * n:(p + 1) * n] >= lo - 1e-9) and np.all(w[p * n:(p + 1) * n] <= hi + 1e-9)
+    # two bench-size pairs through the oracle's stages after the solver (eigsort, spectral coordinates, KNN, 300 + 40
+    # smoothing passes, KNN, k = 3 positions), fed our pre-sort eigenvectors: indices and positions EQUAL, the only
+    # differences allowed upstream are distance ties of the initial correspondence (tests/parity_checks.py)
+    from parity_checks import check_pair_against_oracle
+
+    for p in (3, 47):
+        check_pair_against_oracle(port, out, p, P, pts[off[p]:off[p + 1]], base.tris, pts[off[P + p]:off[P + p + 1]], base.tris,
+                                  6, 3, 300, 40)
     # a pair run alone gives bit-identical correspondences to the same pair inside the batch
     for p in (5, 40):
         sel = np.concatenate([np.arange(off[p], off[p + 1]), np.arange(off[P + p], off[P + p + 1])])
