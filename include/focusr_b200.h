@@ -193,7 +193,8 @@ int focusr_eigs_smallest_dist(const int* row_ptr, const int* cols_local, const d
  * 0 = fp64, 1 = fp32 (k_spmm_f32: 8 nnz + 12 N + 12 b N per launch), 2 = fp32 correction form (k_spmm_corr:
  * 8 nnz + 12 N + 16 b N per launch); reset clears all three.  kind 3 = the persistent filter kernels of the last
  * row-partitioned solve of this process: {nanoseconds CTA 0 spent at the in-kernel barriers, nanoseconds it spent
- * working, steps, 0}. */
+ * working, steps, 0}.  kind 4 = the pruned KNN: {(query, reference) distance evaluations since the last reset, 0, 0,
+ * 0} (synchronises the device). */
 void focusr_profile_reset(void);
 void focusr_profile_get(double* out4_host);
 void focusr_profile_get_kind(int kind, double* out4_host);

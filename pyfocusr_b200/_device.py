@@ -156,6 +156,8 @@ class DeviceGraph:
                     ldv_use = b
                     restarts += 1
                     continue
+                if e.code < 100:   # a solver status, not a CUDA / argument error: say which meshes
+                    e.eigs_info = dict(status=res_i[:, 0].copy(), n_found=res_i[:, 1].copy(), max_residual=res_d[:, 0].copy())
                 raise
             finally:
                 del ws

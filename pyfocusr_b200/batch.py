@@ -111,11 +111,23 @@ class SpectralBatch:
             with torch.cuda.stream(side):
                 smoothed_t = g.mean_filter(g.points, self.graph_smoothing_iterations, 0, nt_total)
             smoothed_t.record_stream(main)
-        vals, vecs, info = g.eigs_smallest(k=n + 1, n_k_needed=n, k_buffer=1, tol=self.tol,
-                                           block_size=self.block_size, options=self.eigs_options)
+        try:
+            vals, vecs, info = g.eigs_smallest(k=n + 1, n_k_needed=n, k_buffer=1, tol=self.tol,
+                                               block_size=self.block_size, options=self.eigs_options)
+        except _lib.FocusrB200Error as exc:
+            info = getattr(exc, "eigs_info", None)
+            if info is None:
+                raise
+            bad = np.nonzero(info["status"] != 0)[0]
+            raise RuntimeError("eigensolve failed for %d of %d meshes: %s (mesh m is the %s of pair m %% %d); the other "
+                               "meshes of the batch were solved -- drop the named pairs and rerun" % (
+                                   bad.size, 2 * P, ", ".join("mesh %d: %s" % (m, _device.EIG_STATUS.get(int(info["status"][m]), "?"))
+                                                              for m in bad[:16]), "target if m < %d else source" % P, P)) from exc
         n_found = info["n_found"]
         if int(n_found.min()) < n:
-            raise RuntimeError("a mesh returned fewer than %d eigenpairs" % n)
+            short = np.nonzero(n_found < n)[0]
+            raise RuntimeError("meshes %s returned fewer than %d eigenpairs (pairs %s)" % (
+                short[:16].tolist(), n, sorted(set(int(m) % P for m in short[:16]))))
         g.normalize_columns(vecs, n_found)
         mark("eigensolve")
 

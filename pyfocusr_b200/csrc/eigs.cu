@@ -21,6 +21,8 @@
 
 namespace fb {
 
+unsigned long long pk_evals_read_and_maybe_reset(bool reset);  // knn_pruned.cu
+
 constexpr int GRAM_ROWS = 1024;  // rows per CTA (8 warps x 128 rows)
 constexpr int GRAM_THREADS = 256;
 
@@ -1151,6 +1153,7 @@ using namespace fb;
 extern "C" {
 
 void focusr_profile_reset(void) {
+  pk_evals_read_and_maybe_reset(true);
   g_filter_profile.collect();
   g_filter_profile_lowp.collect();
   g_filter_profile_corr.collect();
@@ -1161,6 +1164,12 @@ void focusr_profile_reset(void) {
 }
 
 void focusr_profile_get_kind(int kind, double* out4_host) {
+  if (kind == 4) {  // pruned KNN: (query, reference) distance evaluations since the last reset (synchronises the device)
+    cudaDeviceSynchronize();
+    out4_host[0] = (double)pk_evals_read_and_maybe_reset(false);
+    out4_host[1] = out4_host[2] = out4_host[3] = 0.0;
+    return;
+  }
   if (kind == 3) {  // persistent filter kernels of the last row-partitioned solve: CTA 0's {ns at barriers, ns working, steps}
     for (int i = 0; i < 4; ++i) out4_host[i] = g_persist_timing[i];
     return;

@@ -159,6 +159,20 @@ __device__ __forceinline__ bool lex_lt(double d2, int id, double bd, int bi) {
   return d2 < bd || (d2 == bd && id < bi);
 }
 
+// live profile: (query, reference) distance evaluations of the pruned search since the last reset (one atomic per warp
+// at kernel end), so that bench.py can state the KNN's rate as a fraction of the FP64 instruction peak
+__device__ unsigned long long g_pk_evals = 0ull;
+
+unsigned long long pk_evals_read_and_maybe_reset(bool reset) {
+  unsigned long long v = 0ull;
+  cudaMemcpyFromSymbol(&v, g_pk_evals, sizeof(v));
+  if (reset) {
+    const unsigned long long z = 0ull;
+    cudaMemcpyToSymbol(g_pk_evals, &z, sizeof(z));
+  }
+  return v;
+}
+
 template <int D, int K>
 __global__ void __launch_bounds__(PK_TQ)
 k_pk_search(const double* __restrict__ refs_sorted, const int* __restrict__ ref_orig, const int* __restrict__ ref_off,
@@ -208,6 +222,7 @@ k_pk_search(const double* __restrict__ refs_sorted, const int* __restrict__ ref_
   }
   __syncthreads();
   int left = s_j0, right = s_j0 + 1;
+  unsigned n_eval = 0;
   for (int t = 0; t < ntiles; ++t) {
     int j;
     if ((((t & 1) == 0) && left >= 0) || right >= ntiles)
@@ -233,6 +248,7 @@ k_pk_search(const double* __restrict__ refs_sorted, const int* __restrict__ ref_
     for (int e = threadIdx.x; e < cnt; e += PK_TQ) tile_idx[e] = ref_orig[rbase + r0 + e];
     __syncthreads();
     if (need) {
+      n_eval += cnt;
       for (int r = 0; r < cnt; ++r) {
         const double* rp = tile + r * dim;
         double d2 = 0.0;
@@ -259,6 +275,12 @@ k_pk_search(const double* __restrict__ refs_sorted, const int* __restrict__ ref_
       }
     }
     __syncthreads();  // everyone is done with the tile before the next load overwrites it
+  }
+  {  // profile counter: one atomic per warp
+    unsigned tot = n_eval;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if ((threadIdx.x & 31) == 0 && tot) atomicAdd(&g_pk_evals, (unsigned long long)tot);
   }
   if (valid) {
     const size_t o = (size_t)(qbase + qo) * kk;

@@ -26,6 +26,8 @@ def sub_batches(pair_ids, n_sub):
     """A rank's pair ids as ``n_sub`` contiguous, non-empty, near-equal groups (fewer if there are fewer pairs): the
     sub-batches ``SpectralBatch.run_concurrent`` keeps in flight on one GPU."""
     ids = list(pair_ids)
+    if not ids:
+        return []   # a rank without pairs has no sub-batch to run (callers skip the step)
     n_sub = max(1, min(int(n_sub), len(ids)))
     return [ids[k * len(ids) // n_sub:(k + 1) * len(ids) // n_sub] for k in range(n_sub)]
 

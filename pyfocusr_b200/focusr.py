@@ -298,6 +298,10 @@ class Focusr(object):
     def get_smoothed_correspondences(self):
         self.smoothed_target_coords = self.graph_target.mean_filter_graph(
             self.graph_target.points, iterations=self.graph_smoothing_iterations)
+        if self.smoothed_target_coords.shape[0] != self.graph_source.n_points and self.initial_correspondence_type == "hungarian":
+            raise Exception(   # focusr.py:377-385
+                "If number vertices between source & target don't match, initial_correspondence_type must\n"
+                "be 'kd' and not 'hungarian'. Current type is: {}".format(self.initial_correspondence_type))
         self.source_projected_on_target = self.graph_source.mean_filter_graph(
             self.smoothed_target_coords[self.corresponding_target_idx_for_each_source_pt, :],
             iterations=self.projection_smooth_iterations)
@@ -388,6 +392,32 @@ class Focusr(object):
     def get_source_mesh_transformed_nearest_neighbour(self):
         self.nearest_neighbour_transformed_mesh = _mesh_with_points(
             self.graph_source.vtk_mesh, self.nearest_neighbor_transformed_points)
+
+    # ------------------------------------------------------------------ focusr.py:576-599 (scalars for visualisation)
+    @staticmethod
+    def _set_scalars(mesh, values):
+        if isinstance(mesh, PolyData):
+            mesh.GetPointData().SetScalars(np.asarray(values))
+        else:  # a real vtkPolyData  # pragma: no cover
+            from vtk.util.numpy_support import numpy_to_vtk  # type: ignore
+
+            mesh.GetPointData().SetScalars(numpy_to_vtk(np.asarray(values)))
+
+    def set_transformed_source_scalars_to_corresp_target_idx(self):
+        for mesh in (self.weighted_avg_transformed_mesh, self.nearest_neighbour_transformed_mesh):
+            if mesh is not None:
+                self._set_scalars(mesh, self.corresponding_target_idx_for_each_source_pt)
+
+    def set_source_scalars_to_corresp_target_idx(self):
+        self._set_scalars(self.graph_source.vtk_mesh, self.corresponding_target_idx_for_each_source_pt)
+
+    def set_target_scalars_to_corresp_target_idx(self):
+        self._set_scalars(self.graph_target.vtk_mesh, np.arange(self.graph_target.n_points))
+
+    def set_all_mesh_scalars_to_corresp_target_idx(self):
+        self.set_target_scalars_to_corresp_target_idx()
+        self.set_source_scalars_to_corresp_target_idx()
+        self.set_transformed_source_scalars_to_corresp_target_idx()
 
     # viewers (focusr.py:646-795) need itkwidgets: out of scope
     def view_aligned_spectral_coords(self, *a, **k):

@@ -71,8 +71,27 @@ class _Array:
 
 
 class _PointData:
-    def __init__(self, arrays):
+    def __init__(self, arrays, owner=None):
         self._arrays = arrays
+        self._owner = owner
+
+    def SetScalars(self, values):
+        """vtkPointData::SetScalars for the PolyData stand-in: the active scalars become ``values`` (a numpy array, or
+        whatever ``numpy_to_vtk`` returned when VTK is installed)."""
+        if self._owner is None:
+            raise RuntimeError("this point data is not attached to a PolyData")
+        try:
+            from vtk.util.numpy_support import vtk_to_numpy  # type: ignore
+
+            values = vtk_to_numpy(values) if not isinstance(values, np.ndarray) else values
+        except ImportError:
+            pass
+        v = np.asarray(values)
+        if v.shape[0] != self._owner.points.shape[0]:
+            raise ValueError("scalars must have one value per point")
+        old = dict(self._owner.point_scalars)
+        self._owner.point_scalars = {"scalars": v}
+        self._owner.point_scalars.update({k: a for k, a in old.items() if k != "scalars"})
 
     def GetNumberOfArrays(self):
         return len(self._arrays)
@@ -110,7 +129,7 @@ class PolyData:
         return _Cell(self.tris[i])
 
     def GetPointData(self):
-        return _PointData([_Array(k, v) for k, v in self.point_scalars.items()])
+        return _PointData([_Array(k, v) for k, v in self.point_scalars.items()], owner=self)
 
     def copy(self):
         return PolyData(self.points.copy(), self.tris.copy(), dict(self.point_scalars))

@@ -70,3 +70,5 @@ def test_sub_batches_of_a_rank():
         assert len(groups) == min(n_sub, 128) and sum(groups, []) == mine          # contiguous, in order, complete
         assert min(map(len, groups)) >= 1 and max(map(len, groups)) - min(map(len, groups)) <= 1
     assert fdist.sub_batches([7], 2) == [[7]] and fdist.sub_batches([1, 2, 3], 0) == [[1, 2, 3]]
+    # a rank without pairs (pair_shard(3, 3, 4) == []) has no sub-batch at all, not one empty one
+    assert fdist.pair_shard(3, 3, 4) == [] and fdist.sub_batches([], 2) == []

@@ -382,6 +382,17 @@ def test_device_eigsort_decisions_equal_the_host_classes(hostsim):
                 assert np.allclose(q, q1, rtol=1e-13, atol=0) and np.allclose(w, w1, rtol=1e-12, atol=0)
 
 
+def test_polydata_scalar_setters():
+    """focusr.py:576-599 sets point scalars on the meshes for visualisation; the PolyData stand-in takes them."""
+    m = fmesh.icosphere(2)
+    vals = np.arange(m.points.shape[0])
+    m.GetPointData().SetScalars(vals)
+    assert np.array_equal(m.GetPointData().GetScalars().values if hasattr(m.GetPointData().GetScalars(), "values")
+                          else m.point_scalars["scalars"], vals)
+    with pytest.raises(ValueError):
+        m.GetPointData().SetScalars(vals[:-1])
+
+
 def test_non_triangle_cells_are_rejected():
     class Quad:
         def GetNumberOfPoints(self): return 4
