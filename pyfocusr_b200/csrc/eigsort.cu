@@ -405,11 +405,8 @@ int focusr_eigsort_costs(const double* vecs, int ld, const double* points, const
     rc = launch_knn(pts_s, 3, r_off, pts_t, 3, q_off, n_pairs, n_samp_t, 3, 1, nn_idx, nullptr, stream);
   if (rc) return rc;
   const size_t smem = sizeof(double) * (size_t)p2;
-  static size_t attr_smem = 48 * 1024;
-  if (smem > attr_smem) {
-    FB_CUDA(cudaFuncSetAttribute(k_sorted_logcols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
-  }
+  // the opt-in is per device and per function: set whenever it is needed (cheap), never cached process-wide
+  if (smem > 48 * 1024) FB_CUDA(cudaFuncSetAttribute(k_sorted_logcols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_sorted_logcols<<<dim3(3 * n, n_pairs), 512, smem, stream>>>(vecs, ld, mesh_point_off, t_mesh, s_mesh, idx_t,
                                                                 idx_s, n_samp_t, n_samp_s, n, s_max, p2, sorted);
   k_wasserstein<<<dim3(n * n, 2, n_pairs), 256, 0, stream>>>(sorted, n, n_samp_t, n_samp_s, s_max, c_hist, c_hist_f);

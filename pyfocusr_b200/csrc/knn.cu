@@ -101,13 +101,11 @@ int launch_knn(const double* refs, int ld_refs, const int* ref_off, const double
   dim3 grid(div_up(max_queries, KNN_THREADS), n_segments);
   const size_t smem = sizeof(double) * KNN_TILE * dim;
   if (smem > 48 * 1024) {
-    static bool done = false;
-    if (!done) {
-      cudaFuncSetAttribute(k_knn<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * KNN_TILE * KNN_MAX_DIM));
-      cudaFuncSetAttribute(k_knn<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * KNN_TILE * KNN_MAX_DIM));
-      cudaFuncSetAttribute(k_knn<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * KNN_TILE * KNN_MAX_DIM));
-      done = true;
-    }
+    // per device and per function: set on every call that needs it (cheap), never cached process-wide
+    const int cap = (int)(sizeof(double) * KNN_TILE * KNN_MAX_DIM);
+    FB_CUDA(cudaFuncSetAttribute(k_knn<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    FB_CUDA(cudaFuncSetAttribute(k_knn<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    FB_CUDA(cudaFuncSetAttribute(k_knn<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
   }
 #define FB_KNN(DD, KK) \
   k_knn<DD, KK><<<grid, KNN_THREADS, smem, stream>>>(refs, ld_refs, ref_off, queries, ld_queries, query_off, dim, k, idx, dist)

@@ -335,11 +335,8 @@ int launch_knn_pruned(const double* refs, int ld_refs, const int* ref_off, const
   k_pk_bbox<<<n_segments, 256, 0, stream>>>(refs, ld_refs, ref_off, queries, ld_queries, query_off, dim, seg_lo, seg_inv);
   const int p2 = next_pow2(max_refs > max_queries ? max_refs : max_queries);
   const size_t sort_smem = sizeof(unsigned long long) * (size_t)p2;
-  static size_t sort_attr = 48 * 1024;
-  if (sort_smem > sort_attr) {
-    FB_CUDA(cudaFuncSetAttribute(k_pk_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
-    sort_attr = sort_smem;
-  }
+  // the opt-in is per device and per function: set whenever it is needed (cheap), never cached process-wide
+  if (sort_smem > 48 * 1024) FB_CUDA(cudaFuncSetAttribute(k_pk_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
   k_pk_sort<<<dim3(n_segments, 2), 1024, sort_smem, stream>>>(refs, ld_refs, ref_off, queries, ld_queries, query_off,
                                                               dim, seg_lo, seg_inv, p2, refs_sorted, ref_orig, q_orig,
                                                               q_key, tile_lo, tile_hi, tile_key);
