@@ -186,6 +186,116 @@ k_gram(const double* __restrict__ x, const double* __restrict__ z, const double*
   }
 }
 
+// The same Gram pair for WIDE blocks (b >= 64: BASELINE.json configs[4], k up to 64).  There the contraction is bound
+// by the FP64 tensor pipe (4 N b^2 flop against 16 b N bytes: 24 flop/B at b = 96), and k_gram above -- operands straight
+// from global memory, 14 loads per 24 DMMA, every X tile re-read by each of the b/8 column groups -- kept that pipe only
+// 35% busy (profiles/r1_summary.md).  Here a CTA stages 16 rows of X and Z at a time in shared memory (row stride b + 4
+// doubles: the 4 rows x 8 columns of a fragment load fall into distinct banks), the next stage is already in flight in
+// registers while the current one is multiplied, and the 8 warps split the output tiles 4 (p) x 2 (q) so that nothing
+// has to be reduced across warps: every warp writes its own tiles of the (mesh, chunk) partial.  blockIdx.z cuts the q
+// tiles in three so that one 100k-vertex mesh (98 chunks) still fills the 148 SMs twice.
+constexpr int GW_R = 16;   // rows per stage
+constexpr int GW_ZS = 3;   // q-tile groups (grid.z)
+template <int B>
+__global__ void __launch_bounds__(GRAM_THREADS, 2)
+k_gram_wide(const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ degree,
+            const double* __restrict__ degree_inv, const int* __restrict__ mesh_off, int sym,
+            double* __restrict__ partial, int chunks_max) {
+  constexpr int PT = B / 8, QZ = (PT + GW_ZS - 1) / GW_ZS, PW = (PT + 3) / 4, QW = (QZ + 1) / 2;
+  constexpr int LD = B + 4;
+  constexpr int V2 = GW_R * B / 2, NV = (V2 + GRAM_THREADS - 1) / GRAM_THREADS;
+  __shared__ __align__(16) double sx[GW_R][LD];
+  __shared__ __align__(16) double sz[GW_R][LD];
+  __shared__ double sg[GW_R], sh[GW_R];
+  const int mesh = blockIdx.y, chunk = blockIdx.x;
+  const int r0 = mesh_off[mesh] + chunk * GRAM_ROWS;
+  const int r1 = min(mesh_off[mesh + 1], r0 + GRAM_ROWS);
+  if (r0 >= r1) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rr = lane & 3, cc = lane >> 2;
+  const int p_first = (warp >> 1) * PW;
+  const int q_first = blockIdx.z * QZ + (warp & 1) * QW;
+  const int q_lim = min(PT, ((int)blockIdx.z + 1) * QZ);
+  double accg[PW][QW][2], acch[PW][QW][2];
+#pragma unroll
+  for (int a = 0; a < PW; ++a)
+#pragma unroll
+    for (int b = 0; b < QW; ++b) accg[a][b][0] = accg[a][b][1] = acch[a][b][0] = acch[a][b][1] = 0.0;
+  double2 px[NV], pz[NV];
+  double pg = 0.0, ph = 0.0;
+  auto fetch = [&](int rs) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int e = (int)threadIdx.x + v * GRAM_THREADS;
+      px[v] = make_double2(0.0, 0.0);
+      pz[v] = make_double2(0.0, 0.0);
+      if (e < V2) {
+        const int row = rs + (2 * e) / B, col = (2 * e) % B;
+        if (row < r1) {
+          px[v] = __ldg(reinterpret_cast<const double2*>(x + (size_t)row * B + col));
+          pz[v] = __ldg(reinterpret_cast<const double2*>(z + (size_t)row * B + col));
+        }
+      }
+    }
+    pg = ph = 0.0;
+    if ((int)threadIdx.x < GW_R && rs + (int)threadIdx.x < r1) {
+      const int row = rs + (int)threadIdx.x;
+      pg = sym ? degree[row] + 1e-8 : 1.0;
+      ph = sym ? 1.0 : degree_inv[row];
+    }
+  };
+  fetch(r0);
+  for (int rs = r0; rs < r1; rs += GW_R) {
+    __syncthreads();  // the previous stage has been consumed
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int e = (int)threadIdx.x + v * GRAM_THREADS;
+      if (e < V2) {
+        const int lr = (2 * e) / B, col = (2 * e) % B;
+        *reinterpret_cast<double2*>(&sx[lr][col]) = px[v];
+        *reinterpret_cast<double2*>(&sz[lr][col]) = pz[v];
+      }
+    }
+    if ((int)threadIdx.x < GW_R) {
+      sg[threadIdx.x] = pg;
+      sh[threadIdx.x] = ph;
+    }
+    __syncthreads();
+    if (rs + GW_R < r1) fetch(rs + GW_R);  // in flight while this stage is multiplied
+#pragma unroll
+    for (int kk = 0; kk < GW_R; kk += 4) {
+      const int lr = kk + rr;
+      const double gw = sg[lr], hw = sh[lr];
+      double a[PW], bg[QW], bh[QW];
+#pragma unroll
+      for (int t = 0; t < PW; ++t) a[t] = (p_first + t < PT) ? sx[lr][8 * (p_first + t) + cc] : 0.0;
+#pragma unroll
+      for (int t = 0; t < QW; ++t) {
+        const bool ok = q_first + t < q_lim;
+        bg[t] = ok ? sx[lr][8 * (q_first + t) + cc] * gw : 0.0;
+        bh[t] = ok ? sz[lr][8 * (q_first + t) + cc] * hw : 0.0;
+      }
+#pragma unroll
+      for (int t = 0; t < PW; ++t)
+#pragma unroll
+        for (int u = 0; u < QW; ++u) {
+          dmma884(accg[t][u][0], accg[t][u][1], a[t], bg[u]);
+          dmma884(acch[t][u][0], acch[t][u][1], a[t], bh[u]);
+        }
+    }
+  }
+  double* dst = partial + ((size_t)mesh * chunks_max + chunk) * 2 * B * B;
+#pragma unroll
+  for (int t = 0; t < PW; ++t)
+#pragma unroll
+    for (int u = 0; u < QW; ++u) {
+      if (p_first + t >= PT || q_first + u >= q_lim) continue;
+      const int p = 8 * (p_first + t) + cc, q = 8 * (q_first + u) + 2 * rr;
+      *reinterpret_cast<double2*>(dst + (size_t)p * B + q) = make_double2(accg[t][u][0], accg[t][u][1]);
+      *reinterpret_cast<double2*>(dst + (size_t)B * B + (size_t)p * B + q) = make_double2(acch[t][u][0], acch[t][u][1]);
+    }
+}
+
 // One warp (NT = 32, many small meshes in flight) or one CTA (NT = 256, large blocks) per mesh: sum
 // the chunk partials in chunk order, then the b x b Rayleigh-Ritz step in shared memory
 // (Cholesky, congruence, round-robin Jacobi: dense_small.h).
@@ -806,10 +916,16 @@ struct CudaBackend {
   }
   template <int BB>
   void gram_t() {
-    constexpr int QT = GramCfg<BB>::QT;
-    dim3 grid(chunks_max, M, (BB / 8 + QT - 1) / QT);
-    k_gram<BB, QT><<<grid, GRAM_THREADS, 0, stream>>>(X, Xn, g.degree, g.degree_inv, g.mesh_off, sym ? 1 : 0,
-                                                      partial, chunks_max);
+    if constexpr (BB >= 64) {
+      dim3 grid(chunks_max, M, GW_ZS);
+      k_gram_wide<BB><<<grid, GRAM_THREADS, 0, stream>>>(X, Xn, g.degree, g.degree_inv, g.mesh_off, sym ? 1 : 0, partial,
+                                                         chunks_max);
+    } else {
+      constexpr int QT = GramCfg<BB>::QT;
+      dim3 grid(chunks_max, M, (BB / 8 + QT - 1) / QT);
+      k_gram<BB, QT><<<grid, GRAM_THREADS, 0, stream>>>(X, Xn, g.degree, g.degree_inv, g.mesh_off, sym ? 1 : 0,
+                                                        partial, chunks_max);
+    }
   }
   template <int BB>
   void rotate_t() {

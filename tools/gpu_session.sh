@@ -8,6 +8,15 @@ mkdir -p gpurun_out
 what="${*:-tests bench launches full dense}"
 TAG=${TAG:-r2}
 SMALL="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-rowpart"
+# gpurun brings back at most 64 MiB: a report is exported to CSV on the box (raw counters per launch, and the source page
+# with per-line stall samples) and the .ncu-rep itself is dropped
+export_rep() {
+  [ -f $1.ncu-rep ] || return 0
+  ncu -i $1.ncu-rep --page raw --csv > $1_raw.csv 2>/dev/null
+  ncu -i $1.ncu-rep --page source --csv > $1_source.csv 2>/dev/null
+  gzip -f $1_source.csv
+  rm -f $1.ncu-rep
+}
 has() { case " $what " in *" $1 "*) return 0;; esac; return 1; }
 
 if has tests; then
@@ -29,20 +38,26 @@ if has launches && [ $small_ok -eq 0 ]; then
   echo "launch list exit $?"
 fi
 if has full && [ $small_ok -eq 0 ]; then
-  for spec in "corr:k_filter_sell<16, 4, 3:40" "f32:k_filter_sell<16, 4, 0:40" "smooth:k_mean_filter<3>:400"; do
+  for spec in "corr:k_filter_sell<.int.16, .int.4, .int.3,:40" "f32:k_filter_sell<.int.16, .int.4, .int.0,:40" "smooth:k_mean_filter<.int.3>:400"; do
     name=${spec%%:*}; rest=${spec#*:}; pat=${rest%:*}; skip=${rest##*:}
     timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$pat" -s $skip -c 3 \
         -f -o gpurun_out/${TAG}_full_$name $SMALL > gpurun_out/${TAG}_ncu_full_$name.log 2>&1
     echo "full $name exit $?"
+    export_rep gpurun_out/${TAG}_full_$name
   done
 fi
 if has dense; then
   timeout 600 python tools/dense_evidence.py > gpurun_out/${TAG}_dense.json 2> gpurun_out/${TAG}_dense.err
   echo "dense exit $?"; cut -c1-400 gpurun_out/${TAG}_dense.json
   if has densencu; then
-    timeout 900 ncu --set full --clock-control none --kernel-name-base demangled -k "regex:k_gram<96|k_rotate<96|k_pk_search<3, 1" -c 8 \
+    timeout 900 ncu --set full --clock-control none --kernel-name-base demangled -k "regex:k_gram<.int.96|k_rotate<.int.96|k_pk_search<.int.3, .int.1" -c 8 \
         -f -o gpurun_out/${TAG}_full_dense python tools/dense_evidence.py --no-micro > gpurun_out/${TAG}_ncu_full_dense.log 2>&1
     echo "dense ncu exit $?"
+    export_rep gpurun_out/${TAG}_full_dense
   fi
+fi
+if has latency; then
+  timeout 300 python tools/pair_latency.py > gpurun_out/${TAG}_pair_latency.log 2>&1
+  echo "latency exit $?"; cat gpurun_out/${TAG}_pair_latency.log
 fi
 ls -la gpurun_out | tail -30
