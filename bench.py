@@ -284,6 +284,12 @@ def run_ours(a):
             stages[k] = round(stages.get(k, 0.0) + v, 3)
     sb.overlap_smoothing = ov
     total_launches = fdist.all_reduce_sum(launches)
+    dense = None
+    if world == 1 and not a.no_dense:
+        try:
+            dense = dense_side_evidence(jobs[0]["points"], P // S, n)
+        except Exception as exc:  # a reporting extra must never cost the bench line
+            dense = {"error": repr(exc)}
     # BASELINE.json configs[3], outside the timed region: ONE 998 562-vertex icosphere, k = 10
     # smallest eigenpairs (+1 null).  N > 1: row-partitioned over all N GPUs (halo fused into the kernels over NVLink, the
     # filter passes as persistent kernels, dot products all-reduced) -- a strong-scaling number; N = 1: the single-GPU solve.
@@ -356,6 +362,18 @@ def run_ours(a):
     except Exception as exc:  # a reporting extra must never cost the bench line
         secondary["other_hbm_streams"] = {"error": repr(exc)}
     secondary["rowpart_1m"] = rowpart
+    if dense is not None:
+        secondary["knn_frac_fp64_peak"] = dense.pop("knn_frac_fp64_peak", None)
+        secondary["knn_pruned"] = dense.pop("knn_pruned", None)
+        secondary["config5_k65"] = dense.pop("config5_k65", None)
+        secondary["fp64_peaks"] = dense.pop("fp64_peaks", None)
+        if dense:
+            secondary["dense_evidence_error"] = dense
+    if world == 1 and not a.no_nonsym:
+        try:
+            secondary["nonsym_batch"] = nonsym_batch_leg()
+        except Exception as exc:  # a reporting extra must never cost the bench line
+            secondary["nonsym_batch"] = {"error": repr(exc)}
     if world == 1 and not a.no_cpu_baseline:
         secondary["widened_rows_ms"] = widened_rows_timing(a.nu)
     cpu = None
@@ -433,6 +451,133 @@ def rowpart_1m(world, nu=316, k=11):
             "max_rel_err_vs_scipy": rel, "within_1e-6": None if rel is None else bool(rel <= 1e-6)}
 
 
+def dense_side_evidence(points, n_pairs, n):
+    """The FP64-ALU / FP64-tensor side of the path, outside the timed region (N = 1 only):
+      * fp64_peaks: the denominators, measured on THIS GPU by tools/micro/fp64_peak (hand DMMA / DFMA issue loops; built
+        by __graft_entry__.build()), else the figures of profiles/r2_dense_evidence.json (same pool) -- `source` says which;
+      * knn_pruned: the bench-shape KNN (n_pairs segments of n x n, d = 3, k = 1 and 3) with the live count of (query,
+        reference) distance evaluations, hence FP64 instructions per second (3 DSUB + 3 DMUL + 2 DADD per evaluation: no
+        FMA, the sums must round as numpy's do) as a fraction of the DFMA issue peak -> knn_frac_fp64_peak;
+      * config5_k65: BASELINE.json configs[4] top end, k = 65 smallest eigenpairs of the 100 002-vertex perturbed sphere
+        (block 96: Gram / rotation on the FP64 tensor pipe) against the scipy golden vector."""
+    import torch
+
+    from pyfocusr_b200 import _device, _lib
+    from pyfocusr_b200._device import DeviceGraph
+    from pyfocusr_b200.mesh import perturbed_ellipsoid
+
+    lib = _lib.load()
+    out = {}
+    exe = os.path.join(ROOT, "tools", "micro", "fp64_peak")
+    peaks = None
+    if os.path.exists(exe):
+        try:
+            peaks = json.loads(subprocess.run([exe], capture_output=True, text=True, check=True, timeout=120).stdout.strip().splitlines()[-1])
+            peaks["source"] = "tools/micro/fp64_peak on this GPU (of measured)"
+        except Exception:
+            peaks = None
+    if peaks is None:
+        rec = os.path.join(ROOT, "profiles", "r2_dense_evidence.json")
+        if os.path.exists(rec):
+            peaks = dict(json.load(open(rec))["fp64_peaks"], source="profiles/r2_dense_evidence.json (same pool, earlier box)")
+    out["fp64_peaks"] = peaks
+    refs, qs = points[: n_pairs * n], points[n_pairs * n: 2 * n_pairs * n]
+    seg = torch.arange(n_pairs + 1, dtype=torch.int32, device="cuda") * n
+    knn = {}
+    for k in (1, 3):
+        kw = dict(k=k, ref_off=seg, query_off=seg, max_queries=n, max_refs=n)
+        _device.knn(refs, qs, **kw)
+        lib.focusr_profile_reset()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _device.knn(refs, qs, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        pr = np.zeros(4)
+        lib.focusr_profile_get_kind(4, pr.ctypes.data)
+        evals = float(pr[0])
+        rec = {"ms": ms, "queries_per_s": n_pairs * n / ms * 1e3, "evaluations_per_query": evals / (n_pairs * n),
+               "of_brute_force": evals / (float(n_pairs) * n * n), "fp64_instructions_per_s": 8.0 * evals / ms * 1e3}
+        if peaks:
+            rec["frac_of_dfma_issue_peak"] = rec["fp64_instructions_per_s"] / (peaks["dfma_ginstr_per_s"] * 1e9)
+        knn["k%d_d3" % k] = rec
+    out["knn_pruned"] = knn
+    out["knn_frac_fp64_peak"] = {k: v.get("frac_of_dfma_issue_peak") for k, v in knn.items()}
+    m = perturbed_ellipsoid(100, seed=5, semi_axes=(1.0, 1.0, 1.0))
+    g = DeviceGraph([m.points], [m.tris])
+    k = 65
+    g.eigs_smallest(k=k, n_k_needed=k - 1)
+    best = None
+    for _ in range(2):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        vals, vecs, info = g.eigs_smallest(k=k, n_k_needed=k - 1)
+        e1.record()
+        torch.cuda.synchronize()
+        best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
+    rec = {"seconds": best / 1e3, "vertices": int(g.n_points), "block": int(info["block_size"]),
+           "outer_iterations": int(info["outer_iterations"][0]), "filter_degree": int(info["filter_degree"][0]),
+           "max_residual": float(info["max_residual"][0]), "status": int(info["status"][0])}
+    gold_path = os.path.join(ROOT, "tests", "golden", "large_eigs.npz")
+    if os.path.exists(gold_path):
+        gold = np.load(gold_path)["nu100_seed5_k65"]
+        v = vals[0, : k - 1].cpu().numpy()
+        rec["max_rel_err_vs_scipy"] = float(np.max(np.abs(v - gold[: k - 1]) / gold[: k - 1]))
+    rec["fp64_tensor_pipe"] = ("ncu of this solve: profiles/r2_summary.md (k_gram_wide<96>, k_rotate<96>: "
+                               "sm__inst_executed_pipe_tensor_subpipe_dmma / DMMA-active)")
+    out["config5_k65"] = rec
+    return out
+
+
+def nonsym_batch_leg(n_pairs=32, reps=2):
+    """BASELINE.json configs[0] as a batch, outside the timed region (N = 1 only): `n_pairs` jittered copies of the
+    reference's own shipped 15k pair (tests/golden/meshes.npz; open meshes -> structurally NON-symmetric adjacency, 2
+    unreferenced vertices in the source -> the retry contract ends at k = 14 with 11 pairs) through the same batched
+    pipeline.  The eigensolve takes the non-symmetric path: Euclidean projection, fp64 filter steps on CSR, the general
+    b x b Rayleigh-Ritz step on the device (one CTA per mesh), b = 48."""
+    import torch
+
+    from pyfocusr_b200 import SpectralBatch
+
+    z = np.load(os.path.join(ROOT, "tests", "golden", "meshes.npz"))
+    tp, tt = z["target_mesh_15k_points"], z["target_mesh_15k_tris"].astype(np.int64)
+    sp, st = z["source_mesh_15k_points"], z["source_mesh_15k_tris"].astype(np.int64)
+    rng = np.random.RandomState(7)
+    pts, tris, off = [], [], [0]
+    for base_p, base_t in ((tp, tt), (sp, st)):
+        scale = 1e-4 * float(np.ptp(base_p, axis=0).max())
+        for i in range(n_pairs):
+            pts.append(base_p + (scale * rng.randn(*base_p.shape) if i else 0.0))   # copy 0 is the shipped mesh itself
+            tris.append(base_t + off[-1])
+            off.append(off[-1] + base_p.shape[0])
+    pts_d = torch.from_numpy(np.ascontiguousarray(np.concatenate(pts))).cuda()
+    tris_d = torch.from_numpy(np.concatenate(tris).astype(np.int32)).cuda()
+    off = np.asarray(off, dtype=np.int32)
+    sb = SpectralBatch(N_SPECTRAL, N_EXTRA, N_SAMPLES, SMOOTH_T, SMOOTH_S, seed=3)
+    out = sb.run(pts_d, tris_d, off, n_pairs)   # warm-up
+    best = None
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = sb.run(pts_d, tris_d, off, n_pairs)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    info = out["eigs_info"]
+    ok = bool(np.all(info["status"] == 0))
+    return {"config": "configs[0] as a batch: %d jittered copies of the shipped 15k pair (non-symmetric adjacency)" % n_pairs,
+            "pairs_per_s": n_pairs / (best / 1e3), "ms_per_batch": best, "block": int(info["block_size"]),
+            "all_converged": ok, "max_residual": float(info["max_residual"].max()),
+            "k_final": [int(info["k_final"][0]), int(info["k_final"][n_pairs])],
+            "pairs_found": [int(info["n_found"][0]), int(info["n_found"][n_pairs])],
+            "outer_iterations": int(info["outer_iterations"].max()), "filter_degree": int(info["filter_degree"].max())}
+
+
 def widened_rows_timing(nu):
     """SURVEY.md section 8f rows, outside the timed region (N = 1 only): one CPD registration at the reference's
     default sizes on the spectral-coordinate-like synthetic problem of tools/cpd_bench.py, ICP and curvatures on one
@@ -493,6 +638,8 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rowpart", action="store_true", help="skip the 1M-vertex solve reported under secondary_metrics")
+    ap.add_argument("--no-dense", action="store_true", help="skip the KNN / k = 65 FP64 evidence reported under secondary_metrics")
+    ap.add_argument("--no-nonsym", action="store_true", help="skip the non-symmetric batch reported under secondary_metrics")
     a = ap.parse_args()
     return run_reference(a) if a.impl == "reference" else run_ours(a)
 

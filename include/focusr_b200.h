@@ -120,7 +120,9 @@ typedef struct focusr_eigs_options {
   int filter_min_blocks; /* resident CTAs per SM the b = 16 kernels are compiled for: 8 (default), 6 or 5 */
   int filter_pdl;        /* 2 (default): steps chained by programmatic dependent launch, constant streams prefetched
                             before the dependency wait; 1: the same, prefetch after the wait; 0: plain launches */
-  int reserved[11];
+  int nonsym_device;     /* 1 (default): the b x b general Rayleigh-Ritz step of non-symmetric adjacencies (open /
+                            non-manifold meshes) runs on the device, one CTA per mesh (b <= 64); 0: on the host */
+  int reserved[10];
 } focusr_eigs_options;
 void focusr_eigs_default_options(focusr_eigs_options* options);
 int focusr_eigs_block_size(int k, int n_k_needed, int k_buffer, int max_one_way, int max_zero_rows);

@@ -84,7 +84,7 @@ class EigsOptions(C.Structure):
     """``focusr_eigs_options`` (include/focusr_b200.h): per-call options of the eigensolver; no process-wide state."""
 
     _fields_ = [("mixed_precision", _i), ("filter_policy", _i), ("filter_prefetch", _i), ("filter_min_blocks", _i),
-                ("filter_pdl", _i), ("reserved", _i * 11)]
+                ("filter_pdl", _i), ("nonsym_device", _i), ("reserved", _i * 10)]
 
     def __init__(self, **kw):
         super().__init__()

@@ -297,6 +297,8 @@ int chfsi_solve(BE& be, const SolveParams& p, MeshResult* out) {
   std::vector<double> a_prev(M, -1.0), last_a(M, 0.5 * p.beta), last_alow(M, 0.0);
   std::vector<int> done(M, 0), n_low(M, B), flags(M), sel((size_t)M * B), n_out(M), last_kp(M, 1);
   std::vector<double> gh, wbuf, thbuf;
+  std::vector<int> rr_rc(M, 0);
+  bool rr_on_backend = false;
   if (!sym) {
     gh.resize((size_t)2 * M * B * B);
     wbuf.resize((size_t)M * B * B);
@@ -329,32 +331,37 @@ int chfsi_solve(BE& be, const SolveParams& p, MeshResult* out) {
     if (sym) {
       be.rr_sym();
     } else {
-      be.get_GH(gh.data(), gh.data() + (size_t)M * B * B);
-      // the meshes' small eigenproblems are independent: a small OpenMP team (8 threads at most: one process per GPU
-      // times the steps in flight must not oversubscribe the host) -- from 8 meshes up only: for a single pair the team
-      // start-up costs more than it saves (Focusr() 38 -> 79 ms measured)
-      std::vector<int> rr_rc(M, 0);
+      // The meshes' small general eigenproblems: on the backend when it can (CudaBackend: one CTA per mesh,
+      // nonsym_small.h, b <= 64 -- nothing leaves the device until the residuals do), else here on the host.
+      std::vector<double> cut(M);
+      for (int m = 0; m < M; ++m) cut[m] = a_prev[m] < 0.0 ? 0.5 * p.beta : 2.0 * a_prev[m];
+      rr_on_backend = be.rr_nonsym_device(cut.data());
+      if (!rr_on_backend) {
+        be.get_GH(gh.data(), gh.data() + (size_t)M * B * B);
+        // independent problems: a small OpenMP team (8 threads at most: one process per GPU times the steps in flight
+        // must not oversubscribe the host) -- from 8 meshes up only: for a single pair the team start-up costs more
+        // than it saves (Focusr() 38 -> 79 ms measured)
 #if defined(_OPENMP)
 #pragma omp parallel for schedule(dynamic) if (M >= 8) num_threads(8)
 #endif
-      for (int m = 0; m < M; ++m) {
-        const double cut = a_prev[m] < 0.0 ? 0.5 * p.beta : 2.0 * a_prev[m];
-        rr_rc[m] = rr_nonsym_host(gh.data() + (size_t)m * B * B, gh.data() + (size_t)(M + m) * B * B, B, cut,
-                                  wbuf.data() + (size_t)m * B * B, thbuf.data() + (size_t)m * B, &n_low[m]);
+        for (int m = 0; m < M; ++m)
+          rr_rc[m] = rr_nonsym_host(gh.data() + (size_t)m * B * B, gh.data() + (size_t)(M + m) * B * B, B, cut[m],
+                                    wbuf.data() + (size_t)m * B * B, thbuf.data() + (size_t)m * B, &n_low[m]);
+        be.set_W_theta(wbuf.data(), thbuf.data());
       }
-      for (int m = 0; m < M; ++m) {
-        const int r = rr_rc[m];
-        if (r < 0 && !done[m]) {
+    }
+    be.rotate_and_residual();
+    be.get_theta_res(theta.data(), res.data());
+    if (!sym) {
+      if (rr_on_backend) be.get_nonsym_info(rr_rc.data(), n_low.data());
+      for (int m = 0; m < M; ++m)
+        if (rr_rc[m] < 0 && !done[m]) {  // the QR iteration failed
           out[m].status = SOLVE_BREAKDOWN;
           done[m] = 1;
           ++n_done;
           rc = SOLVE_BREAKDOWN;
         }
-      }
-      be.set_W_theta(wbuf.data(), thbuf.data());
     }
-    be.rotate_and_residual();
-    be.get_theta_res(theta.data(), res.data());
 
     bool any_flag = false;
     for (int m = 0; m < M; ++m) {

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "chfsi_driver.hpp"
+#include "nonsym_small.h"
 #include "common.cuh"
 #include "nccl_dyn.h"
 #include "rowops.h"
@@ -338,6 +339,44 @@ k_rr_sym(const double* __restrict__ partial, int chunks_max, const int* __restri
   if (tid == 0) info[mesh] = rc;
 }
 
+// Non-symmetric adjacency (open / non-manifold meshes): the general b x b Rayleigh-Ritz step, one CTA per mesh, all in
+// shared memory (nonsym_small.h has the algorithm; 48 b^2 bytes + scratch, hence b <= 64).  The Cholesky factor is parked
+// in `g_save` (global) while its shared-memory space holds the back-substituted vectors.
+constexpr int RRN_THREADS = 128;
+static size_t rr_nonsym_smem_bytes(int B) {
+  return sizeof(double) * 2 * (size_t)B * B + sizeof(Cd) * 2 * (size_t)B * B + nonsym_small_scratch_bytes(B) +
+         sizeof(double) * RRN_THREADS;
+}
+__global__ void __launch_bounds__(RRN_THREADS)
+k_rr_nonsym(const double* __restrict__ partial, int chunks_max, const int* __restrict__ mesh_off, int B, int M,
+            const double* __restrict__ cut, double* __restrict__ g_save, double* __restrict__ w_out,
+            double* __restrict__ theta_out, int* __restrict__ info) {
+  extern __shared__ double sm[];
+  double* g = sm;
+  double* h = g + B * B;
+  Cd* Hc = reinterpret_cast<Cd*>(h + B * B);
+  Cd* Qc = Hc + B * B;
+  unsigned char* scratch = reinterpret_cast<unsigned char*>(Qc + B * B);
+  double* red = reinterpret_cast<double*>(scratch + nonsym_small_scratch_bytes(B));
+  const int mesh = blockIdx.x, tid = threadIdx.x;
+  const int nchunks = (mesh_off[mesh + 1] - mesh_off[mesh] + GRAM_ROWS - 1) / GRAM_ROWS;
+  const double* src = partial + (size_t)mesh * chunks_max * 2 * B * B;
+  for (int e = tid; e < B * B; e += RRN_THREADS) {
+    double sg = 0.0, sh = 0.0;
+    for (int c = 0; c < nchunks; ++c) {
+      sg += src[(size_t)c * 2 * B * B + e];
+      sh += src[(size_t)c * 2 * B * B + B * B + e];
+    }
+    g[e] = sg;
+    h[e] = sh;
+  }
+  __syncthreads();
+  BlockPar par{red};
+  const int rc = rr_nonsym_small(g, h, Hc, Qc, g_save + (size_t)mesh * B * B, B, cut[mesh], w_out + (size_t)mesh * B * B,
+                                 theta_out + (size_t)mesh * B, info + M + mesh, scratch, par);
+  if (tid == 0) info[mesh] = rc;
+}
+
 // Non-symmetric path: only the chunk reduction happens on the device; the host does the rest.
 __global__ void k_reduce_gh(const double* __restrict__ partial, int chunks_max,
                             const int* __restrict__ mesh_off, int B, double* __restrict__ g_out,
@@ -514,7 +553,7 @@ struct PinnedPool {
     return p;
   }
 };
-static thread_local PinnedPool g_pin_small, g_pin_tables;
+static thread_local PinnedPool g_pin_small, g_pin_tables, g_pin_cut;
 
 // Live profile of the dominant kernel (the Chebyshev SpMM step): CUDA events bracket every
 // filter() on the launching stream; the elapsed time is collected at the next synchronisation the
@@ -792,6 +831,7 @@ struct CudaBackend {
   DistCtx* dist = nullptr;  // row-partitioned multi-GPU solve (one mesh); null = everything is local
   bool mixed = true;        // fp32 filter passes allowed (focusr_eigs_options.mixed_precision)
   FilterTuning tune;        // kernel form of the fp32 filter steps
+  bool nonsym_device = true;  // non-symmetric Rayleigh-Ritz on the device (focusr_eigs_options.nonsym_device)
   SellF32 sell;             // SELL-64 fp32 copy of the matrix (tune.format == 0)
 
   int n_meshes() const { return M; }
@@ -1002,6 +1042,40 @@ struct CudaBackend {
     FB_COUNT_LAUNCH(1);
     check("rr_sym");
     return 0;
+  }
+  // non-symmetric Rayleigh-Ritz on the device (b <= 64); `cut` [M] from the driver.  W, theta stay on the device; the
+  // return codes and n_low come back with get_nonsym_info after the residuals.
+  bool rr_nonsym_device(const double* cut_host) {
+    if (B > 64 || !nonsym_device) return false;
+    const size_t smem = rr_nonsym_smem_bytes(B);
+    double* pin = (double*)g_pin_cut.get(sizeof(double) * (size_t)M);  // its own pool: the tables of the filter that is
+                                                                        // still running are staged in the other ones
+    if (!pin) {
+      fail(cudaErrorMemoryAllocation, "pinned staging (cut)");
+      return true;
+    }
+    memcpy(pin, cut_host, sizeof(double) * (size_t)M);
+    fail(cudaMemcpyAsync(corr_ab, pin, sizeof(double) * (size_t)M, cudaMemcpyHostToDevice, stream), "H2D cut");
+    if (smem > 48 * 1024)
+      fail(cudaFuncSetAttribute(k_rr_nonsym, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem opt-in (rr_nonsym)");
+    const double* src = dist ? dist->small : partial;
+    const int cm = dist ? 1 : chunks_max;
+    const int* offs = dist ? dist->fake_off : g.mesh_off;
+    k_rr_nonsym<<<M, RRN_THREADS, smem, stream>>>(src, cm, offs, B, M, corr_ab, G, W, theta, rr_info);
+    FB_COUNT_LAUNCH(1);
+    check("rr_nonsym");
+    return true;
+  }
+  void get_nonsym_info(int* rc_out, int* n_low_out) {
+    int* pin = (int*)g_pin_small.get(sizeof(int) * 2 * (size_t)M);
+    if (!pin) {
+      fail(cudaErrorMemoryAllocation, "pinned staging");
+      return;
+    }
+    fail(cudaMemcpyAsync(pin, rr_info, sizeof(int) * 2 * (size_t)M, cudaMemcpyDeviceToHost, stream), "D2H rr info");
+    fail(cudaStreamSynchronize(stream), "sync after rr info");
+    memcpy(rc_out, pin, sizeof(int) * (size_t)M);
+    memcpy(n_low_out, pin + M, sizeof(int) * (size_t)M);
   }
   void get_GH(double* gh, double* hh) {
     dim3 grid(div_up(B * B, 256), M);
@@ -1250,7 +1324,7 @@ static size_t eigs_ws_layout(int n_rows, int n_meshes, int max_mesh_rows, int B,
   int* flags = cv.take<int>((size_t)n_meshes);
   int* sel = cv.take<int>((size_t)n_meshes * B);
   int* n_out = cv.take<int>((size_t)n_meshes);
-  int* rr_info = cv.take<int>((size_t)n_meshes);
+  int* rr_info = cv.take<int>((size_t)2 * n_meshes);  // return code per mesh; n_low per mesh (non-symmetric path)
   int* off = cv.take<int>((size_t)n_meshes + 1);
   if (be) {
     be->X = X; be->Y = Y; be->Xn = Xn; be->partial = partial; be->partial_res = partial_res;
@@ -1343,6 +1417,7 @@ void focusr_eigs_default_options(focusr_eigs_options* o) {
   o->filter_prefetch = 1;
   o->filter_min_blocks = 8;
   o->filter_pdl = 2;
+  o->nonsym_device = 1;
   for (int& r : o->reserved) r = 0;
 }
 
@@ -1450,6 +1525,7 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
     be.g = SpmmGraph{row_ptr, cols, weights, degree, degree_inv, nullptr, M, 0};
     be.mixed = opt.mixed_precision != 0;
     be.tune = tune;
+    be.nonsym_device = opt.nonsym_device != 0;
     if (have_f32) {
       be.sell.entries = f32.entries;
       be.sell.slice_ptr = f32.slice_ptr;
@@ -1775,6 +1851,7 @@ int focusr_eigs_smallest_dist(const int* row_ptr, const int* cols_local, const d
   // fp32 filter passes: SELL copy of the local rows, remote columns encoded for the in-kernel peer gather.  P2P mode
   // only (the fp32 views live in the peer-shared blocks); the ncclSend/ncclRecv path keeps the fp64 steps.
   be.mixed = opt.mixed_precision != 0;
+  be.nonsym_device = opt.nonsym_device != 0;
   be.tune.policy = opt.filter_policy;
   be.tune.prefetch = opt.filter_prefetch;
   be.tune.min_blocks = opt.filter_min_blocks;

@@ -13,12 +13,25 @@
 #include "../../pyfocusr_b200/csrc/cpd_host.hpp"
 #include "../../pyfocusr_b200/csrc/chfsi_driver.hpp"
 #include "../../pyfocusr_b200/csrc/eigsort_decide.h"
+#include "../../pyfocusr_b200/csrc/nonsym_small.h"
 #include "../../pyfocusr_b200/csrc/rowops.h"
 
 namespace {
 
 double g_lowp_floor = 0.0;   // hostsim_set_lowp: SolveParams::lowp_floor of the next solves
 int g_last_lowp_degree = 0;  // lowp_degree of mesh 0 of the last solve
+int g_nonsym_small = 1;      // hostsim_set_nonsym_small: 1 = the device algorithm (nonsym_small.h, sequential Par), 0 = nonsym_host.hpp
+
+int rr_nonsym_small_host(const double* g, const double* h, int b, double cut, double* w, double* theta, int* n_low) {
+  std::vector<double> gh((size_t)2 * b * b), rs((size_t)b * b);
+  std::memcpy(gh.data(), g, sizeof(double) * b * b);
+  std::memcpy(gh.data() + (size_t)b * b, h, sizeof(double) * b * b);
+  std::vector<fb::Cd> hc((size_t)b * b), qc((size_t)b * b);
+  std::vector<unsigned char> scratch(fb::nonsym_small_scratch_bytes(b) + 16);
+  fb::SeqPar par;
+  return fb::rr_nonsym_small(gh.data(), gh.data() + (size_t)b * b, hc.data(), qc.data(), rs.data(), b, cut, w, theta, n_low,
+                             scratch.data(), par);
+}
 
 struct HostBackend {
   const int* rp;
@@ -114,6 +127,23 @@ struct HostBackend {
                                      rank.data(), rot.data(), pq.data(), B, par);
     }
     return worst;
+  }
+  // the device form of the non-symmetric Rayleigh-Ritz step (what CudaBackend runs in one CTA per mesh)
+  std::vector<int> ns_rc, ns_low;
+  bool rr_nonsym_device(const double* cut) {
+    if (!g_nonsym_small || B > 64) return false;
+    ns_rc.assign(M, 0);
+    ns_low.assign(M, 0);
+    for (int m = 0; m < M; ++m)
+      ns_rc[m] = rr_nonsym_small_host(&G[(size_t)m * B * B], &H[(size_t)m * B * B], B, cut[m], &W[(size_t)m * B * B],
+                                      &theta[(size_t)m * B], &ns_low[m]);
+    return true;
+  }
+  void get_nonsym_info(int* rc, int* n_low) {
+    for (int m = 0; m < M; ++m) {
+      rc[m] = ns_rc[m];
+      n_low[m] = ns_low[m];
+    }
   }
   void get_GH(double* g, double* h) {
     std::memcpy(g, G.data(), G.size() * sizeof(double));
@@ -305,6 +335,14 @@ int hostsim_eigs(const int* rp, const int* cols, const double* w, const double* 
 }
 
 void hostsim_set_lowp(double floor) { g_lowp_floor = floor; }
+void hostsim_set_nonsym_small(int on) { g_nonsym_small = on; }
+
+// the non-symmetric Rayleigh-Ritz step in its device form (nonsym_small.h) and in its host form (chfsi_driver.hpp)
+int hostsim_rr_nonsym(int device_form, const double* g, const double* h, int b, double cut, double* w, double* theta, int* n_low) {
+  if (device_form) return rr_nonsym_small_host(g, h, b, cut, w, theta, n_low);
+  std::vector<double> gg(g, g + (size_t)b * b), hh(h, h + (size_t)b * b);
+  return fb::rr_nonsym_host(gg.data(), hh.data(), b, cut, w, theta, n_low);
+}
 int hostsim_last_lowp_degree(void) { return g_last_lowp_degree; }
 
 int hostsim_rr_sym(double* g, double* h, double* w, double* theta, int b) {

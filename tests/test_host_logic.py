@@ -45,6 +45,42 @@ def test_eig_general_matches_numpy(hostsim, n):
     assert np.max(np.abs(a @ v - v * e[None, :])) <= 1e-11 * np.max(np.abs(ref))
 
 
+@pytest.mark.parametrize("b", [8, 16, 24, 48, 64])
+def test_rr_nonsym_device_form_matches_numpy_and_the_host_form(hostsim, b):
+    """csrc/nonsym_small.h (the algorithm one CTA per mesh runs on the B200, here with the sequential Par) against
+    numpy's eig of the same pencil and against csrc/nonsym_host.hpp: same low real Ritz values in the same order, Ritz
+    vectors that satisfy the projected problem, a full-rank basis."""
+    rng = np.random.RandomState(b)
+    n = 6 * b
+    x = rng.randn(n, b)
+    # a nearly diagonalisable operator with a few complex pairs, like the one-way entries of an open mesh produce
+    d = np.sort(rng.rand(n)) * 2.0
+    lop = np.diag(d)
+    for i in range(0, 6, 2):
+        lop[n - 2 - i, n - 1 - i], lop[n - 1 - i, n - 2 - i] = 0.3, -0.3
+    lop += 1e-3 * rng.randn(n, n)
+    g, h = x.T @ x, x.T @ (lop @ x)
+    outs = []
+    for form in (1, 0):
+        w, th, nl = np.zeros((b, b)), np.zeros(b), np.zeros(1, np.int32)
+        rc = hostsim.hostsim_rr_nonsym(form, np.ascontiguousarray(g), np.ascontiguousarray(h), b, 1.2, w, th, nl)
+        assert rc == 0
+        outs.append((w, th, int(nl[0])))
+    (w, th, nl), (w0, th0, nl0) = outs
+    ev = np.linalg.eigvals(np.linalg.solve(g, h))
+    real_low = np.sort(ev[(np.abs(ev.imag) <= 1e-8 * np.abs(ev)) & (ev.real <= 1.2)].real)
+    assert nl == nl0 == real_low.size and nl > 0
+    assert np.allclose(th[:nl], real_low, rtol=1e-9, atol=1e-12) and np.allclose(th[:nl], th0[:nl], rtol=1e-9, atol=1e-12)
+    for j in range(nl):   # H w = theta G w
+        r = h @ w[:, j] - th[j] * (g @ w[:, j])
+        assert np.linalg.norm(r) <= 1e-8 * np.linalg.norm(h @ w[:, j])
+        c = abs(w[:, j] @ g @ w0[:, j]) / np.sqrt((w[:, j] @ g @ w[:, j]) * (w0[:, j] @ g @ w0[:, j]))
+        assert abs(c - 1.0) <= 1e-8   # same Ritz vector as the host form, up to sign
+    assert np.linalg.matrix_rank(w) == b and np.linalg.cond(w) < 1e10
+    # the two forms span the same invariant subspaces pair by pair: compare the sorted real parts of all Ritz values
+    assert np.allclose(np.sort(th), np.sort(th0), rtol=1e-8, atol=1e-10)
+
+
 def test_edge_weight_matches_numpy(hostsim):
     rng = np.random.RandomState(0)
     for _ in range(200):

@@ -7,7 +7,7 @@ set -u
 mkdir -p gpurun_out
 what="${*:-tests bench launches full dense}"
 TAG=${TAG:-r2}
-SMALL="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-rowpart"
+SMALL="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-rowpart --no-nonsym --no-dense"
 # gpurun brings back at most 64 MiB: a report is exported to CSV on the box (raw counters per launch, and the source page
 # with per-line stall samples) and the .ncu-rep itself is dropped
 export_rep() {
