@@ -621,6 +621,19 @@ def widened_rows_timing(nu):
     t, s_ = ellipsoid_pair(0, nu)
     res["icp_100it_1000_landmarks"], _ = timed(lambda: _device.icp(t.points, t.tris, s_.points))
     res["curvatures_one_mesh"], _ = timed(lambda: _device.curvatures(t.points, t.tris))
+    # the 'hungarian' correspondence (focusr.py:340-349): N x N assignment on the GPU next to scipy's on one host core,
+    # on a geometric instance with long augmenting paths (4000 points of an ellipsoid matched to displaced copies)
+    from scipy.optimize import linear_sum_assignment
+    rng = np.random.RandomState(11)
+    p = rng.randn(4000, 3)
+    p = p / np.linalg.norm(p, axis=1)[:, None] * np.array([1.0, 0.8, 0.6])
+    q = p[rng.permutation(4000)] + 0.3 * rng.randn(4000, 3)
+    cost = _device.cdist(q, p)
+    res["hungarian_lsap_4000x4000"], (_, col) = timed(lambda: _device.linear_sum_assignment(cost))
+    t0 = time.perf_counter()
+    _, col_ref = linear_sum_assignment(cost.cpu().numpy())
+    res["hungarian_lsap_4000x4000_scipy_1core"] = (time.perf_counter() - t0) * 1e3
+    res["hungarian_lsap_equal_to_scipy"] = bool(np.array_equal(col, col_ref))
     return res
 
 

@@ -281,10 +281,19 @@ int focusr_knn(const double* refs, int ld_refs, const int* ref_off, int n_refs_t
                focusr_stream_t stream);
 
 /* The distance matrix of the 'hungarian' correspondence (focusr.py:340-349: scipy cdist(spectral_pts,
- * target_pts), euclidean): out [n_a][n_b] = |a_i - b_j|_2.  The assignment itself stays on the host in scipy's
- * linear_sum_assignment, exactly as the reference calls it. */
+ * target_pts), euclidean): out [n_a][n_b] = |a_i - b_j|_2. */
 int focusr_cdist(const double* a, int n_a, const double* b, int n_b, int dim, double* out,
                  focusr_stream_t stream);
+
+/* The assignment of the 'hungarian' correspondence (focusr.py:347: scipy.optimize.linear_sum_assignment): scipy's own
+ * algorithm (shortest augmenting paths, rectangular_lsap.cpp) with its scan order and tie rules, so the assignment is
+ * the one scipy returns also where the optimum is not unique; one 8-CTA thread-block cluster, column state in
+ * distributed shared memory (csrc/lsap.cu).  cost: device, row-major [n_rows][n_cols], finite, n_rows <= n_cols (pass
+ * the transpose otherwise), n_cols <= 51200.  col4row: device int32 [n_rows] = scipy's col_ind.  *status_host: 0, or
+ * -1 when no assignment exists (non-finite costs).  Synchronises `stream`. */
+size_t focusr_lsap_workspace_bytes(int n_rows);
+int focusr_lsap(const double* cost, int n_rows, int n_cols, int* col4row, int* status_host, void* workspace,
+                size_t workspace_bytes, focusr_stream_t stream);
 
 /* E3  get_weighted_final_node_locations (focusr.py:401-426) from the k=3 neighbours:
  * coincident neighbour -> its target point, else inverse-distance weighted mean of the three

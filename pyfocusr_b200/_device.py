@@ -259,6 +259,48 @@ def knn(refs, queries, k=1, ref_off=None, query_off=None, max_queries=None, max_
     return idx, dist
 
 
+def cdist(a, b):
+    """scipy.spatial.distance.cdist(a, b) (euclidean) on the device: [n_a][n_b] float64."""
+    torch = _torch()
+    a = torch.as_tensor(a, dtype=torch.float64, device="cuda").contiguous()
+    b = torch.as_tensor(b, dtype=torch.float64, device="cuda").contiguous()
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float64, device=a.device)
+    _lib.call("focusr_cdist", _lib.ptr(a), int(a.shape[0]), _lib.ptr(b), int(b.shape[0]), int(a.shape[1]),
+              _lib.ptr(out), _lib.stream_ptr())
+    return out
+
+
+def linear_sum_assignment(cost):
+    """scipy.optimize.linear_sum_assignment(cost) for a device matrix: (row_ind, col_ind) as numpy int64 arrays, the
+    assignment scipy itself returns (same algorithm, same tie rules; ``focusr_lsap``).  Raises ValueError for a matrix
+    without a finite assignment, as scipy does."""
+    import ctypes as C
+
+    torch = _torch()
+    cost = torch.as_tensor(cost, dtype=torch.float64, device="cuda")
+    if cost.ndim != 2:
+        raise ValueError("expected a matrix (2-D array), got a %d array" % cost.ndim)
+    nr, nc = int(cost.shape[0]), int(cost.shape[1])
+    if nr == 0 or nc == 0:
+        return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    transposed = nr > nc
+    m = (cost.t() if transposed else cost).contiguous()
+    rows, cols = int(m.shape[0]), int(m.shape[1])
+    col4row = torch.empty(rows, dtype=torch.int32, device=m.device)
+    ws_bytes = int(_lib.load().focusr_lsap_workspace_bytes(rows))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=m.device)
+    status = C.c_int(0)
+    _lib.call("focusr_lsap", _lib.ptr(m), rows, cols, _lib.ptr(col4row), C.addressof(status), _lib.ptr(ws), ws_bytes,
+              _lib.stream_ptr())
+    if status.value != 0:
+        raise ValueError("cost matrix is infeasible")
+    a = col4row.cpu().numpy().astype(np.int64)
+    if not transposed:
+        return np.arange(rows, dtype=np.int64), a
+    order = np.argsort(a, kind="stable")   # scipy: rows of the original matrix in ascending order
+    return a[order], order.astype(np.int64)
+
+
 def gather_rows(values, idx, idx_base=None):
     torch = _torch()
     n, c = int(idx.shape[0]), int(values.shape[1])

@@ -64,6 +64,8 @@ SIGNATURES = {
     "focusr_knn_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "focusr_knn": (_i, [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "focusr_cdist": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp]),
+    "focusr_lsap_workspace_bytes": (_sz, [_i]),
+    "focusr_lsap": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "focusr_weighted_positions": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "focusr_curvature_workspace_bytes": (_sz, [_i, _i]),
     "focusr_curvatures": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

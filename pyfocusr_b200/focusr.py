@@ -268,17 +268,11 @@ class Focusr(object):
 
     # ------------------------------------------------------------------ focusr.py:340-366
     def get_hungarian_correspondence(self, target_pts, spectral_pts):
-        """focusr.py:340-349: the N x N distance matrix on the GPU, then scipy's linear_sum_assignment on the host
-        exactly as the reference calls it (an O(N^3) third-party solve; minutes at 15k vertices there too)."""
-        from scipy.optimize import linear_sum_assignment
-
-        torch = _lib.require_cuda()
-        a = torch.from_numpy(np.ascontiguousarray(spectral_pts, dtype=np.float64)).cuda()
-        b = torch.from_numpy(np.ascontiguousarray(target_pts, dtype=np.float64)).cuda()
-        dist = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float64, device=a.device)
-        _lib.call("focusr_cdist", _lib.ptr(a), int(a.shape[0]), _lib.ptr(b), int(b.shape[0]), int(a.shape[1]),
-                  _lib.ptr(dist), _lib.stream_ptr())
-        _, target_idx = linear_sum_assignment(dist.cpu().numpy())
+        """focusr.py:340-349: the N x N distance matrix and its assignment, both on the GPU -- ``focusr_cdist`` and
+        ``focusr_lsap``, scipy's own shortest-augmenting-path algorithm with its scan order and tie rules in one
+        thread-block cluster, so ``target_idx`` is what ``scipy.optimize.linear_sum_assignment`` returns."""
+        dist = _device.cdist(spectral_pts, target_pts)
+        _, target_idx = _device.linear_sum_assignment(dist)
         self.corresponding_target_idx_for_each_source_pt = target_idx
 
     def get_kd_correspondence(self, target_pts, spectral_pts):

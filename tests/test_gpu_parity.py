@@ -708,8 +708,38 @@ def test_error_behaviour_and_degenerate_inputs(torch):
         _device.knn(refs, qs, k=9)
 
 
+def test_device_lsap_equals_scipy(torch):
+    """focusr_lsap (csrc/lsap.cu: scipy's shortest-augmenting-path algorithm in one thread-block cluster) against
+    scipy.optimize.linear_sum_assignment: the same assignment, also on matrices full of ties (integer costs, duplicated
+    points), rectangular both ways, tiny, and a 2500-point geometric instance with long augmenting paths."""
+    from scipy.optimize import linear_sum_assignment
+    from scipy.spatial.distance import cdist
+
+    from pyfocusr_b200 import _device
+
+    rng = np.random.RandomState(3)
+    cases = []
+    for n, m in ((1, 1), (2, 2), (9, 9), (40, 47), (47, 40), (300, 300), (257, 400), (1030, 1030)):
+        cases.append(rng.rand(n, m))
+        cases.append(rng.randint(0, 4, (n, m)).astype(np.float64))
+    pts = rng.randint(0, 6, (600, 2)).astype(np.float64)              # duplicated points: many equal distances
+    cases.append(cdist(pts[:500], pts))
+    p = rng.randn(2500, 3)
+    p /= np.linalg.norm(p, axis=1)[:, None]
+    cases.append(cdist(p[rng.permutation(2500)] + 0.3 * rng.randn(2500, 3), p))
+    for c in cases:
+        row, col = _device.linear_sum_assignment(torch.from_numpy(np.ascontiguousarray(c)).cuda())
+        r_ref, c_ref = linear_sum_assignment(c)
+        assert np.array_equal(row, r_ref) and np.array_equal(col, c_ref), c.shape
+    bad = np.ones((3, 3))
+    bad[0, :] = np.inf
+    with pytest.raises(ValueError):
+        _device.linear_sum_assignment(torch.from_numpy(bad).cuda())
+
+
 def test_hungarian_correspondence(torch, synth):
-    """focusr.py:340-349: cdist on the GPU bit-equal to scipy's, assignment by the same scipy call as the reference."""
+    """focusr.py:340-349: cdist on the GPU bit-equal to scipy's; the assignment (focusr_lsap on the GPU) equal to the scipy
+    call the reference makes."""
     import pyfocusr_b200 as pyfocusr
     from scipy.optimize import linear_sum_assignment
     from scipy.spatial.distance import cdist

@@ -19,6 +19,10 @@ export_rep() {
 }
 has() { case " $what " in *" $1 "*) return 0;; esac; return 1; }
 
+if has lsap; then   # new cluster kernel: on its own, under a short limit, before anything else relies on the GPU
+  timeout 180 python -m pytest tests/test_gpu_parity.py -x -q -k "lsap or hungarian" > gpurun_out/${TAG}_lsap.log 2>&1
+  echo "lsap tests exit $?"; tail -5 gpurun_out/${TAG}_lsap.log
+fi
 if has tests; then
   timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_gputest.log 2>&1
   echo "gpu tests exit $?"; tail -3 gpurun_out/${TAG}_gputest.log

@@ -19,6 +19,25 @@ for tag, (tn, sn), kw in (("configs[0] 15k pair, defaults", ("target_mesh_15k", 
         t1 = time.perf_counter()
         f.align_maps()
         torch.cuda.synchronize(); t2 = time.perf_counter()
+    # where the constructor's time goes (one more run, device synchronised at every boundary)
+    from pyfocusr_b200.graph import Graph
+    stages, orig = [], Graph.get_graph_spectrum
+    def timed_spectrum(self, *a, **k):
+        torch.cuda.synchronize(); s0 = time.perf_counter()
+        out = orig(self, *a, **k)
+        torch.cuda.synchronize(); stages.append((time.perf_counter() - s0) * 1e3)
+        return out
+    Graph.get_graph_spectrum = timed_spectrum
+    np.random.seed(0)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    f = pyfocusr.Focusr(mt, ms, icp_register_first=False, list_features_to_calc=[], registration="identity", **kw)
+    torch.cuda.synchronize(); t1 = time.perf_counter()
+    Graph.get_graph_spectrum = orig
+    print("   constructor %.1f ms, of which Laplacian + eigensolve per graph: %s ms; eigensolver reports: %s" % (
+        (t1 - t0) * 1e3, ", ".join("%.1f" % v for v in stages),
+        [getattr(g, "eigs_info", None) and {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in g.eigs_info.items()
+                                             if k in ("outer_iterations", "filter_degree", "block_size", "k_final")}
+         for g in (f.graph_target, f.graph_source)]), flush=True)
     ns = kw.get("n_spectral_features", 3)
     np.random.seed(0)
     t3 = time.perf_counter()
