@@ -60,6 +60,22 @@ if has dense; then
     export_rep gpurun_out/${TAG}_full_dense
   fi
 fi
+if has ab; then
+  timeout 600 python tools/kernel_ab.py > gpurun_out/${TAG}_kernel_ab.log 2>&1
+  echo "kernel_ab exit $?"; tail -8 gpurun_out/${TAG}_kernel_ab.log
+fi
+if has knnncu; then
+  timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:k_gram_wide|k_pk_search<.int.3" -c 10 \
+      -f -o gpurun_out/${TAG}_full_gramknn python tools/dense_evidence.py --no-micro --k65-only > gpurun_out/${TAG}_ncu_full_gramknn.log 2>&1
+  echo "gram/knn ncu exit $?"
+  export_rep gpurun_out/${TAG}_full_gramknn
+fi
+if has latlist; then
+  timeout 300 python tools/pair_latency.py --no-oracle > gpurun_out/${TAG}_pair_latency_plain.log 2>&1 &&
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 12000 --csv --log-file gpurun_out/${TAG}_launches_pair.csv \
+      python tools/pair_latency.py --no-oracle > gpurun_out/${TAG}_ncu_pair.log 2>&1
+  echo "pair launch list exit $?"
+fi
 if has latency; then
   timeout 300 python tools/pair_latency.py > gpurun_out/${TAG}_pair_latency.log 2>&1
   echo "latency exit $?"; cat gpurun_out/${TAG}_pair_latency.log
