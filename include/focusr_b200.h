@@ -76,13 +76,6 @@ int focusr_mean_filter(const int* row_ptr, const int* cols, const double* weight
                        const double* degree, int row_begin, int row_end, const double* values_in,
                        double* values_out, int n_cols, int iterations, void* workspace,
                        size_t workspace_bytes, focusr_stream_t stream);
-/* The same call with the kernel form chosen by the caller (A/B tooling, tools/kernel_ab.py): 0 = a thread walks its row
- * entry by entry, 1 = all of a row's columns, weights and iterate rows are loaded before the arithmetic (what
- * focusr_mean_filter runs).  Identical results, bit for bit. */
-int focusr_mean_filter_form(int form, const int* row_ptr, const int* cols, const double* weights,
-                            const double* degree, int row_begin, int row_end, const double* values_in,
-                            double* values_out, int n_cols, int iterations, void* workspace,
-                            size_t workspace_bytes, focusr_stream_t stream);
 
 /* out[i][:] = in[idx[i]][:]  (focusr.py:387 `smoothed_target_coords[corresponding_idx, :]`;
  * focusr.py:429-431 nearest-neighbour positions).  `idx_base[i]` (nullable) is added to idx[i]. */

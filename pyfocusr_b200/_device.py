@@ -208,10 +208,9 @@ class DeviceGraph:
         return out
 
     # --- K5 -----------------------------------------------------------------------------------
-    def mean_filter(self, values, iterations, row_begin=0, row_end=None, form=None):
+    def mean_filter(self, values, iterations, row_begin=0, row_end=None):
         """values: device [n_points][c]; rows [row_begin, row_end) must be whole meshes (rows outside are ignored).
-        Returns a new tensor.  One launch per pass, chained by programmatic dependent launch.  ``form`` (A/B tooling
-        only): 0 = the serial row walk, 1 = loads first; default = the library's choice.  Same bits either way."""
+        Returns a new tensor.  One launch per pass, chained by programmatic dependent launch."""
         torch = _torch()
         lib = _lib.load()
         row_end = self.n_points if row_end is None else row_end
@@ -223,12 +222,9 @@ class DeviceGraph:
             raise ValueError("mean_filter: the row range must cover whole meshes")
         ws_bytes = int(lib.focusr_mean_filter_workspace_bytes(int(row_end - row_begin), c))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
-        args = (_lib.ptr(self.row_ptr), _lib.ptr(self.cols), _lib.ptr(self.weights), _lib.ptr(self.degree), int(row_begin),
-                int(row_end), _lib.ptr(values), _lib.ptr(out), c, int(iterations), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
-        if form is None:
-            _lib.call("focusr_mean_filter", *args)
-        else:
-            _lib.call("focusr_mean_filter_form", int(form), *args)
+        _lib.call("focusr_mean_filter", _lib.ptr(self.row_ptr), _lib.ptr(self.cols), _lib.ptr(self.weights),
+                  _lib.ptr(self.degree), int(row_begin), int(row_end), _lib.ptr(values), _lib.ptr(out),
+                  c, int(iterations), _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
         return out
 
 

@@ -29,7 +29,6 @@ SIGNATURES = {
     "focusr_laplacian_csr": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "focusr_mean_filter_workspace_bytes": (_sz, [_i, _i]),
     "focusr_mean_filter": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _sz, _vp]),
-    "focusr_mean_filter_form": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _sz, _vp]),
     "focusr_gather_rows": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "focusr_eigs_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "focusr_sell_entries_cap": (C.c_longlong, [_vp, _vp, _i]),

@@ -35,6 +35,7 @@ FB_HD Cd cd_conj(Cd a) { return cd_make(a.re, -a.im); }
 FB_HD Cd cd_neg(Cd a) { return cd_make(-a.re, -a.im); }
 FB_HD double cd_norm(Cd a) { return a.re * a.re + a.im * a.im; }
 FB_HD double cd_abs(Cd a) { return hypot(a.re, a.im); }
+FB_HD double cd_abs1(Cd a) { return fabs(a.re) + fabs(a.im); }  // LAPACK's CABS1: the cheap magnitude of the deflation test
 FB_HD Cd cd_div(Cd a, Cd b) {  // Smith's algorithm
   if (fabs(b.re) >= fabs(b.im)) {
     const double r = b.im / b.re, d = b.re + b.im * r;
@@ -57,8 +58,9 @@ FB_HD size_t nonsym_small_scratch_bytes(int b) {
 
 // Complex Schur form of the complex matrix H (n x n, row-major): H <- T upper triangular, Q <- the unitary factor.
 // v, cs, sn: n complex of scratch each.  Returns the number of eigenvalues deflated by force (0 = converged).
+// `small` : n ints of scratch (deflation flags).
 template <class Par>
-FB_HD int schur_complex(Cd* H, Cd* Q, int n, Cd* v, Cd* cs, Cd* sn, double* hnorm_out, const Par& par) {
+FB_HD int schur_complex(Cd* H, Cd* Q, int n, Cd* v, Cd* cs, Cd* sn, int* small_sub, double* hnorm_out, const Par& par) {
 #define FB_H(i, j) H[(i) * n + (j)]
   par.for_n(n * n, [&](int e) { Q[e] = cd_make((e / n == e % n) ? 1.0 : 0.0, 0.0); });
   par.sync();
@@ -116,13 +118,17 @@ FB_HD int schur_complex(Cd* H, Cd* Q, int n, Cd* v, Cd* cs, Cd* sn, double* hnor
   int failed = 0, ihi = n - 1, iter = 0;
   while (ihi > 0) {
     par.sync();
-    int l = ihi;
-    while (l > 0) {
-      double s = cd_abs(FB_H(l - 1, l - 1)) + cd_abs(FB_H(l, l));
+    // deflation test of every subdiagonal entry of the active window at once (zlahqr's criterion with CABS1: a hypot
+    // per entry and thread, scanned serially, was most of the kernel's time), then the scan over the flags
+    par.for_n(ihi, [&](int t) {
+      const int l2 = t + 1;
+      double s = cd_abs1(FB_H(l2 - 1, l2 - 1)) + cd_abs1(FB_H(l2, l2));
       if (s == 0.0) s = hnorm;
-      if (cd_abs(FB_H(l, l - 1)) <= eps * s) break;
-      --l;
-    }
+      small_sub[l2] = cd_abs1(FB_H(l2, l2 - 1)) <= eps * s;
+    });
+    par.sync();
+    int l = ihi;
+    while (l > 0 && !small_sub[l]) --l;
     bool force = false;
     if (l != ihi && ++iter > 60) {  // give up on this eigenvalue, deflate by force
       ++failed;
@@ -158,11 +164,13 @@ FB_HD int schur_complex(Cd* H, Cd* Q, int n, Cd* v, Cd* cs, Cd* sn, double* hnor
     // (r, 0) analytically and is written after the sweep, so nobody writes what the others are still reading.
     for (int k = l; k < ihi; ++k) {
       const Cd x = FB_H(k, k), y = FB_H(k + 1, k);
-      const double r = sqrt(cd_norm(x) + cd_norm(y));
+      const double r2 = cd_norm(x) + cd_norm(y);
+      const double r = sqrt(r2);
       Cd c = cd_make(1.0, 0.0), s = cd_make(0.0, 0.0);
       if (r > 0.0) {
-        c = cd_scale(x, 1.0 / r);
-        s = cd_scale(y, 1.0 / r);
+        const double rinv = 1.0 / r;
+        c = cd_scale(x, rinv);
+        s = cd_scale(y, rinv);
       }
       if (par.lane() == 0) {
         cs[k] = c;
@@ -251,7 +259,7 @@ FB_HD int rr_nonsym_small(double* g, double* h, Cd* Hc, Cd* Qc, double* r_save, 
   });
   par.sync();
   double hnorm = 1.0;
-  const int failed = schur_complex(Hc, Qc, n, v, cs, sn, &hnorm, par);
+  const int failed = schur_complex(Hc, Qc, n, v, cs, sn, is_real, &hnorm, par);
   if (failed != 0) return -1;
   // --- eigenvectors of the triangular factor (a thread owns an eigenvalue; vector k lives in column k of Y)
   Cd* Y = reinterpret_cast<Cd*>(g);

@@ -26,7 +26,11 @@
 //     against 17.8 ms for 300 passes over 128 meshes and removed: the pass is bound by its 6.4-wave launches, not by
 //     the row walk (programmatic dependent launch: 17.8 -> 17.0 ms).  Marking the matrix stream evict_first in L2, which
 //     pays in the filter steps, costs here (18.3 -> 20.0 ms): the 140 MB matrix of 128 targets is partly L2-resident
-//     from one pass to the next.
+//     from one pass to the next.  ncu at bench size (profiles/r2_summary.md): DRAM 49% busy, L1 61%, 65% of the warp
+//     slots filled (40 registers), no pipe saturated, 0.95x of the algorithmic bytes moved.  A form that loads all
+//     columns, weights and iterate rows of a row before its arithmetic (rows <= 8 entries; 80 registers, 3 CTAs per SM)
+//     was measured at 21.1 ms against 17.15 ms for the serial walk (gpurun_out/r2d_kernel_ab.log) and removed: fewer
+//     resident threads cost more than the longer load batches of each thread bring.
 #include <vector>
 
 #include "common.cuh"
@@ -971,108 +975,6 @@ k_mean_filter(const int* __restrict__ row_ptr, const int* __restrict__ cols, con
     if (k < nc) o[k] = acc[k];
 }
 
-// The same pass with the memory-level parallelism spelled out.  ncu of k_mean_filter at bench size (profiles/r2_summary.md):
-// DRAM 49% busy, L1 61%, 65% of the warp slots filled, no pipe saturated, stalls on the three dependent loads of every
-// entry (row_ptr -> column -> iterate row) -- latency-bound: a CTA lives as long as ~7 such chains one after the other.
-// Here a thread first loads ALL columns and weights of its row (rows of up to 8 entries: every mesh vertex of valence
-// <= 8; longer rows take the serial walk), then gathers the iterate rows of four entries at a time, and only then does
-// the arithmetic -- in exactly the order of the serial walk (stored order descending, diagonal spliced in at its sorted
-// position, multiply then add), so the result is the same bit for bit.
-template <int C>
-__global__ void __launch_bounds__(256, 3)
-k_mean_filter_mlp(const int* __restrict__ row_ptr, const int* __restrict__ cols, const double* __restrict__ weights,
-                  const double* __restrict__ degree, int row_begin, int row_end, const double* __restrict__ x,
-                  double* __restrict__ out) {
-  const int i = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
-  {
-    const int c0 = row_begin + blockIdx.x * blockDim.x, c1 = min(row_end, c0 + (int)blockDim.x);
-    const int q0 = row_ptr[c0], q1 = row_ptr[c1];
-    for (int q = q0 + 32 * (int)threadIdx.x; q < q1; q += 32 * (int)blockDim.x) prefetch_l2_line(cols + q);
-    for (int q = q0 + 16 * (int)threadIdx.x; q < q1; q += 16 * (int)blockDim.x) prefetch_l2_line(weights + q);
-  }
-  pdl_wait();
-  pdl_launch_dependents();
-  if (i >= row_end) return;
-  const int p0 = row_ptr[i], p1 = row_ptr[i + 1];
-  const int len = p1 - p0;
-  const double dsm = FB_DIV(1.0, FB_ADD(1.0, degree[i]));
-  double acc[C];
-#pragma unroll
-  for (int k = 0; k < C; ++k) acc[k] = 0.0;
-  const double* xi = x + (size_t)i * C;
-  bool diag_done = false;
-  if (len <= 8) {
-    int jj[8];
-    double ww[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const bool ok = e < len;
-      jj[e] = ok ? __ldg(cols + (p1 - 1 - e)) : i;
-      ww[e] = ok ? __ldg(weights + (p1 - 1 - e)) : 0.0;
-    }
-    double xs[C];
-#pragma unroll
-    for (int k = 0; k < C; ++k) xs[k] = xi[k];
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      double xv[4][C];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const double* xj = x + (size_t)jj[4 * half + e] * C;
-#pragma unroll
-        for (int k = 0; k < C; ++k) xv[e][k] = (4 * half + e < len) ? xj[k] : 0.0;
-      }
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (4 * half + e < len) {
-          const int j = jj[4 * half + e];
-          if (!diag_done && j < i) {
-#pragma unroll
-            for (int k = 0; k < C; ++k) acc[k] = FB_ADD(acc[k], FB_MUL(dsm, xs[k]));
-            diag_done = true;
-          }
-          double val;
-          if (j == i) {
-            val = FB_MUL(dsm, FB_ADD(ww[4 * half + e], 1.0));
-            diag_done = true;
-          } else {
-            val = FB_MUL(dsm, ww[4 * half + e]);
-          }
-#pragma unroll
-          for (int k = 0; k < C; ++k) acc[k] = FB_ADD(acc[k], FB_MUL(val, xv[e][k]));
-        }
-      }
-    }
-  } else {
-    for (int p = p1 - 1; p >= p0; --p) {
-      const int j = cols[p];
-      const double wp = weights[p];
-      if (!diag_done && j < i) {
-#pragma unroll
-        for (int k = 0; k < C; ++k) acc[k] = FB_ADD(acc[k], FB_MUL(dsm, xi[k]));
-        diag_done = true;
-      }
-      double val;
-      if (j == i) {
-        val = FB_MUL(dsm, FB_ADD(wp, 1.0));
-        diag_done = true;
-      } else {
-        val = FB_MUL(dsm, wp);
-      }
-      const double* xj = x + (size_t)j * C;
-#pragma unroll
-      for (int k = 0; k < C; ++k) acc[k] = FB_ADD(acc[k], FB_MUL(val, xj[k]));
-    }
-  }
-  if (!diag_done) {
-#pragma unroll
-    for (int k = 0; k < C; ++k) acc[k] = FB_ADD(acc[k], FB_MUL(dsm, xi[k]));
-  }
-  double* o = out + (size_t)i * C;
-#pragma unroll
-  for (int k = 0; k < C; ++k) o[k] = acc[k];
-}
-
 __global__ void k_copy_rows(const double* __restrict__ in, double* __restrict__ out, long long begin, long long end) {
   const long long t = begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < end) out[t] = in[t];
@@ -1104,28 +1006,9 @@ long long focusr_sell_entries_cap(const int* mesh_point_off_host, const int* mes
 
 size_t focusr_mean_filter_workspace_bytes(int n_rows, int n_cols) { return smooth_layout(n_rows, n_cols, nullptr).bytes; }
 
-static int mean_filter_impl(int form, const int* row_ptr, const int* cols, const double* weights, const double* degree,
-                            int row_begin, int row_end, const double* values_in, double* values_out, int n_cols,
-                            int iterations, void* workspace, size_t workspace_bytes, focusr_stream_t stream_);
-
 int focusr_mean_filter(const int* row_ptr, const int* cols, const double* weights, const double* degree,
                        int row_begin, int row_end, const double* values_in, double* values_out, int n_cols,
                        int iterations, void* workspace, size_t workspace_bytes, focusr_stream_t stream_) {
-  return mean_filter_impl(1, row_ptr, cols, weights, degree, row_begin, row_end, values_in, values_out, n_cols, iterations,
-                          workspace, workspace_bytes, stream_);
-}
-
-// A/B handle of tools/kernel_ab.py: form 0 = the serial row walk, 1 = loads first (the default of focusr_mean_filter)
-int focusr_mean_filter_form(int form, const int* row_ptr, const int* cols, const double* weights, const double* degree,
-                            int row_begin, int row_end, const double* values_in, double* values_out, int n_cols,
-                            int iterations, void* workspace, size_t workspace_bytes, focusr_stream_t stream_) {
-  return mean_filter_impl(form, row_ptr, cols, weights, degree, row_begin, row_end, values_in, values_out, n_cols,
-                          iterations, workspace, workspace_bytes, stream_);
-}
-
-static int mean_filter_impl(int form, const int* row_ptr, const int* cols, const double* weights, const double* degree,
-                            int row_begin, int row_end, const double* values_in, double* values_out, int n_cols,
-                            int iterations, void* workspace, size_t workspace_bytes, focusr_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   FB_REQUIRE(row_end > row_begin && n_cols >= 1 && n_cols <= 8 && iterations >= 0,
              "mean_filter: need rows, 1 <= n_cols <= 8, iterations >= 0");
@@ -1150,11 +1033,7 @@ static int mean_filter_impl(int form, const int* row_ptr, const int* cols, const
   for (int it = 0; it < iterations; ++it) {
     double* dst = it == iterations - 1 ? values_out : ((it & 1) ? pb : pa);
     cudaError_t e;
-    if (n_cols == 3 && form == 1)
-      e = launch_pdl(k_mean_filter_mlp<3>, grid, block, stream, row_ptr, cols, weights, degree, row_begin, row_end, src, dst);
-    else if (n_cols == 1 && form == 1)
-      e = launch_pdl(k_mean_filter_mlp<1>, grid, block, stream, row_ptr, cols, weights, degree, row_begin, row_end, src, dst);
-    else if (n_cols == 3)
+    if (n_cols == 3)
       e = launch_pdl(k_mean_filter<3>, grid, block, stream, row_ptr, cols, weights, degree, row_begin, row_end, src, dst, 3);
     else if (n_cols == 1)
       e = launch_pdl(k_mean_filter<1>, grid, block, stream, row_ptr, cols, weights, degree, row_begin, row_end, src, dst, 1);

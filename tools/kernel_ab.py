@@ -79,19 +79,19 @@ def main():
     # --- smoothing: 300 passes over the targets
     nt = int(off[n_pairs])
     smooth_bytes = n_pairs * 300 * (12.0 * nnz + 60.0 * n)
-    for form in (0, 1, 0, 1):
+    for _rep in range(1):
         best = 1e9
         for _ in range(3):
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            out = g.mean_filter(g.points, 300, 0, nt, form=form)
+            out = g.mean_filter(g.points, 300, 0, nt)
             e1.record()
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1))
         gbs = smooth_bytes / best / 1e6
-        print("smoothing form %d (%s): %.2f ms for 300 passes over %d meshes  %.0f GB/s (%.1f%%)  sha %s" % (
-            form, "loads first" if form else "serial row walk", best, n_pairs, gbs, gbs / peak * 100, sha(out[:nt])), flush=True)
+        print("smoothing: %.2f ms for 300 passes over %d meshes  %.0f GB/s (%.1f%%)  sha %s" % (
+            best, n_pairs, gbs, gbs / peak * 100, sha(out[:nt])), flush=True)
 
 
 if __name__ == "__main__":
