@@ -39,12 +39,12 @@ k_spmm(const int* __restrict__ row_ptr, const int* __restrict__ cols, const doub
        const double* __restrict__ degree, const double* __restrict__ degree_inv,
        const int* __restrict__ mesh_off, const double* __restrict__ y, const double* __restrict__ x_prev,
        double* __restrict__ out, const double* __restrict__ alpha, const double* __restrict__ gamma,
-       const double* __restrict__ center, int step, int n_steps) {
+       const double* __restrict__ center, int step, int n_steps, int rows_per_block) {
   constexpr int VPT = B / (2 * TPR);
   static_assert(VPT * 2 * TPR == B, "block size must be a multiple of 2*TPR");
   const int mesh = blockIdx.y;
-  const int r0 = mesh_off[mesh] + blockIdx.x * SPMM_ROWS_PER_BLOCK;
-  const int r1 = min(mesh_off[mesh + 1], r0 + SPMM_ROWS_PER_BLOCK);
+  const int r0 = mesh_off[mesh] + blockIdx.x * rows_per_block;
+  const int r1 = min(mesh_off[mesh + 1], r0 + rows_per_block);
   if (r0 >= r1) return;
   double al = 1.0, ga = 0.0, cc = 0.0;
   if (MODE == 0) {
@@ -115,16 +115,21 @@ template <int B, int TPR>
 static int launch_spmm_b(int mode, const SpmmGraph& g, const double* y, const double* x_prev, double* out,
                          const double* alpha, const double* gamma, const double* center, int step,
                          int n_steps, cudaStream_t stream) {
-  dim3 grid(div_up(g.max_mesh_rows, SPMM_ROWS_PER_BLOCK), g.n_meshes);
+  // A CTA normally walks 256 rows in passes of 256 / TPR; a single mesh (the drop-in Focusr(target, source) call: 15k
+  // rows = 60 such CTAs on 148 SMs, 20 us per step of 16 MB) gets one pass per CTA instead, so that the whole GPU works
+  // on the step.  Same arithmetic per row either way.
+  int rpb = SPMM_ROWS_PER_BLOCK;
+  if ((long long)div_up(g.max_mesh_rows, rpb) * g.n_meshes < 2 * 148) rpb = SPMM_THREADS / TPR;
+  dim3 grid(div_up(g.max_mesh_rows, rpb), g.n_meshes);
   if (mode == 0)
     k_spmm<B, TPR, 0><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv,
-                                                         g.mesh_off, y, x_prev, out, alpha, gamma, center, step, n_steps);
+                                                         g.mesh_off, y, x_prev, out, alpha, gamma, center, step, n_steps, rpb);
   else if (mode == 1)
     k_spmm<B, TPR, 1><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv,
-                                                         g.mesh_off, y, x_prev, out, alpha, gamma, center, step, n_steps);
+                                                         g.mesh_off, y, x_prev, out, alpha, gamma, center, step, n_steps, rpb);
   else
     k_spmm<B, TPR, 2><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv,
-                                                         g.mesh_off, y, x_prev, out, alpha, gamma, center, step, n_steps);
+                                                         g.mesh_off, y, x_prev, out, alpha, gamma, center, step, n_steps, rpb);
   FB_COUNT_LAUNCH(1);
   return FB_OK;
 }
