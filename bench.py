@@ -570,8 +570,20 @@ def nonsym_batch_leg(n_pairs=32, reps=2):
         best = ms if best is None else min(best, ms)
     info = out["eigs_info"]
     ok = bool(np.all(info["status"] == 0))
+    # the same batch with every filter pass in fp64 (what the fp32 forms buy on the non-symmetric path)
+    sb.eigs_options = dict(mixed_precision=0)
+    sb.run(pts_d, tris_d, off, n_pairs)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out64 = sb.run(pts_d, tris_d, off, n_pairs)
+    e1.record()
+    torch.cuda.synchronize()
+    ms64 = e0.elapsed_time(e1)
     return {"config": "configs[0] as a batch: %d jittered copies of the shipped 15k pair (non-symmetric adjacency)" % n_pairs,
             "pairs_per_s": n_pairs / (best / 1e3), "ms_per_batch": best, "block": int(info["block_size"]),
+            "fp32_filter_degree": int(info["fp32_filter_degree"].max()),
+            "pairs_per_s_fp64_only": n_pairs / (ms64 / 1e3), "filter_degree_fp64_only": int(out64["eigs_info"]["filter_degree"].max()),
             "all_converged": ok, "max_residual": float(info["max_residual"].max()),
             "k_final": [int(info["k_final"][0]), int(info["k_final"][n_pairs])],
             "pairs_found": [int(info["n_found"][0]), int(info["n_found"][n_pairs])],

@@ -64,7 +64,8 @@ struct SolveParams {
   int probe_degree;  // > 0: tighten beta per mesh with a top-of-spectrum probe of this many filter steps
                      // (symmetric batches only); 0: filter up to `beta` as given
   double land;       // the sized pass aims at land * tol
-  double lowp_floor; // > 0: fp32 filter passes are allowed (symmetric batches on a backend that offers them); a pass on
+  double lowp_floor; // > 0: fp32 filter passes are allowed (on a backend that offers them; symmetric and non-symmetric
+                     // adjacencies alike: the shipped open meshes converge in the same number of steps); a pass on
                      // fp32 blocks must be predicted to leave every residual above this value.  0: fp64 only
   double lowp_aim;   // residual a sized plain-fp32 pass aims at (>= lowp_floor), from where the fp32 correction
                      // form can reach the tolerance
@@ -315,7 +316,9 @@ int chfsi_solve(BE& be, const SolveParams& p, MeshResult* out) {
     out[m].lowp_degree = 0;
   }
   std::vector<double> alpha, gamma, center(M), beta_m(M, p.beta);
-  const bool lowp_on = sym && p.lowp_floor > 0.0 && be.lowp_available();
+  // (non-symmetric runs take the fp32 forms too: the correction form is an algebraic identity for any (x, theta), columns
+  // whose Ritz value lies above the filter edge -- the carried complex pairs among them -- are normalised at the edge)
+  const bool lowp_on = p.lowp_floor > 0.0 && be.lowp_available();
   if (sym && p.probe_degree > 0) {
     probe_upper_bound(be, p, beta_m.data());
     if (lowp_on)

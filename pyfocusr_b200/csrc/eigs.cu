@@ -1493,12 +1493,10 @@ int focusr_eigs_smallest(const int* row_ptr, const int* cols, const double* weig
   tune.min_blocks = opt.filter_min_blocks;
   tune.pdl = opt.filter_pdl;
   {
-    bool any_sym = false;
-    for (int m = 0; m < n_meshes; ++m) any_sym = any_sym || mesh_info_host[FOCUSR_MESH_INFO_INTS * m + 1] == 0;
     const long long sell_cap = sell_entries_cap(mesh_point_off_host, mesh_info_host, n_meshes, 0);
     const size_t extra = f32_layout(sell_cap, n_points, n_meshes, nullptr).bytes;
     const size_t base = eigs_ws_layout(n_points, n_meshes, max_rows, B, nullptr, nullptr, 0);
-    if (any_sym && opt.mixed_precision != 0 && workspace_bytes >= base + extra) {
+    if (opt.mixed_precision != 0 && workspace_bytes >= base + extra) {
       ws_main = workspace_bytes - extra;
       char* tail = reinterpret_cast<char*>(workspace) + ws_main;
       tail += (256 - (reinterpret_cast<uintptr_t>(tail) & 255)) & 255;

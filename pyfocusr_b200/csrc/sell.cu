@@ -242,16 +242,16 @@ k_filter_sell(const int2* __restrict__ entries, const int* __restrict__ slice_pt
               const float2* __restrict__ ddi, const int* __restrict__ mesh_off, const void* __restrict__ y_,
               const float* __restrict__ x_prev, const float* __restrict__ r, void* __restrict__ out_, float* __restrict__ y_copy,
               const void* __restrict__ alpha_, const void* __restrict__ gamma_, const double* __restrict__ center, int step,
-              int n_steps, int has_prev, int prefetch, int early) {
+              int n_steps, int has_prev, int prefetch, int early, int rows_per_cta) {
   constexpr int VPT = B / (4 * TPR);
   static_assert(VPT * 4 * TPR == B, "block size must be a multiple of 4*TPR");
   constexpr bool CORR = MODE >= 3;
   constexpr int KEEP = POL & 1, STRM = (POL >> 1) & 1;
   const int mesh = blockIdx.y;
-  const int r0 = mesh_off[mesh] + blockIdx.x * FS_ROWS;
-  const int r1 = min(mesh_off[mesh + 1], r0 + FS_ROWS);
+  const int r0 = mesh_off[mesh] + blockIdx.x * rows_per_cta;
+  const int r1 = min(mesh_off[mesh + 1], r0 + rows_per_cta);
   if (r0 >= r1) return;
-  const int slice0 = mso[mesh] + blockIdx.x * (FS_ROWS / SELL_ROWS);
+  const int slice0 = mso[mesh] + blockIdx.x * (rows_per_cta / SELL_ROWS);
   const unsigned long long pol_keep = KEEP ? policy_evict_last() : 0ull;
   const unsigned long long pol_strm = STRM ? policy_evict_first() : 0ull;
   const float* yf = static_cast<const float*>(y_);
@@ -272,7 +272,7 @@ k_filter_sell(const int2* __restrict__ entries, const int* __restrict__ slice_pt
         if (CORR) prefetch_l2_line(r + (size_t)pr * B + 32 * l);
       }
     }
-    const int ns = min(FS_ROWS / SELL_ROWS, (r1 - r0 + SELL_ROWS - 1) / SELL_ROWS);
+    const int ns = min(rows_per_cta / SELL_ROWS, (r1 - r0 + SELL_ROWS - 1) / SELL_ROWS);
     const int q0 = slice_ptr[slice0], q1 = slice_ptr[slice0 + ns];
     for (int q = q0 + 16 * (int)threadIdx.x; q < q1; q += 16 * FS_THREADS) prefetch_l2_line(entries + q);
   }
@@ -310,7 +310,7 @@ k_filter_sell(const int2* __restrict__ entries, const int* __restrict__ slice_pt
   static_assert(RP % SELL_ROWS == 0, "a CTA pass must cover whole slices");
   const int gs = g / SELL_ROWS, rl = g % SELL_ROWS;
 #pragma unroll 1
-  for (int pass = 0; pass < FS_ROWS / RP; ++pass) {
+  for (int pass = 0; pass < rows_per_cta / RP; ++pass) {
     const int rb = r0 + pass * RP + gs * SELL_ROWS;  // first row of this thread's slice
     if (rb >= r1) break;
     const int row = rb + rl;
@@ -419,16 +419,16 @@ k_filter_sell(const int2* __restrict__ entries, const int* __restrict__ slice_pt
 template <int B, int TPR, int MODE, int MINB>
 static void launch_fs_pol(int pol, dim3 grid, cudaStream_t stream, const SellF32& m, const int* mesh_off, const void* y,
                           const float* x_prev, const float* r, void* out, float* y_copy, const void* alpha, const void* gamma,
-                          const double* center, int step, int n_steps, int has_prev, int prefetch, int pdl) {
+                          const double* center, int step, int n_steps, int has_prev, int prefetch, int pdl, int rpc) {
 #define FB_FS_GO(P)                                                                                                        \
   if (pdl)                                                                                                                 \
     launch_pdl(k_filter_sell<B, TPR, MODE, P, MINB>, grid, dim3(FS_THREADS), stream, m.entries, m.slice_ptr,               \
                m.mesh_slice_off, m.ddi, mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, center, step, n_steps, has_prev, \
-               prefetch, pdl == 2 ? 1 : 0);                                                                                \
+               prefetch, pdl == 2 ? 1 : 0, rpc);                                                                                \
   else                                                                                                                     \
     k_filter_sell<B, TPR, MODE, P, MINB><<<grid, FS_THREADS, 0, stream>>>(m.entries, m.slice_ptr, m.mesh_slice_off, m.ddi,  \
                                                                           mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, \
-                                                                          center, step, n_steps, has_prev, prefetch, 0)
+                                                                          center, step, n_steps, has_prev, prefetch, 0, rpc)
   switch (pol & 3) {
     case 0: FB_FS_GO(0); break;
     case 1: FB_FS_GO(1); break;
@@ -443,19 +443,23 @@ static int launch_fs_b(int mode, const SellF32& m, const int* mesh_off, int n_me
                        const float* x_prev, const float* r, void* out, float* y_copy, const void* alpha, const void* gamma,
                        const double* center, int step, int n_steps, bool has_prev, const FilterTuning& tune,
                        cudaStream_t stream) {
-  dim3 grid(div_up(max_mesh_rows, FS_ROWS), n_meshes);
+  // a CTA normally covers 256 rows (4 slices) in passes of 256 / TPR; a batch with fewer than two waves of such CTAs (a
+  // single mesh: the drop-in Focusr call) gets one pass per CTA so that the whole GPU works on the step
+  int rpc = FS_ROWS;
+  if ((long long)div_up(max_mesh_rows, FS_ROWS) * n_meshes < 2 * 148) rpc = FS_THREADS / TPR;
+  dim3 grid(div_up(max_mesh_rows, rpc), n_meshes);
   constexpr int VPT = B / (4 * TPR);
   constexpr int MB = VPT == 1 ? 8 : (VPT == 2 ? 6 : 3);
   const int hp = has_prev ? 1 : 0, pf = tune.prefetch ? 1 : 0;
 #define FB_FS_MODE(MODE_, MINB_) \
-  launch_fs_pol<B, TPR, MODE_, MINB_>(tune.policy, grid, stream, m, mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, center, step, n_steps, hp, pf, tune.pdl)
+  launch_fs_pol<B, TPR, MODE_, MINB_>(tune.policy, grid, stream, m, mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, center, step, n_steps, hp, pf, tune.pdl, rpc)
   // the occupancy A/B (6 or 5 resident CTAs instead of 8) exists for the two steady-state b = 16 kernels only
   if (B == 16 && (mode == 0 || mode == 3) && (tune.min_blocks == 6 || tune.min_blocks == 5)) {
     constexpr int BB = B == 16 ? B : 16, TT = B == 16 ? TPR : 4;
-    if (mode == 0 && tune.min_blocks == 6) launch_fs_pol<BB, TT, 0, 6>(tune.policy, grid, stream, m, mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, center, step, n_steps, hp, pf, tune.pdl);
-    else if (mode == 0) launch_fs_pol<BB, TT, 0, 5>(tune.policy, grid, stream, m, mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, center, step, n_steps, hp, pf, tune.pdl);
-    else if (tune.min_blocks == 6) launch_fs_pol<BB, TT, 3, 6>(tune.policy, grid, stream, m, mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, center, step, n_steps, hp, pf, tune.pdl);
-    else launch_fs_pol<BB, TT, 3, 5>(tune.policy, grid, stream, m, mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, center, step, n_steps, hp, pf, tune.pdl);
+    if (mode == 0 && tune.min_blocks == 6) launch_fs_pol<BB, TT, 0, 6>(tune.policy, grid, stream, m, mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, center, step, n_steps, hp, pf, tune.pdl, rpc);
+    else if (mode == 0) launch_fs_pol<BB, TT, 0, 5>(tune.policy, grid, stream, m, mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, center, step, n_steps, hp, pf, tune.pdl, rpc);
+    else if (tune.min_blocks == 6) launch_fs_pol<BB, TT, 3, 6>(tune.policy, grid, stream, m, mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, center, step, n_steps, hp, pf, tune.pdl, rpc);
+    else launch_fs_pol<BB, TT, 3, 5>(tune.policy, grid, stream, m, mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, center, step, n_steps, hp, pf, tune.pdl, rpc);
   } else {
     switch (mode) {
       case 0: FB_FS_MODE(0, MB); break;

@@ -39,7 +39,7 @@ def hostsim():
     so = os.path.join(d, "libhostsim.so")
     src_m = max(os.path.getmtime(os.path.join(d, "hostsim.cpp")),
                 *(os.path.getmtime(os.path.join(ROOT, "pyfocusr_b200", "csrc", f))
-                  for f in ("chfsi_driver.hpp", "dense_small.h", "nonsym_host.hpp", "rowops.h", "eigsort_decide.h")))
+                  for f in ("chfsi_driver.hpp", "dense_small.h", "nonsym_host.hpp", "nonsym_small.h", "rowops.h", "eigsort_decide.h")))
     if not os.path.exists(so) or os.path.getmtime(so) < src_m:
         subprocess.check_call(["sh", os.path.join(d, "build.sh")])
     lib = C.CDLL(so)

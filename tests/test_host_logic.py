@@ -167,9 +167,9 @@ def test_driver_mixed_precision_passes(hostsim, shipped_meshes):
     try:
         rc, vals, vecs, ri, offs, sym, rd = _solve(hostsim, ms[:1], 7, 6, 16, tol=1e-12, full=True)
         assert rc == 0 and rd[0, 0] <= 1e-12
-        # the non-symmetric path never takes fp32 passes
+        # the non-symmetric path takes the fp32 forms too (test_driver_nonsymmetric_fp32_passes)
         _solve(hostsim, [shipped_meshes["target_mesh_15k"]], 7, 6, 48)
-        assert hostsim.hostsim_last_lowp_degree() == 0
+        assert hostsim.hostsim_last_lowp_degree() > 0
     finally:
         hostsim.hostsim_set_lowp(0.0)
 
@@ -224,6 +224,25 @@ def test_driver_nonsymmetric_with_retry(hostsim, shipped_meshes):
     rc, vals, vecs, ri, offs, sym = _solve(hostsim, [m], 7, 6, 48)
     assert rc == 0 and not sym and ri[0, 0] == 0 and ri[0, 1] == 11 and ri[0, 2] == 14
     _check(m, vals[0, :11], vecs[:, :11], 6)
+
+
+def test_driver_nonsymmetric_fp32_passes(hostsim, shipped_meshes):
+    """The fp32 filter forms on the reference's own open meshes (non-symmetric adjacency, complex pairs carried in the
+    block): every pass iterates in fp32 (plain blocks, then the correction form), no more steps than in fp64, same parity."""
+    for name in ("source_mesh_15k", "target_mesh_15k"):
+        m = shipped_meshes[name]
+        rc0, _, _, ri0, _, sym = _solve(hostsim, [m], 7, 6, 40)
+        hostsim.hostsim_set_lowp(1.4e-6)
+        try:
+            rc, vals, vecs, ri, offs, sym, rd = _solve(hostsim, [m], 7, 6, 40, full=True)
+            lowp = hostsim.hostsim_last_lowp_degree()
+        finally:
+            hostsim.hostsim_set_lowp(0.0)
+        assert rc0 == 0 and rc == 0 and not sym
+        assert lowp == ri[0, 4] > 0                        # every filter step of the solve ran in fp32
+        assert ri[0, 4] <= 1.05 * ri0[0, 4] and ri[0, 1] == ri0[0, 1] and ri[0, 2] == ri0[0, 2]
+        assert rd[0, 0] <= 1e-10
+        _check(m, vals[0, :ri[0, 1]], vecs[:, :ri[0, 1]], 6)
 
 
 def test_driver_isolated_vertices_symmetric(hostsim):

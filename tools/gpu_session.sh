@@ -79,5 +79,7 @@ fi
 if has latency; then
   timeout 300 python tools/pair_latency.py > gpurun_out/${TAG}_pair_latency.log 2>&1
   echo "latency exit $?"; cat gpurun_out/${TAG}_pair_latency.log
+  timeout 300 python tools/pair_latency.py --fp64 --no-oracle > gpurun_out/${TAG}_pair_latency_fp64.log 2>&1
+  echo "latency (fp64 passes) exit $?"; cat gpurun_out/${TAG}_pair_latency_fp64.log
 fi
 ls -la gpurun_out | tail -30

@@ -7,18 +7,30 @@ import pyfocusr_b200 as pyfocusr
 from pyfocusr_b200.mesh import PolyData
 from oracle import port
 
+if "--fp64" in sys.argv:   # A/B: every filter pass in fp64 (the default lets them iterate in fp32)
+    from pyfocusr_b200._device import DeviceGraph
+    _orig_eigs = DeviceGraph.eigs_smallest
+    def _eigs_fp64(self, *a, **k):
+        k.setdefault("options", dict(mixed_precision=0))
+        return _orig_eigs(self, *a, **k)
+    DeviceGraph.eigs_smallest = _eigs_fp64
+    print("A/B: options.mixed_precision = 0")
+
 z = np.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "meshes.npz"))
 def mesh(n): return PolyData(z[n + "_points"], z[n + "_tris"])
 for tag, (tn, sn), kw in (("configs[0] 15k pair, defaults", ("target_mesh_15k", "source_mesh_15k"), {}),
                           ("configs[1] 5k pair, n_spectral_features=10", ("target_mesh", "source_mesh"), dict(n_spectral_features=10))):
     mt, ms = mesh(tn), mesh(sn)
-    for rep in range(3):
+    reps = []
+    for rep in range(6):
         np.random.seed(0)
         torch.cuda.synchronize(); t0 = time.perf_counter()
         f = pyfocusr.Focusr(mt, ms, icp_register_first=False, list_features_to_calc=[], registration="identity", **kw)
-        t1 = time.perf_counter()
+        torch.cuda.synchronize(); t1 = time.perf_counter()
         f.align_maps()
         torch.cuda.synchronize(); t2 = time.perf_counter()
+        reps.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3))
+    print("   all repetitions, constructor + align_maps [ms]: " + ", ".join("%.1f + %.1f" % r for r in reps), flush=True)
     # where the constructor's time goes (one more run, device synchronised at every boundary)
     from pyfocusr_b200.graph import Graph
     stages, orig = [], Graph.get_graph_spectrum
