@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libfocusr_b200.so")
+# FOCUSR_B200_LIB: an alternative build of the same library (kernel A/B builds of tools/knn_ab.sh); never a fallback
+LIB_PATH = os.environ.get("FOCUSR_B200_LIB") or os.path.join(_HERE, "csrc", "libfocusr_b200.so")
 
 _vp = C.c_void_p
 _i = C.c_int

@@ -17,8 +17,14 @@
 
 namespace fb {
 
-constexpr int PK_TR = 128;  // references per tile
-constexpr int PK_TQ = 128;  // queries per CTA
+#ifndef FB_PK_TR
+#define FB_PK_TR 128
+#endif
+#ifndef FB_PK_TQ
+#define FB_PK_TQ 128
+#endif
+constexpr int PK_TR = FB_PK_TR;  // references per tile (A/B builds: tools/knn_ab.sh)
+constexpr int PK_TQ = FB_PK_TQ;  // queries per CTA
 constexpr int PK_SORT_MAX = 16384;
 constexpr int PK_MAX_DIM = 32;
 

@@ -236,22 +236,25 @@ int sell_build_f32(const int* row_ptr, const int* cols, const double* weights, c
 // MODE 3: z_next = al_j ((L - c) z + r_j) - ga_j z_prev       (correction form; al, ga per column: float tables)
 // MODE 4: x += that (fp64 block), nothing else stored
 // ---------------------------------------------------------------------------------------------------------------
-template <int B, int TPR, int MODE, int POL, int MINB>
+// ROWS: rows per CTA -- 256 (4 slices, 256 / TPR rows per pass), or one pass (256 / TPR rows) for batches that would not
+// fill the GPU otherwise (a single mesh: the drop-in Focusr call).  A compile-time constant: as a kernel argument it cost
+// the correction step 11% (0.221 -> 0.245 ms per launch at 32 registers).
+template <int B, int TPR, int MODE, int POL, int MINB, int ROWS>
 __global__ void __launch_bounds__(FS_THREADS, MINB)
 k_filter_sell(const int2* __restrict__ entries, const int* __restrict__ slice_ptr, const int* __restrict__ mso,
               const float2* __restrict__ ddi, const int* __restrict__ mesh_off, const void* __restrict__ y_,
               const float* __restrict__ x_prev, const float* __restrict__ r, void* __restrict__ out_, float* __restrict__ y_copy,
               const void* __restrict__ alpha_, const void* __restrict__ gamma_, const double* __restrict__ center, int step,
-              int n_steps, int has_prev, int prefetch, int early, int rows_per_cta) {
+              int n_steps, int has_prev, int prefetch, int early) {
   constexpr int VPT = B / (4 * TPR);
   static_assert(VPT * 4 * TPR == B, "block size must be a multiple of 4*TPR");
   constexpr bool CORR = MODE >= 3;
   constexpr int KEEP = POL & 1, STRM = (POL >> 1) & 1;
   const int mesh = blockIdx.y;
-  const int r0 = mesh_off[mesh] + blockIdx.x * rows_per_cta;
-  const int r1 = min(mesh_off[mesh + 1], r0 + rows_per_cta);
+  const int r0 = mesh_off[mesh] + blockIdx.x * ROWS;
+  const int r1 = min(mesh_off[mesh + 1], r0 + ROWS);
   if (r0 >= r1) return;
-  const int slice0 = mso[mesh] + blockIdx.x * (rows_per_cta / SELL_ROWS);
+  const int slice0 = mso[mesh] + blockIdx.x * (ROWS / SELL_ROWS);
   const unsigned long long pol_keep = KEEP ? policy_evict_last() : 0ull;
   const unsigned long long pol_strm = STRM ? policy_evict_first() : 0ull;
   const float* yf = static_cast<const float*>(y_);
@@ -272,7 +275,7 @@ k_filter_sell(const int2* __restrict__ entries, const int* __restrict__ slice_pt
         if (CORR) prefetch_l2_line(r + (size_t)pr * B + 32 * l);
       }
     }
-    const int ns = min(rows_per_cta / SELL_ROWS, (r1 - r0 + SELL_ROWS - 1) / SELL_ROWS);
+    const int ns = min(ROWS / SELL_ROWS, (r1 - r0 + SELL_ROWS - 1) / SELL_ROWS);
     const int q0 = slice_ptr[slice0], q1 = slice_ptr[slice0 + ns];
     for (int q = q0 + 16 * (int)threadIdx.x; q < q1; q += 16 * FS_THREADS) prefetch_l2_line(entries + q);
   }
@@ -310,7 +313,7 @@ k_filter_sell(const int2* __restrict__ entries, const int* __restrict__ slice_pt
   static_assert(RP % SELL_ROWS == 0, "a CTA pass must cover whole slices");
   const int gs = g / SELL_ROWS, rl = g % SELL_ROWS;
 #pragma unroll 1
-  for (int pass = 0; pass < rows_per_cta / RP; ++pass) {
+  for (int pass = 0; pass < ROWS / RP; ++pass) {
     const int rb = r0 + pass * RP + gs * SELL_ROWS;  // first row of this thread's slice
     if (rb >= r1) break;
     const int row = rb + rl;
@@ -420,15 +423,20 @@ template <int B, int TPR, int MODE, int MINB>
 static void launch_fs_pol(int pol, dim3 grid, cudaStream_t stream, const SellF32& m, const int* mesh_off, const void* y,
                           const float* x_prev, const float* r, void* out, float* y_copy, const void* alpha, const void* gamma,
                           const double* center, int step, int n_steps, int has_prev, int prefetch, int pdl, int rpc) {
-#define FB_FS_GO(P)                                                                                                        \
-  if (pdl)                                                                                                                 \
-    launch_pdl(k_filter_sell<B, TPR, MODE, P, MINB>, grid, dim3(FS_THREADS), stream, m.entries, m.slice_ptr,               \
-               m.mesh_slice_off, m.ddi, mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, center, step, n_steps, has_prev, \
-               prefetch, pdl == 2 ? 1 : 0, rpc);                                                                                \
-  else                                                                                                                     \
-    k_filter_sell<B, TPR, MODE, P, MINB><<<grid, FS_THREADS, 0, stream>>>(m.entries, m.slice_ptr, m.mesh_slice_off, m.ddi,  \
-                                                                          mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, \
-                                                                          center, step, n_steps, has_prev, prefetch, 0, rpc)
+#define FB_FS_GO_R(P, R)                                                                                                     \
+  if (pdl)                                                                                                                   \
+    launch_pdl(k_filter_sell<B, TPR, MODE, P, MINB, R>, grid, dim3(FS_THREADS), stream, m.entries, m.slice_ptr,              \
+               m.mesh_slice_off, m.ddi, mesh_off, y, x_prev, r, out, y_copy, alpha, gamma, center, step, n_steps, has_prev,   \
+               prefetch, pdl == 2 ? 1 : 0);                                                                                  \
+  else                                                                                                                       \
+    k_filter_sell<B, TPR, MODE, P, MINB, R><<<grid, FS_THREADS, 0, stream>>>(m.entries, m.slice_ptr, m.mesh_slice_off, m.ddi, \
+                                                                             mesh_off, y, x_prev, r, out, y_copy, alpha,      \
+                                                                             gamma, center, step, n_steps, has_prev, prefetch, 0)
+#define FB_FS_GO(P) FB_FS_GO_R(P, FS_ROWS)
+  if (rpc != FS_ROWS) {  // small batch: one pass per CTA, default cache policy of the streams (no A/B forms of this one)
+    FB_FS_GO_R(3, FS_THREADS / TPR);
+    return;
+  }
   switch (pol & 3) {
     case 0: FB_FS_GO(0); break;
     case 1: FB_FS_GO(1); break;
@@ -436,6 +444,7 @@ static void launch_fs_pol(int pol, dim3 grid, cudaStream_t stream, const SellF32
     default: FB_FS_GO(3); break;
   }
 #undef FB_FS_GO
+#undef FB_FS_GO_R
 }
 
 template <int B, int TPR>

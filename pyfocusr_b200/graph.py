@@ -96,7 +96,11 @@ class Graph(object):
         self.mean_pts_scale_range = np.mean(self.pts_scale_range)
         self.normed_points = (self.points - np.min(self.points, axis=0)) / self.mean_pts_scale_range
 
-        self.adjacency_matrix = sparse.lil_matrix((self.n_points, self.n_points))
+        # graph.py:82 creates an empty n x n lil_matrix here; that is 2 n Python lists (30 000 container objects for a 15k
+        # mesh), enough to trigger a full garbage-collection pass every other construction (a bimodal 43 / 90 ms for the
+        # Focusr constructor on the shipped 15k pair).  An empty CSR matrix is the same placeholder without the objects;
+        # get_weighted_adjacency_matrix replaces it either way.
+        self.adjacency_matrix = sparse.csr_matrix((self.n_points, self.n_points))
         self.degree_matrix = None
         self.degree_matrix_inv = None
         self.laplacian_matrix = None
