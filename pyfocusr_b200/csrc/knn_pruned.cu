@@ -17,11 +17,17 @@
 
 namespace fb {
 
+// Tile sizes, measured at bench shape (128 segments of 15 212 x 15 212, d = 3; tools/knn_ab.sh, gpurun_out/r2g_knn_ab.log),
+// k = 1 / k = 3 in ms, distance evaluations per query in brackets:
+//   references per tile x queries per CTA   128 x 128: 2.76 / 4.33 (359 / 440)     64 x 128: 2.59 / 3.90 (209 / 261)
+//   64 x 64: 2.12 / 3.21 (189 / 244)   128 x 64: 2.39 / 3.79   32 x 64: 2.50 / 3.48 (109 / 145)   256 x 128: 3.63 / 5.65
+// Smaller reference tiles prune more but cost a box test and a barrier each; fewer queries per CTA shrink the union of
+// tiles the CTA has to stage.
 #ifndef FB_PK_TR
-#define FB_PK_TR 128
+#define FB_PK_TR 64
 #endif
 #ifndef FB_PK_TQ
-#define FB_PK_TQ 128
+#define FB_PK_TQ 64
 #endif
 constexpr int PK_TR = FB_PK_TR;  // references per tile (A/B builds: tools/knn_ab.sh)
 constexpr int PK_TQ = FB_PK_TQ;  // queries per CTA

@@ -4,7 +4,7 @@
 # each on the GPU (bash tools/knn_ab.sh run).  Results are bit-identical by construction (exact search, same tie rule).
 set -u
 cd "$(dirname "$0")/.."
-VARIANTS="128:128 64:128 64:64 128:64 32:64 256:128"
+VARIANTS=${VARIANTS:-"128:128 64:128 64:64 128:64 32:64 256:128"}
 CS=pyfocusr_b200/csrc
 if [ "${1:-run}" = build ]; then
   mkdir -p $CS/ab
