@@ -374,6 +374,10 @@ def run_ours(a):
             secondary["nonsym_batch"] = nonsym_batch_leg()
         except Exception as exc:  # a reporting extra must never cost the bench line
             secondary["nonsym_batch"] = {"error": repr(exc)}
+        try:
+            secondary["single_pair_ms"] = single_pair_leg()
+        except Exception as exc:
+            secondary["single_pair_ms"] = {"error": repr(exc)}
     if world == 1 and not a.no_cpu_baseline:
         secondary["widened_rows_ms"] = widened_rows_timing(a.nu)
     cpu = None
@@ -588,6 +592,42 @@ def nonsym_batch_leg(n_pairs=32, reps=2):
             "k_final": [int(info["k_final"][0]), int(info["k_final"][n_pairs])],
             "pairs_found": [int(info["n_found"][0]), int(info["n_found"][n_pairs])],
             "outer_iterations": int(info["outer_iterations"].max()), "filter_degree": int(info["filter_degree"].max())}
+
+
+def single_pair_leg(reps=5):
+    """BASELINE.json configs[0] and configs[1] through the drop-in API, outside the timed region (N = 1 only): the
+    reference's own shipped meshes (tests/golden/meshes.npz), `Focusr(target, source, ...)` + `align_maps()` with ICP off
+    and CPD = identity, wall-clock with the device synchronised, median of `reps` after one
+    warm-up call.  Latency of ONE pair, not throughput: the batched numbers are the headline."""
+    import torch
+
+    import pyfocusr_b200 as pyfocusr
+    from pyfocusr_b200.mesh import PolyData
+
+    z = np.load(os.path.join(ROOT, "tests", "golden", "meshes.npz"))
+    out = {}
+    for tag, (tn, sn), kw in (("configs0_15k_pair_defaults", ("target_mesh_15k", "source_mesh_15k"), {}),
+                              ("configs1_5k_pair_n_spectral_features_10", ("target_mesh", "source_mesh"), dict(n_spectral_features=10))):
+        mt, ms = PolyData(z[tn + "_points"], z[tn + "_tris"]), PolyData(z[sn + "_points"], z[sn + "_tris"])
+        times = []
+        for rep in range(reps + 1):
+            np.random.seed(0)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            f = pyfocusr.Focusr(mt, ms, icp_register_first=False, list_features_to_calc=[], registration="identity", **kw)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            f.align_maps()
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            if rep:
+                times.append(((t1 - t0) * 1e3, (t2 - t1) * 1e3))
+        ctor, align = np.median([t[0] for t in times]), np.median([t[1] for t in times])
+        out[tag] = {"constructor_ms": float(ctor), "align_maps_ms": float(align), "total_ms": float(ctor + align),
+                    "vertices": [int(mt.points.shape[0]), int(ms.points.shape[0])],
+                    "eigenpairs_kept": [int(f.graph_target.eig_vals.size), int(f.graph_source.eig_vals.size)],
+                    "correspondences": int(np.asarray(f.corresponding_target_idx_for_each_source_pt).size)}
+    return out
 
 
 def widened_rows_timing(nu):

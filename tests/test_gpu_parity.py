@@ -253,6 +253,32 @@ def test_eigs_mixed_precision_passes(torch, shipped_meshes, synth, block):
     assert sha(x1b.cpu().numpy()) == sha(x1)
 
 
+def test_eigs_nonsymmetric_fp32_passes_and_device_rayleigh_ritz(torch, shipped_meshes):
+    """The reference's own open meshes (structurally non-symmetric adjacency) as one batch: the fp32 filter forms against
+    options.mixed_precision = 0, and the device form of the general b x b Rayleigh-Ritz step (k_rr_nonsym) against the
+    host form (options.nonsym_device = 0): same retry contract, same eigenvalues, same parity with scipy."""
+    from pyfocusr_b200._device import DeviceGraph
+
+    ms = [shipped_meshes["target_mesh_15k"], shipped_meshes["source_mesh_15k"]]
+    g = DeviceGraph([m.points for m in ms], [m.tris for m in ms])
+    assert np.all(g.mesh_info_host[:, 1] > 0)                       # one-way entries: the non-symmetric path
+    runs = {}
+    for tag, opt in (("default", None), ("fp64", dict(mixed_precision=0)), ("host_rr", dict(nonsym_device=0))):
+        vals, vecs, info = g.eigs_smallest(k=7, n_k_needed=6, options=opt)
+        runs[tag] = (vals.cpu().numpy(), vecs.cpu().numpy(), info)
+        assert info["status"].tolist() == [0, 0] and info["max_residual"].max() <= 1e-10
+        assert info["k_final"].tolist() == [7, 14] and info["n_found"].tolist() == [6, 11]
+    v, x, i = runs["default"]
+    assert np.all(i["fp32_filter_degree"] == i["filter_degree"]) and np.all(runs["fp64"][2]["fp32_filter_degree"] == 0)
+    assert i["filter_degree"].max() <= 1.1 * runs["fp64"][2]["filter_degree"].max()
+    for tag in ("fp64", "host_rr"):
+        for k, n in enumerate((6, 11)):
+            assert np.max(np.abs(v[k, :n] - runs[tag][0][k, :n]) / runs[tag][0][k, :n]) <= 1e-8, tag
+    for k, (m, n) in enumerate(zip(ms, (6, 11))):
+        o0, o1 = g.mesh_off_host[k], g.mesh_off_host[k + 1]
+        check_eigs(v[k, :n], x[o0:o1, :n], m, 6)
+
+
 def test_eigs_icosphere_multiplets(torch, synth):
     """Exact 3/5/7-fold multiplets: k=11 cuts the l=3 multiplet."""
     from oracle import port
