@@ -931,8 +931,19 @@ int launch_filter_persist(bool corr, int b, const PersistArgs& a, cudaStream_t s
 // row of A backwards and splices the diagonal in at its sorted position, which reproduces that bit for bit.  Passes are
 // chained by programmatic dependent launch: the CTA prefetches its slice of the matrix, which no pass writes, into L2
 // before it waits for the previous pass.
+// Occupancy of the smoothing pass (A/B: tools/smooth_ab.sh, gpurun_out/r2s_smooth_ab.log; 300 passes over 128 meshes):
+// compiled for 4 / 6 / 8 resident CTAs of 256 threads per SM (64 / 40 / 32 registers): 20.50 / 17.47 / 16.67 ms; at full
+// occupancy (32 registers) with 512 / 256 / 128 / 96 / 64 threads per CTA: 17.49 / 16.66 / 16.01 / 16.00 / 16.07 ms (the
+// round started at 17.15 ms: 40 registers, 256 threads).  The pass is latency-bound (header comment), so every resident
+// warp counts, and small CTAs leave fewer warp slots idle while a CTA drains.
+#ifndef FB_SMOOTH_THREADS
+#define FB_SMOOTH_THREADS 128
+#endif
+#ifndef FB_SMOOTH_MINB
+#define FB_SMOOTH_MINB (2048 / FB_SMOOTH_THREADS)
+#endif
 template <int C>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(FB_SMOOTH_THREADS, FB_SMOOTH_MINB)
 k_mean_filter(const int* __restrict__ row_ptr, const int* __restrict__ cols, const double* __restrict__ weights,
               const double* __restrict__ degree, int row_begin, int row_end, const double* __restrict__ x,
               double* __restrict__ out, int n_cols_rt) {
@@ -1026,7 +1037,7 @@ int focusr_mean_filter(const int* row_ptr, const int* cols, const double* weight
   FB_REQUIRE(row_end > row_begin && n_cols >= 1 && n_cols <= 8 && iterations >= 0,
              "mean_filter: need rows, 1 <= n_cols <= 8, iterations >= 0");
   const int n = row_end - row_begin;
-  const int T = 256;
+  const int T = FB_SMOOTH_THREADS;
   if (iterations == 0) {
     const long long b = (long long)row_begin * n_cols, e = (long long)row_end * n_cols;
     k_copy_rows<<<div_up(e - b, T), T, 0, stream>>>(values_in, values_out, b, e);
