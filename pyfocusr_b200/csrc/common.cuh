@@ -65,6 +65,13 @@ struct Carver {
 };
 
 inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+// SMs of the current device (148 on B200): asked per call, never cached process-wide (a process may use several GPUs)
+inline int sm_count() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+    return 148;
+  return sms;
+}
 
 // number of launches issued by this library since load (bench.py reports it as gpu_launches); atomic because
 // independent calls may come from several host threads (one stream each), as the batched CPD does

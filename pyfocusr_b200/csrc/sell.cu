@@ -455,7 +455,7 @@ static int launch_fs_b(int mode, const SellF32& m, const int* mesh_off, int n_me
   // a CTA normally covers 256 rows (4 slices) in passes of 256 / TPR; a batch with fewer than two waves of such CTAs (a
   // single mesh: the drop-in Focusr call) gets one pass per CTA so that the whole GPU works on the step
   int rpc = FS_ROWS;
-  if ((long long)div_up(max_mesh_rows, FS_ROWS) * n_meshes < 2 * 148) rpc = FS_THREADS / TPR;
+  if ((long long)div_up(max_mesh_rows, FS_ROWS) * n_meshes < 2 * sm_count()) rpc = FS_THREADS / TPR;
   dim3 grid(div_up(max_mesh_rows, rpc), n_meshes);
   constexpr int VPT = B / (4 * TPR);
   constexpr int MB = VPT == 1 ? 8 : (VPT == 2 ? 6 : 3);

@@ -119,7 +119,7 @@ static int launch_spmm_b(int mode, const SpmmGraph& g, const double* y, const do
   // rows = 60 such CTAs on 148 SMs, 20 us per step of 16 MB) gets one pass per CTA instead, so that the whole GPU works
   // on the step.  Same arithmetic per row either way.
   int rpb = SPMM_ROWS_PER_BLOCK;
-  if ((long long)div_up(g.max_mesh_rows, rpb) * g.n_meshes < 2 * 148) rpb = SPMM_THREADS / TPR;
+  if ((long long)div_up(g.max_mesh_rows, rpb) * g.n_meshes < 2 * sm_count()) rpb = SPMM_THREADS / TPR;
   dim3 grid(div_up(g.max_mesh_rows, rpb), g.n_meshes);
   if (mode == 0)
     k_spmm<B, TPR, 0><<<grid, SPMM_THREADS, 0, stream>>>(g.row_ptr, g.cols, g.weights, g.degree, g.degree_inv,
