@@ -410,6 +410,71 @@ def test_device_lsap_is_scipys_algorithm_including_ties(hostsim):
     assert hostsim.hostsim_lsap(bad, 3, np.zeros(3, dtype=np.int32)) == -1
 
 
+def test_lsap_cluster_scheme_is_scipys_scan():
+    """The bookkeeping csrc/lsap.cu uses in place of scipy's `remaining` array and serial scan, restated in numpy: every
+    column keeps its POSITION in scipy's scan order (removing position p moves the last position to p), the minimum is
+    taken by (value, tie key) with key = 2^30 + position for unassigned columns (the last one in scan order wins) and
+    2^30 - 1 - position for assigned ones (the first one wins), and the duals are updated per visited column.  Must give
+    scipy's assignment on matrices full of ties, square and rectangular."""
+    from scipy.optimize import linear_sum_assignment
+
+    def scheme(cost):
+        nr, nc = cost.shape
+        u, v = np.zeros(nr), np.zeros(nc)
+        col4row, r4c, path = -np.ones(nr, int), -np.ones(nc, int), -np.ones(nc, int)
+        for cur in range(nr):
+            spc, sc, pos = np.full(nc, np.inf), np.zeros(nc, bool), nc - 1 - np.arange(nc)
+            min_val, i, nrem, sink, prev_last, prev_index = 0.0, cur, nc, -1, -1, -1
+            while sink < 0:
+                best = None
+                for j in range(nc):            # "every thread updates its columns"
+                    if sc[j]:
+                        continue
+                    if pos[j] == prev_last:
+                        pos[j] = prev_index
+                    r = ((min_val + cost[i, j]) - u[i]) - v[j]
+                    if r < spc[j]:
+                        spc[j], path[j] = r, i
+                    key = (0x40000000 + pos[j]) if r4c[j] < 0 else (0x3FFFFFFF - pos[j])
+                    if best is None or spc[j] < best[0] or (spc[j] == best[0] and key > best[1]):
+                        best = (spc[j], key, j)
+                min_val, key, js = best
+                index = key - 0x40000000 if key >= 0x40000000 else 0x3FFFFFFF - key
+                sc[js] = True
+                prev_last, prev_index, nrem = nrem - 1, index, nrem - 1
+                if r4c[js] < 0:
+                    sink = js
+                else:
+                    i = r4c[js]
+            u[cur] += min_val
+            for j in np.nonzero(sc)[0]:
+                d = min_val - spc[j]
+                if r4c[j] >= 0:
+                    u[r4c[j]] += d
+                v[j] -= d
+            j = sink
+            while True:
+                ii = path[j]
+                r4c[j] = ii
+                col4row[ii], j = j, col4row[ii]
+                if ii == cur:
+                    break
+        return col4row
+
+    rng = np.random.RandomState(5)
+    for t in range(60):
+        n = rng.randint(2, 24)
+        m = n + rng.randint(0, 4)
+        if t % 3 == 0:
+            c = rng.rand(n, m)
+        elif t % 3 == 1:
+            c = rng.randint(0, 3, (n, m)).astype(float)
+        else:
+            p = rng.randint(0, 3, (m, 2)).astype(float)
+            c = np.sqrt(((p[:n, None] - p[None]) ** 2).sum(-1))
+        assert np.array_equal(scheme(c), linear_sum_assignment(c)[1]), (t, n, m)
+
+
 def test_device_eigsort_decisions_equal_the_host_classes(hostsim):
     """eigsort_decide_pair (the kernel body of focusr_eigsort_decide) against the drop-in classes' host code
     (c_lambda_matrix + decide_matches + moves_from_matches, i.e. the reference's eigsort.py:66-122, 142-160) and the
