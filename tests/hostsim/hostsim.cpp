@@ -22,6 +22,30 @@ double g_lowp_floor = 0.0;   // hostsim_set_lowp: SolveParams::lowp_floor of the
 int g_last_lowp_degree = 0;  // lowp_degree of mesh 0 of the last solve
 int g_nonsym_small = 1;      // hostsim_set_nonsym_small: 1 = the device algorithm (nonsym_small.h, sequential Par), 0 = nonsym_host.hpp
 
+// A second sequential `Par`: the indices of every parallel loop in DESCENDING order.  A loop body that reads what another
+// index of the same loop writes (a race on the GPU) gives different results under the two orders.
+struct RevPar {
+  template <class F>
+  void for_n(int n, F f) const {
+    for (int i = n - 1; i >= 0; --i) f(i);
+  }
+  void sync() const {}
+  double sum(double v) const { return v; }
+  int lane() const { return 0; }
+};
+
+template <class Par>
+int rr_nonsym_small_par(const double* g, const double* h, int b, double cut, double* w, double* theta, int* n_low) {
+  std::vector<double> gh((size_t)2 * b * b), rs((size_t)b * b);
+  std::memcpy(gh.data(), g, sizeof(double) * b * b);
+  std::memcpy(gh.data() + (size_t)b * b, h, sizeof(double) * b * b);
+  std::vector<fb::Cd> hc((size_t)b * b), qc((size_t)b * b);
+  std::vector<unsigned char> scratch(fb::nonsym_small_scratch_bytes(b) + 16);
+  Par par;
+  return fb::rr_nonsym_small(gh.data(), gh.data() + (size_t)b * b, hc.data(), qc.data(), rs.data(), b, cut, w, theta, n_low,
+                             scratch.data(), par);
+}
+
 int rr_nonsym_small_host(const double* g, const double* h, int b, double cut, double* w, double* theta, int* n_low) {
   std::vector<double> gh((size_t)2 * b * b), rs((size_t)b * b);
   std::memcpy(gh.data(), g, sizeof(double) * b * b);
@@ -339,6 +363,7 @@ void hostsim_set_nonsym_small(int on) { g_nonsym_small = on; }
 
 // the non-symmetric Rayleigh-Ritz step in its device form (nonsym_small.h) and in its host form (chfsi_driver.hpp)
 int hostsim_rr_nonsym(int device_form, const double* g, const double* h, int b, double cut, double* w, double* theta, int* n_low) {
+  if (device_form == 2) return rr_nonsym_small_par<RevPar>(g, h, b, cut, w, theta, n_low);   // loops in reverse order
   if (device_form) return rr_nonsym_small_host(g, h, b, cut, w, theta, n_low);
   std::vector<double> gg(g, g + (size_t)b * b), hh(h, h + (size_t)b * b);
   return fb::rr_nonsym_host(gg.data(), hh.data(), b, cut, w, theta, n_low);

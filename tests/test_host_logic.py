@@ -81,6 +81,36 @@ def test_rr_nonsym_device_form_matches_numpy_and_the_host_form(hostsim, b):
     assert np.allclose(np.sort(th), np.sort(th0), rtol=1e-8, atol=1e-10)
 
 
+@pytest.mark.parametrize("b", [8, 24, 40, 64])
+def test_rr_nonsym_device_form_has_no_loop_order_dependence(hostsim, b):
+    """Race check of csrc/nonsym_small.h without a GPU: every `par.for_n` of the device algorithm run once in ascending
+    and once in descending index order.  A body that read what another index of the same loop writes -- a data race in
+    the CUDA kernel, where the indices are threads -- would change the result; only the accumulation order of the few
+    reductions may differ (rounding)."""
+    rng = np.random.RandomState(100 + b)
+    n = 5 * b
+    x = rng.randn(n, b)
+    lop = np.diag(np.sort(rng.rand(n)) * 2.0) + 1e-3 * rng.randn(n, n)
+    for i in range(0, 4, 2):
+        lop[n - 2 - i, n - 1 - i], lop[n - 1 - i, n - 2 - i] = 0.25, -0.25
+    g, h = np.ascontiguousarray(x.T @ x), np.ascontiguousarray(x.T @ (lop @ x))
+    res = []
+    for form in (1, 2):
+        w, th, nl = np.zeros((b, b)), np.zeros(b), np.zeros(1, np.int32)
+        assert hostsim.hostsim_rr_nonsym(form, g, h, b, 1.2, w, th, nl) == 0
+        res.append((w, th, int(nl[0])))
+    (w1, t1, n1), (w2, t2, n2) = res
+    assert n1 == n2 and np.allclose(t1, t2, rtol=1e-10, atol=1e-12)
+    for j in range(b):   # same columns up to sign and rounding; the (Re, Im) columns of a complex pair up to the phase of
+        # its eigenvector, i.e. as the plane they span
+        same = np.nonzero(np.abs(t2 - t1[j]) <= 1e-9 * max(1.0, abs(t1[j])))[0]
+        basis = w2[:, same]
+        coef = np.linalg.lstsq(basis, w1[:, j], rcond=None)[0]
+        assert np.linalg.norm(basis @ coef - w1[:, j]) <= 1e-7 * np.linalg.norm(w1[:, j]), (j, same.tolist())
+        if j < n1:
+            assert same.size == 1
+
+
 def test_edge_weight_matches_numpy(hostsim):
     rng = np.random.RandomState(0)
     for _ in range(200):
