@@ -51,6 +51,7 @@ def hostsim():
     lib.hostsim_set_lowp.argtypes = [C.c_double]
     lib.hostsim_set_lowp.restype = None
     lib.hostsim_rr_sym.argtypes = [dp, dp, dp, dp, C.c_int]
+    lib.hostsim_rr_sym_rev.argtypes = [dp, dp, dp, dp, C.c_int]
     lib.hostsim_eig_general.argtypes = [dp, C.c_int, dp, dp]
     lib.hostsim_rr_nonsym.argtypes = [C.c_int, dp, dp, C.c_int, C.c_double, dp, dp, ip]
     lib.hostsim_set_nonsym_small.argtypes = [C.c_int]

@@ -377,6 +377,14 @@ int hostsim_rr_sym(double* g, double* h, double* w, double* theta, int b) {
   return fb::rayleigh_ritz_sym(g, h, y.data(), w, theta, rank.data(), rot.data(), pq.data(), b, par);
 }
 
+// the same with every parallel loop in descending index order (race check, see RevPar)
+int hostsim_rr_sym_rev(double* g, double* h, double* w, double* theta, int b) {
+  std::vector<double> y((size_t)b * b), rot(b + 2);
+  std::vector<int> rank(b), pq(b + 2);
+  RevPar par;
+  return fb::rayleigh_ritz_sym(g, h, y.data(), w, theta, rank.data(), rot.data(), pq.data(), b, par);
+}
+
 // a (n x n, symmetric) is overwritten by the eigenvectors (columns); evals unsorted
 int hostsim_eig_sym(double* a, double* evals, int n) { return fb::eig_sym_host(a, evals, n); }
 

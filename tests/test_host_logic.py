@@ -32,6 +32,26 @@ def test_rayleigh_ritz_sym_matches_lapack(hostsim, b):
     assert np.all(np.diff(th) >= 0)
 
 
+@pytest.mark.parametrize("b", [8, 16, 32, 48, 96])
+def test_rayleigh_ritz_sym_has_no_loop_order_dependence(hostsim, b):
+    """The same race check for the symmetric step (csrc/dense_small.h: Cholesky, congruence, round-robin Jacobi)."""
+    rng = np.random.RandomState(7 * b)
+    x = rng.randn(6 * b, b)
+    d = np.sort(rng.rand(6 * b)) * 2.0
+    g, h = x.T @ x, x.T @ (d[:, None] * x)
+    out = []
+    for fn in (hostsim.hostsim_rr_sym, hostsim.hostsim_rr_sym_rev):
+        gg, hh, w, th = g.copy(), h.copy(), np.zeros((b, b)), np.zeros(b)   # both are overwritten
+        rc = fn(gg, hh, w, th, b)
+        assert rc >> 8 == 0 and (rc & 0xFF) < 30          # no clamped pivot, Jacobi converged
+        out.append((w, th))
+    (w1, t1), (w2, t2) = out
+    assert np.allclose(t1, t2, rtol=1e-11, atol=1e-13)
+    for j in range(b):
+        c = abs(w1[:, j] @ g @ w2[:, j]) / np.sqrt((w1[:, j] @ g @ w1[:, j]) * (w2[:, j] @ g @ w2[:, j]))
+        assert abs(c - 1.0) <= 1e-8, j
+
+
 @pytest.mark.parametrize("n", [2, 7, 32, 64])
 def test_eig_general_matches_numpy(hostsim, n):
     rng = np.random.RandomState(n)
